@@ -1,0 +1,272 @@
+/*
+ * sakura_b200.h -- C ABI of libsakura_b200.so
+ *
+ * B200-native (sm_100a CUDA) drop-in for ONE hot path of libsakura 5.3: masked
+ * least-squares baseline fitting of single-dish spectra with iterative
+ * sigma-clipping, plus the residual statistics it depends on.
+ *
+ * Every `sakura_*` symbol below keeps the name, argument order, argument
+ * meaning, alignment contract and status codes of the reference declaration it
+ * replaces (cited as `sakura.h:<line>` = libsakura/src/libsakura/sakura.h and
+ * `baseline.cc:<line>` etc. of tnakazato/sakura).  A caller written against
+ * <libsakura/sakura.h> for this path links against this library unchanged.
+ * The `...Batch` entry points are new: many spectra per call, row r of every
+ * array belonging to spectrum r; results equal a loop over the single-row call.
+ *
+ * Pointers are HOST pointers unless the function name ends in `Device`.
+ * No torch / C++ types cross this boundary.  The header is valid C99.
+ */
+#ifndef SAKURA_B200_H_
+#define SAKURA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+#include <stdbool.h>
+#include <sys/types.h>
+
+#ifdef __cplusplus
+extern "C" {
+# define SAKURA_B200_NOEXCEPT noexcept
+#else
+# define SAKURA_B200_NOEXCEPT
+#endif
+
+/* ---- status codes ------------------------------------------------------ */
+
+/** Replaces sakura_Status, sakura.h:64-82. */
+typedef enum {
+	sakura_Status_kOK = 0,
+	sakura_Status_kNG = 1,
+	sakura_Status_kInvalidArgument = 2,
+	sakura_Status_kNoMemory = 3,
+	sakura_Status_kUnknownError = 99
+} sakura_Status;
+
+/** Replaces sakura_LSQFitStatus, sakura.h:1570-1586. */
+typedef enum {
+	sakura_LSQFitStatus_kOK = 0,
+	sakura_LSQFitStatus_kNG = 1,
+	sakura_LSQFitStatus_kNotEnoughData = 2,
+	sakura_LSQFitStatus_kNumElements
+} sakura_LSQFitStatus;
+
+/** Replaces sakura_LSQFitType, sakura.h:1591-1603. */
+typedef enum {
+	sakura_LSQFitType_kPolynomial,
+	sakura_LSQFitType_kChebyshev,
+	sakura_LSQFitType_kNumElements
+} sakura_LSQFitType;
+
+/** Replaces sakura_StatisticsResultFloat, sakura.h:208-237 (48 bytes). */
+typedef struct {
+	size_t count;
+	double sum;
+	double square_sum;
+	float min;
+	float max;
+	ssize_t index_of_min;
+	ssize_t index_of_max;
+} sakura_StatisticsResultFloat;
+
+/** Opaque, as in sakura.h:1608. One context per thread (sakura.h:1613-1615). */
+struct sakura_LSQFitContextFloat;
+
+/* ---- lifecycle, allocator hooks, alignment ----------------------------- */
+
+typedef void *(*sakura_UserAllocator)(size_t size); /* sakura.h:98 */
+typedef void (*sakura_UserDeallocator)(void *pointer); /* sakura.h:111 */
+
+/** Replaces sakura_Initialize, sakura.h:125 (gen_util.cc:95-104).
+ *  Host-side context memory goes through the hooks; device memory does not. */
+sakura_Status sakura_Initialize(sakura_UserAllocator allocator,
+		sakura_UserDeallocator deallocator) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_CleanUp, sakura.h:137. Releases cached device buffers. */
+void sakura_CleanUp(void) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_GetAlignment, sakura.h:160. Returns 32 (the AVX build's value,
+ *  localdef.h:75-86) so that callers' buffers are laid out identically. */
+size_t sakura_GetAlignment(void) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_IsAligned, sakura.h:151. */
+bool sakura_IsAligned(void const *ptr) SAKURA_B200_NOEXCEPT;
+/** Replace sakura_AlignAny / AlignFloat / AlignDouble, sakura.h:170-197. */
+void *sakura_AlignAny(size_t size_of_arena, void *arena, size_t size_required)
+		SAKURA_B200_NOEXCEPT;
+float *sakura_AlignFloat(size_t elements_in_arena, float *arena, size_t elements_required)
+		SAKURA_B200_NOEXCEPT;
+double *sakura_AlignDouble(size_t elements_in_arena, double *arena,
+		size_t elements_required) SAKURA_B200_NOEXCEPT;
+
+/* ---- statistics --------------------------------------------------------- */
+
+/** Replaces sakura_ComputeStatisticsFloat, sakura.h:254 (statistics.cc:871). */
+sakura_Status sakura_ComputeStatisticsFloat(size_t num_data, float const data[],
+		bool const is_valid[], sakura_StatisticsResultFloat *result) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_ComputeAccurateStatisticsFloat, sakura.h:264 (statistics.cc:879). */
+sakura_Status sakura_ComputeAccurateStatisticsFloat(size_t num_data, float const data[],
+		bool const is_valid[], sakura_StatisticsResultFloat *result) SAKURA_B200_NOEXCEPT;
+/** NEW. Row r: data + r*data_stride, is_valid + r*mask_stride (strides in elements). */
+sakura_Status sakura_ComputeStatisticsFloatBatch(size_t num_spectra, size_t num_data,
+		float const data[], size_t data_stride, bool const is_valid[], size_t mask_stride,
+		sakura_StatisticsResultFloat result[/*num_spectra*/]) SAKURA_B200_NOEXCEPT;
+/** NEW. Same with device pointers; asynchronous on `cuda_stream` (a cudaStream_t, may be 0). */
+sakura_Status sakura_ComputeStatisticsFloatBatchDevice(size_t num_spectra, size_t num_data,
+		float const d_data[], size_t data_stride, bool const d_is_valid[], size_t mask_stride,
+		sakura_StatisticsResultFloat d_result[/*num_spectra*/], void *cuda_stream)
+				SAKURA_B200_NOEXCEPT;
+
+/* ---- normal-equation building blocks ------------------------------------ */
+
+/** Replaces sakura_GetLSQCoefficientsDouble, sakura.h:1403 (numeric_operation.cc:867). */
+sakura_Status sakura_GetLSQCoefficientsDouble(size_t const num_data, float const data[],
+		bool const mask[], size_t const num_model_bases, double const basis_data[],
+		size_t const num_lsq_bases, size_t const use_bases_idx[], double lsq_matrix[],
+		double lsq_vector[]) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_UpdateLSQCoefficientsDouble, sakura.h:1482 (numeric_operation.cc:905). */
+sakura_Status sakura_UpdateLSQCoefficientsDouble(size_t const num_data, float const data[],
+		bool const mask[], size_t const num_exclude_indices, size_t const exclude_indices[],
+		size_t const num_model_bases, double const basis_data[], size_t const num_lsq_bases,
+		size_t const use_bases_idx[], double lsq_matrix[], double lsq_vector[])
+				SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_SolveSimultaneousEquationsByLUDouble, sakura.h:1520
+ *  (numeric_operation.cc:948): full-pivot LU, rank-revealing, never fails. */
+sakura_Status sakura_SolveSimultaneousEquationsByLUDouble(size_t num_equations,
+		double const in_matrix[], double const in_vector[], double out[])
+				SAKURA_B200_NOEXCEPT;
+
+/* ---- fit contexts --------------------------------------------------------- */
+
+/** Replaces sakura_CreateLSQFitContextPolynomialFloat, sakura.h:1635 (baseline.cc:1515). */
+sakura_Status sakura_CreateLSQFitContextPolynomialFloat(sakura_LSQFitType const lsqfit_type,
+		uint16_t order, size_t num_data, struct sakura_LSQFitContextFloat **context)
+				SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_CreateLSQFitContextCubicSplineFloat, sakura.h:1660 (baseline.cc:1555). */
+sakura_Status sakura_CreateLSQFitContextCubicSplineFloat(uint16_t npiece, size_t num_data,
+		struct sakura_LSQFitContextFloat **context) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_CreateLSQFitContextSinusoidFloat, sakura.h:1686 (baseline.cc:1591). */
+sakura_Status sakura_CreateLSQFitContextSinusoidFloat(uint16_t nwave, size_t num_data,
+		struct sakura_LSQFitContextFloat **context) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_DestroyLSQFitContextFloat, sakura.h:1701 (baseline.cc:1627). */
+sakura_Status sakura_DestroyLSQFitContextFloat(struct sakura_LSQFitContextFloat *context)
+		SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_GetNumberOfCoefficientsFloat, sakura.h:2084 (baseline.cc:1646). */
+sakura_Status sakura_GetNumberOfCoefficientsFloat(
+		struct sakura_LSQFitContextFloat const *context, uint16_t order, size_t *num_coeff)
+				SAKURA_B200_NOEXCEPT;
+
+/* ---- single-spectrum fits (reference signatures) -------------------------- */
+
+/** Replaces sakura_LSQFitPolynomialFloat, sakura.h:1773-1781 (baseline.cc:1687). */
+sakura_Status sakura_LSQFitPolynomialFloat(struct sakura_LSQFitContextFloat const *context,
+		uint16_t order, size_t num_data, float const data[], bool const mask[],
+		float clip_threshold_sigma, uint16_t num_fitting_max, size_t num_coeff,
+		double coeff[], float best_fit[], float residual[], bool final_mask[], float *rms,
+		sakura_LSQFitStatus *lsqfit_status) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_LSQFitCubicSplineFloat, sakura.h:1859-1868 (baseline.cc:1761). */
+sakura_Status sakura_LSQFitCubicSplineFloat(struct sakura_LSQFitContextFloat const *context,
+		size_t num_pieces, size_t num_data, float const data[], bool const mask[],
+		float clip_threshold_sigma, uint16_t num_fitting_max, double coeff[][4],
+		float best_fit[], float residual[], bool final_mask[], float *rms, size_t boundary[],
+		sakura_LSQFitStatus *lsqfit_status) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_LSQFitSinusoidFloat, sakura.h:1947-1955 (baseline.cc:1835). */
+sakura_Status sakura_LSQFitSinusoidFloat(struct sakura_LSQFitContextFloat const *context,
+		size_t num_nwave, size_t const nwave[], size_t num_data, float const data[],
+		bool const mask[], float clip_threshold_sigma, uint16_t num_fitting_max,
+		size_t num_coeff, double coeff[], float best_fit[], float residual[],
+		bool final_mask[], float *rms, sakura_LSQFitStatus *lsqfit_status)
+				SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_SubtractPolynomialFloat, sakura.h:1981 (baseline.cc:1902). */
+sakura_Status sakura_SubtractPolynomialFloat(struct sakura_LSQFitContextFloat const *context,
+		size_t num_data, float const data[], size_t num_coeff, double const coeff[],
+		float out[]) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_SubtractCubicSplineFloat, sakura.h:2018 (baseline.cc:1941). */
+sakura_Status sakura_SubtractCubicSplineFloat(struct sakura_LSQFitContextFloat const *context,
+		size_t num_data, float const data[], size_t num_pieces, double const coeff[][4],
+		size_t const boundary[], float out[]) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_SubtractSinusoidFloat, sakura.h:2059 (baseline.cc:1983). */
+sakura_Status sakura_SubtractSinusoidFloat(struct sakura_LSQFitContextFloat const *context,
+		size_t num_data, float const data[], size_t num_nwave, size_t const nwave[],
+		size_t num_coeff, double const coeff[], float out[]) SAKURA_B200_NOEXCEPT;
+
+/* ---- NEW: batched many-spectra fits ---------------------------------------
+ *
+ * Row r of `data`/`best_fit`/`residual` starts at element r*data_stride, of
+ * `mask`/`final_mask` at r*mask_stride, of `coeff` at r*num_coeff (spline:
+ * r*num_pieces*4), of `boundary` at r*(num_pieces+1).  `rms`, `status`,
+ * `lsqfit_status` have one entry per row.  Per-row semantics are exactly those of
+ * the single-row call (baseline.cc:1115-1224, 1268-1409):
+ *   status[r] = the sakura_Status the single-row call would have returned
+ *               (kOK, or kNG when the row has too few usable channels),
+ *   lsqfit_status[r] = kOK / kNG / kNotEnoughData,
+ *   a failing row leaves its coeff/best_fit/residual/rms untouched, and its
+ *   final_mask untouched unless clipping had already started (SURVEY A-13).
+ * The return value is kInvalidArgument when the *call* is malformed (NULL /
+ * unaligned base pointers, strides that break row alignment, order/num_coeff
+ * out of range), kNoMemory when device memory cannot be had, kUnknownError on a
+ * CUDA failure, else kOK -- also when some rows failed: inspect status[].
+ * coeff, best_fit, residual may be NULL.  Host variant: base pointers must be
+ * sakura-aligned and the strides multiples that keep every row aligned.
+ * Device variant: device pointers, 16-byte aligned rows, asynchronous on
+ * `cuda_stream` (cudaStream_t; 0 = default stream); in-place final_mask==mask is
+ * allowed, residual/best_fit must not alias data.
+ */
+sakura_Status sakura_LSQFitPolynomialFloatBatch(
+		struct sakura_LSQFitContextFloat const *context, uint16_t order, size_t num_spectra,
+		size_t num_data, float const data[], size_t data_stride, bool const mask[],
+		size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max,
+		size_t num_coeff, double coeff[], float best_fit[], float residual[],
+		bool final_mask[], float rms[], int32_t status[], int32_t lsqfit_status[])
+				SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_LSQFitPolynomialFloatBatchDevice(
+		struct sakura_LSQFitContextFloat const *context, uint16_t order, size_t num_spectra,
+		size_t num_data, float const d_data[], size_t data_stride, bool const d_mask[],
+		size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max,
+		size_t num_coeff, double d_coeff[], float d_best_fit[], float d_residual[],
+		bool d_final_mask[], float d_rms[], int32_t d_status[], int32_t d_lsqfit_status[],
+		void *cuda_stream) SAKURA_B200_NOEXCEPT;
+
+sakura_Status sakura_LSQFitCubicSplineFloatBatch(
+		struct sakura_LSQFitContextFloat const *context, size_t num_pieces, size_t num_spectra,
+		size_t num_data, float const data[], size_t data_stride, bool const mask[],
+		size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max,
+		double coeff[/*num_spectra*num_pieces*4*/], float best_fit[], float residual[],
+		bool final_mask[], float rms[], size_t boundary[/*num_spectra*(num_pieces+1)*/],
+		int32_t status[], int32_t lsqfit_status[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_LSQFitCubicSplineFloatBatchDevice(
+		struct sakura_LSQFitContextFloat const *context, size_t num_pieces, size_t num_spectra,
+		size_t num_data, float const d_data[], size_t data_stride, bool const d_mask[],
+		size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max,
+		double d_coeff[], float d_best_fit[], float d_residual[], bool d_final_mask[],
+		float d_rms[], size_t d_boundary[], int32_t d_status[], int32_t d_lsqfit_status[],
+		void *cuda_stream) SAKURA_B200_NOEXCEPT;
+
+sakura_Status sakura_LSQFitSinusoidFloatBatch(
+		struct sakura_LSQFitContextFloat const *context, size_t num_nwave,
+		size_t const nwave[], size_t num_spectra, size_t num_data, float const data[],
+		size_t data_stride, bool const mask[], size_t mask_stride, float clip_threshold_sigma,
+		uint16_t num_fitting_max, size_t num_coeff, double coeff[], float best_fit[],
+		float residual[], bool final_mask[], float rms[], int32_t status[],
+		int32_t lsqfit_status[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_LSQFitSinusoidFloatBatchDevice(
+		struct sakura_LSQFitContextFloat const *context, size_t num_nwave,
+		size_t const nwave[/*host*/], size_t num_spectra, size_t num_data,
+		float const d_data[], size_t data_stride, bool const d_mask[], size_t mask_stride,
+		float clip_threshold_sigma, uint16_t num_fitting_max, size_t num_coeff,
+		double d_coeff[], float d_best_fit[], float d_residual[], bool d_final_mask[],
+		float d_rms[], int32_t d_status[], int32_t d_lsqfit_status[], void *cuda_stream)
+				SAKURA_B200_NOEXCEPT;
+
+/* ---- NEW: library introspection (measurement support) --------------------- */
+
+/** Number of CUDA kernels this library has launched in this process so far. */
+uint64_t sakura_b200_GetKernelLaunchCount(void) SAKURA_B200_NOEXCEPT;
+/** Name of the kernel variant the last fit call dispatched to ("poly_fast", "general", ...). */
+char const *sakura_b200_GetLastKernelName(void) SAKURA_B200_NOEXCEPT;
+/** Text of the last CUDA error seen by the library ("" if none). */
+char const *sakura_b200_GetLastErrorMessage(void) SAKURA_B200_NOEXCEPT;
+/** "sakura_b200 <version> (sm_100a)". */
+char const *sakura_b200_GetVersionString(void) SAKURA_B200_NOEXCEPT;
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* SAKURA_B200_H_ */

@@ -1,0 +1,311 @@
+"""ctypes binding of the C ABI in include/sakura_b200.h.
+
+Host-side mirror of the reference's python-binding for this path
+(libsakura/python-binding/python-binding.cc:1610-1757 `create_baseline_context`,
+`lsqfit_polynomial`, `compute_statistics`; aligned buffers :505-563), extended with the
+batched entry points.  numpy arrays in, numpy arrays out; torch tensors are accepted by
+the `*_device` methods through `data_ptr()`.
+
+The binding never computes anything itself: every call goes through
+libsakura_b200.so, and loading fails loudly when the library cannot be built/loaded.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+ALIGNMENT = 32
+
+STATUS_OK, STATUS_NG, STATUS_INVALID_ARGUMENT, STATUS_NO_MEMORY, STATUS_UNKNOWN = 0, 1, 2, 3, 99
+LSQFIT_OK, LSQFIT_NG, LSQFIT_NOT_ENOUGH_DATA = 0, 1, 2
+LSQFIT_TYPE_POLYNOMIAL, LSQFIT_TYPE_CHEBYSHEV = 0, 1
+
+
+class StatisticsResult(C.Structure):
+    """sakura_StatisticsResultFloat (sakura.h:208-237)."""
+    _fields_ = [("count", C.c_size_t), ("sum", C.c_double), ("square_sum", C.c_double),
+                ("min", C.c_float), ("max", C.c_float),
+                ("index_of_min", C.c_ssize_t), ("index_of_max", C.c_ssize_t)]
+
+
+STAT_DTYPE = np.dtype([("count", np.uint64), ("sum", np.float64), ("square_sum", np.float64),
+                       ("min", np.float32), ("max", np.float32),
+                       ("index_of_min", np.int64), ("index_of_max", np.int64)], align=True)
+assert STAT_DTYPE.itemsize == C.sizeof(StatisticsResult) == 48
+
+
+def aligned_empty(shape, dtype, align: int = 64) -> np.ndarray:
+    """Uninitialised C-contiguous array whose base address is `align`-byte aligned
+    (the reference's new_uninitialized_aligned_ndarray, python-binding.cc:505-563)."""
+    dtype = np.dtype(dtype)
+    shape = (shape,) if np.isscalar(shape) else tuple(shape)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    raw = np.empty(nbytes + align, dtype=np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + nbytes].view(dtype).reshape(shape)
+
+
+def aligned_copy(a, dtype=None, align: int = 64) -> np.ndarray:
+    a = np.asarray(a)
+    out = aligned_empty(a.shape, dtype or a.dtype, align)
+    out[...] = a
+    return out
+
+
+def _is_aligned(a: np.ndarray) -> bool:
+    return a.ctypes.data % ALIGNMENT == 0
+
+
+def _ptr(a: Optional[np.ndarray]):
+    return None if a is None else C.c_void_p(a.ctypes.data)
+
+
+def default_library_path() -> str:
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsakura_b200.so")
+
+
+class SakuraLib:
+    """A loaded library that exports the sakura.h LSQ-fit / statistics C API."""
+
+    def __init__(self, path: Optional[str] = None, has_batch: bool = True):
+        if path is None:
+            path = default_library_path()
+            if not os.path.exists(path):
+                from . import build as _build
+                _build.build()
+        if not os.path.exists(path):
+            raise OSError(f"{path} is missing: libsakura_b200.so must be built "
+                          "(python -m sakura_b200.build); there is no CPU fallback")
+        self.path = path
+        self.lib = C.CDLL(path)
+        self.has_batch = has_batch
+        self._declare()
+        st = self.lib.sakura_Initialize(None, None)
+        if st != STATUS_OK:
+            raise RuntimeError("sakura_Initialize failed")
+
+    # ------------------------------------------------------------------ prototypes
+    def _declare(self) -> None:
+        L = self.lib
+        vp, sz, u16, f32 = C.c_void_p, C.c_size_t, C.c_uint16, C.c_float
+        L.sakura_Initialize.argtypes = [vp, vp]
+        L.sakura_Initialize.restype = C.c_int
+        L.sakura_GetAlignment.restype = sz
+        L.sakura_IsAligned.argtypes = [vp]
+        L.sakura_IsAligned.restype = C.c_bool
+        L.sakura_CreateLSQFitContextPolynomialFloat.argtypes = [C.c_int, u16, sz, C.POINTER(vp)]
+        L.sakura_CreateLSQFitContextCubicSplineFloat.argtypes = [u16, sz, C.POINTER(vp)]
+        L.sakura_CreateLSQFitContextSinusoidFloat.argtypes = [u16, sz, C.POINTER(vp)]
+        L.sakura_DestroyLSQFitContextFloat.argtypes = [vp]
+        L.sakura_GetNumberOfCoefficientsFloat.argtypes = [vp, u16, C.POINTER(sz)]
+        L.sakura_LSQFitPolynomialFloat.argtypes = [vp, u16, sz, vp, vp, f32, u16, sz, vp, vp, vp, vp,
+                                                   C.POINTER(f32), C.POINTER(C.c_int)]
+        L.sakura_LSQFitCubicSplineFloat.argtypes = [vp, sz, sz, vp, vp, f32, u16, vp, vp, vp, vp,
+                                                    C.POINTER(f32), vp, C.POINTER(C.c_int)]
+        L.sakura_LSQFitSinusoidFloat.argtypes = [vp, sz, vp, sz, vp, vp, f32, u16, sz, vp, vp, vp, vp,
+                                                 C.POINTER(f32), C.POINTER(C.c_int)]
+        L.sakura_SubtractPolynomialFloat.argtypes = [vp, sz, vp, sz, vp, vp]
+        L.sakura_SubtractCubicSplineFloat.argtypes = [vp, sz, vp, sz, vp, vp, vp]
+        L.sakura_SubtractSinusoidFloat.argtypes = [vp, sz, vp, sz, vp, sz, vp, vp]
+        L.sakura_ComputeStatisticsFloat.argtypes = [sz, vp, vp, vp]
+        L.sakura_ComputeAccurateStatisticsFloat.argtypes = [sz, vp, vp, vp]
+        L.sakura_GetLSQCoefficientsDouble.argtypes = [sz, vp, vp, sz, vp, sz, vp, vp, vp]
+        L.sakura_UpdateLSQCoefficientsDouble.argtypes = [sz, vp, vp, sz, vp, sz, vp, sz, vp, vp, vp]
+        L.sakura_SolveSimultaneousEquationsByLUDouble.argtypes = [sz, vp, vp, vp]
+        for name in ("sakura_CreateLSQFitContextPolynomialFloat",
+                     "sakura_CreateLSQFitContextCubicSplineFloat",
+                     "sakura_CreateLSQFitContextSinusoidFloat", "sakura_DestroyLSQFitContextFloat",
+                     "sakura_GetNumberOfCoefficientsFloat", "sakura_LSQFitPolynomialFloat",
+                     "sakura_LSQFitCubicSplineFloat", "sakura_LSQFitSinusoidFloat",
+                     "sakura_SubtractPolynomialFloat", "sakura_SubtractCubicSplineFloat",
+                     "sakura_SubtractSinusoidFloat", "sakura_ComputeStatisticsFloat",
+                     "sakura_ComputeAccurateStatisticsFloat", "sakura_GetLSQCoefficientsDouble",
+                     "sakura_UpdateLSQCoefficientsDouble",
+                     "sakura_SolveSimultaneousEquationsByLUDouble"):
+            getattr(L, name).restype = C.c_int
+        if not self.has_batch:
+            return
+        i32p = vp
+        L.sakura_LSQFitPolynomialFloatBatch.argtypes = [vp, u16, sz, sz, vp, sz, vp, sz, f32, u16, sz,
+                                                        vp, vp, vp, vp, vp, i32p, i32p]
+        L.sakura_LSQFitPolynomialFloatBatchDevice.argtypes = \
+            L.sakura_LSQFitPolynomialFloatBatch.argtypes + [vp]
+        L.sakura_LSQFitCubicSplineFloatBatch.argtypes = [vp, sz, sz, sz, vp, sz, vp, sz, f32, u16,
+                                                         vp, vp, vp, vp, vp, vp, i32p, i32p]
+        L.sakura_LSQFitCubicSplineFloatBatchDevice.argtypes = \
+            L.sakura_LSQFitCubicSplineFloatBatch.argtypes + [vp]
+        L.sakura_LSQFitSinusoidFloatBatch.argtypes = [vp, sz, vp, sz, sz, vp, sz, vp, sz, f32, u16, sz,
+                                                      vp, vp, vp, vp, vp, i32p, i32p]
+        L.sakura_LSQFitSinusoidFloatBatchDevice.argtypes = \
+            L.sakura_LSQFitSinusoidFloatBatch.argtypes + [vp]
+        L.sakura_ComputeStatisticsFloatBatch.argtypes = [sz, sz, vp, sz, vp, sz, vp]
+        L.sakura_ComputeStatisticsFloatBatchDevice.argtypes = [sz, sz, vp, sz, vp, sz, vp, vp]
+        for name in ("sakura_LSQFitPolynomialFloatBatch", "sakura_LSQFitPolynomialFloatBatchDevice",
+                     "sakura_LSQFitCubicSplineFloatBatch", "sakura_LSQFitCubicSplineFloatBatchDevice",
+                     "sakura_LSQFitSinusoidFloatBatch", "sakura_LSQFitSinusoidFloatBatchDevice",
+                     "sakura_ComputeStatisticsFloatBatch", "sakura_ComputeStatisticsFloatBatchDevice"):
+            getattr(L, name).restype = C.c_int
+        L.sakura_b200_GetKernelLaunchCount.restype = C.c_uint64
+        L.sakura_b200_GetLastKernelName.restype = C.c_char_p
+        L.sakura_b200_GetLastErrorMessage.restype = C.c_char_p
+        L.sakura_b200_GetVersionString.restype = C.c_char_p
+
+    # ------------------------------------------------------------------ contexts
+    def create_polynomial_context(self, order: int, num_data: int,
+                                  lsqfit_type: int = LSQFIT_TYPE_POLYNOMIAL):
+        ctx = C.c_void_p()
+        st = self.lib.sakura_CreateLSQFitContextPolynomialFloat(lsqfit_type, order, num_data,
+                                                                C.byref(ctx))
+        return st, (ctx if st == STATUS_OK else None)
+
+    def create_cubicspline_context(self, npiece: int, num_data: int):
+        ctx = C.c_void_p()
+        st = self.lib.sakura_CreateLSQFitContextCubicSplineFloat(npiece, num_data, C.byref(ctx))
+        return st, (ctx if st == STATUS_OK else None)
+
+    def create_sinusoid_context(self, nwave: int, num_data: int):
+        ctx = C.c_void_p()
+        st = self.lib.sakura_CreateLSQFitContextSinusoidFloat(nwave, num_data, C.byref(ctx))
+        return st, (ctx if st == STATUS_OK else None)
+
+    def destroy_context(self, ctx) -> int:
+        return self.lib.sakura_DestroyLSQFitContextFloat(ctx)
+
+    def get_number_of_coefficients(self, ctx, order: int):
+        n = C.c_size_t(0)
+        st = self.lib.sakura_GetNumberOfCoefficientsFloat(ctx, order, C.byref(n))
+        return st, n.value
+
+    # ------------------------------------------------------------------ launch accounting
+    def kernel_launch_count(self) -> int:
+        return int(self.lib.sakura_b200_GetKernelLaunchCount())
+
+    def last_kernel_name(self) -> str:
+        return self.lib.sakura_b200_GetLastKernelName().decode()
+
+    def last_error(self) -> str:
+        return self.lib.sakura_b200_GetLastErrorMessage().decode()
+
+    # ------------------------------------------------------------------ batched fits (host arrays)
+    @staticmethod
+    def _prep_rows(data, mask):
+        data = np.asarray(data)
+        mask = np.asarray(mask)
+        if data.ndim == 1:
+            data = data[None, :]
+            mask = mask[None, :]
+        if data.dtype != np.float32 or not data.flags.c_contiguous or not _is_aligned(data):
+            data = aligned_copy(data, np.float32)
+        if mask.dtype != np.bool_ or not mask.flags.c_contiguous or not _is_aligned(mask):
+            mask = aligned_copy(mask, np.bool_)
+        return data, mask
+
+    def lsqfit_polynomial_batch(self, ctx, order: int, data, mask, clip_threshold_sigma: float,
+                                num_fitting_max: int, num_coeff: Optional[int] = None,
+                                want_coeff: bool = True, want_best_fit: bool = False,
+                                want_residual: bool = True, out: Optional[dict] = None) -> dict:
+        """Rows of `data`/`mask` ([R, n]) through sakura_LSQFitPolynomialFloatBatch."""
+        data, mask = self._prep_rows(data, mask)
+        R, n = data.shape
+        K = order + 1 if num_coeff is None else num_coeff
+        res = out if out is not None else {}
+        res.setdefault("coeff", aligned_empty((R, K), np.float64) if want_coeff else None)
+        res.setdefault("best_fit", aligned_empty((R, n), np.float32) if want_best_fit else None)
+        res.setdefault("residual", aligned_empty((R, n), np.float32) if want_residual else None)
+        res.setdefault("final_mask", aligned_empty((R, n), np.bool_))
+        res.setdefault("rms", aligned_empty((R,), np.float32))
+        res["status"] = aligned_empty((R,), np.int32)
+        res["lsqfit_status"] = aligned_empty((R,), np.int32)
+        if out is None:
+            for k in ("coeff", "best_fit", "residual", "rms"):
+                if res[k] is not None:
+                    res[k][...] = np.nan
+            res["final_mask"][...] = False
+        res["call_status"] = self.lib.sakura_LSQFitPolynomialFloatBatch(
+            ctx, order, R, n, _ptr(data), n, _ptr(mask), n, clip_threshold_sigma, num_fitting_max, K,
+            _ptr(res["coeff"]), _ptr(res["best_fit"]), _ptr(res["residual"]), _ptr(res["final_mask"]),
+            _ptr(res["rms"]), _ptr(res["status"]), _ptr(res["lsqfit_status"]))
+        return res
+
+    def lsqfit_cubicspline_batch(self, ctx, num_pieces: int, data, mask, clip_threshold_sigma: float,
+                                 num_fitting_max: int, want_coeff: bool = True,
+                                 want_best_fit: bool = False, want_residual: bool = True) -> dict:
+        data, mask = self._prep_rows(data, mask)
+        R, n = data.shape
+        res = {
+            "coeff": aligned_empty((R, num_pieces, 4), np.float64) if want_coeff else None,
+            "best_fit": aligned_empty((R, n), np.float32) if want_best_fit else None,
+            "residual": aligned_empty((R, n), np.float32) if want_residual else None,
+            "final_mask": aligned_empty((R, n), np.bool_),
+            "rms": aligned_empty((R,), np.float32),
+            "boundary": aligned_empty((R, num_pieces + 1), np.uint64),
+            "status": aligned_empty((R,), np.int32),
+            "lsqfit_status": aligned_empty((R,), np.int32),
+        }
+        for k in ("coeff", "best_fit", "residual", "rms"):
+            if res[k] is not None:
+                res[k][...] = np.nan
+        res["final_mask"][...] = False
+        res["boundary"][...] = np.iinfo(np.uint64).max
+        res["call_status"] = self.lib.sakura_LSQFitCubicSplineFloatBatch(
+            ctx, num_pieces, R, n, _ptr(data), n, _ptr(mask), n, clip_threshold_sigma, num_fitting_max,
+            _ptr(res["coeff"]), _ptr(res["best_fit"]), _ptr(res["residual"]), _ptr(res["final_mask"]),
+            _ptr(res["rms"]), _ptr(res["boundary"]), _ptr(res["status"]), _ptr(res["lsqfit_status"]))
+        return res
+
+    def lsqfit_sinusoid_batch(self, ctx, nwave: Sequence[int], data, mask, clip_threshold_sigma: float,
+                              num_fitting_max: int, num_coeff: Optional[int] = None,
+                              want_coeff: bool = True, want_best_fit: bool = False,
+                              want_residual: bool = True) -> dict:
+        data, mask = self._prep_rows(data, mask)
+        R, n = data.shape
+        nw = aligned_copy(np.asarray(nwave, dtype=np.uint64))
+        if num_coeff is None:
+            num_coeff = 2 * len(nw) - 1 if nw[0] == 0 else 2 * len(nw)
+        res = {
+            "coeff": aligned_empty((R, num_coeff), np.float64) if want_coeff else None,
+            "best_fit": aligned_empty((R, n), np.float32) if want_best_fit else None,
+            "residual": aligned_empty((R, n), np.float32) if want_residual else None,
+            "final_mask": aligned_empty((R, n), np.bool_),
+            "rms": aligned_empty((R,), np.float32),
+            "status": aligned_empty((R,), np.int32),
+            "lsqfit_status": aligned_empty((R,), np.int32),
+        }
+        for k in ("coeff", "best_fit", "residual", "rms"):
+            if res[k] is not None:
+                res[k][...] = np.nan
+        res["final_mask"][...] = False
+        res["call_status"] = self.lib.sakura_LSQFitSinusoidFloatBatch(
+            ctx, len(nw), _ptr(nw), R, n, _ptr(data), n, _ptr(mask), n, clip_threshold_sigma,
+            num_fitting_max, num_coeff, _ptr(res["coeff"]), _ptr(res["best_fit"]),
+            _ptr(res["residual"]), _ptr(res["final_mask"]), _ptr(res["rms"]), _ptr(res["status"]),
+            _ptr(res["lsqfit_status"]))
+        return res
+
+    # ------------------------------------------------------------------ statistics
+    def compute_statistics_batch(self, data, mask) -> np.ndarray:
+        data, mask = self._prep_rows(data, mask)
+        R, n = data.shape
+        result = aligned_empty((R,), STAT_DTYPE)
+        st = self.lib.sakura_ComputeStatisticsFloatBatch(R, n, _ptr(data), n, _ptr(mask), n,
+                                                         _ptr(result))
+        if st != STATUS_OK:
+            raise RuntimeError(f"sakura_ComputeStatisticsFloatBatch -> {st}: {self.last_error()}")
+        return result
+
+    def compute_statistics(self, data, mask, accurate: bool = True):
+        """Single array through sakura_Compute[Accurate]StatisticsFloat; returns (status, record)."""
+        data = np.asarray(data)
+        mask = np.asarray(mask)
+        if data.dtype != np.float32 or not _is_aligned(data) or not data.flags.c_contiguous:
+            data = aligned_copy(data, np.float32)
+        if mask.dtype != np.bool_ or not _is_aligned(mask) or not mask.flags.c_contiguous:
+            mask = aligned_copy(mask, np.bool_)
+        result = aligned_empty((1,), STAT_DTYPE)
+        fn = (self.lib.sakura_ComputeAccurateStatisticsFloat if accurate
+              else self.lib.sakura_ComputeStatisticsFloat)
+        st = fn(data.size, _ptr(data), _ptr(mask), _ptr(result))
+        return st, result[0]

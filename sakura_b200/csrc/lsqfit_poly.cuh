@@ -1,0 +1,39 @@
+// Register-resident polynomial LSQ-fit kernel (the north-star hot path); see lsqfit_poly.cu.
+#ifndef SAKURA_B200_LSQFIT_POLY_CUH_
+#define SAKURA_B200_LSQFIT_POLY_CUH_
+
+#include <stddef.h>
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace sakura_b200 {
+
+struct PolyFitParams {
+	size_t num_spectra;
+	int n; // channels per spectrum
+	int K; // fitted bases = order + 1
+	float const *data;
+	size_t data_stride;
+	uint8_t const *mask;
+	size_t mask_stride;
+	float clip_threshold_sigma;
+	int num_fitting_max;
+	double *coeff; // may be NULL; [num_spectra][K]
+	float *best_fit; // may be NULL
+	float *residual; // may be NULL
+	uint8_t *final_mask;
+	float *rms;
+	int32_t *status;
+	int32_t *lsqfit_status;
+	int32_t *flags; // may be NULL; bit0 results published, bit1 final_mask written
+};
+
+/** True when the shape/alignment can be served by the register-resident kernel. */
+bool PolyFastSupported(size_t n, size_t K, size_t data_stride, size_t mask_stride, void const *data,
+		void const *mask, void const *best_fit, void const *residual, void const *final_mask);
+
+cudaError_t LaunchPolyFit(PolyFitParams const &p, int num_sms, cudaStream_t stream, int *launches);
+
+} // namespace sakura_b200
+
+#endif
