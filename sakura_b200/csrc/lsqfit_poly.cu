@@ -1,11 +1,849 @@
-// placeholder until the register-resident kernel lands (next commit)
+// Polynomial baseline fit, the north-star hot path (sakura_LSQFitPolynomialFloat semantics,
+// libsakura/src/baseline.cc:1115-1224, 1268-1329) as one persistent sm_100a kernel.
+//
+// One CTA (NT = 128 or 256 threads) owns one spectrum at a time. The row (float data + byte
+// mask) is read from HBM exactly once with coalesced 128-bit / 32-bit loads; the data and
+// the residual live in shared memory and the mask lives in registers (one bit per channel,
+// <= 32 channels per thread) for all clip iterations; every output is written once.
+// Algorithmic HBM traffic per spectrum: n*(4+1) in, n*(1+4) out (+ coeff/rms/status).
+//
+// Per row:
+//   prologue  : load; count valid channels; data moments T_k = sum_valid y z^k (FP64, z = channel)
+//               power sums over the flagged channels -> S_k = (all-channel constant) - flagged
+//   warp 0    : Hankel normal equations G[j][k] = S[j+k]; in-register LDL^T solve
+//   iteration : pass A  model (FP64 Horner) -> float, residual = y - model (float),
+//                       count / sum / sum-of-squares over valid channels (FP64)
+//               thresholds exactly as baseline.cc:1200-1207 (rounded to float)
+//               pass B  clip predicate of baseline.cc:1088 in float; channel n-1 never examined;
+//                       S_k, T_k contributions of the clipped channels only (downdate, the
+//                       reference's own strategy: numeric_operation.cc:283-314, 448-479)
+//               warp 0  downdate, re-solve
+//
+// What differs from the reference's arithmetic (see DESIGN.md "Arithmetic contract"): the
+// Gram matrix is assembled from 2K-1 power sums instead of K*K per-channel products, sums are
+// tree- instead of sequentially ordered, and the solve is LDL^T in natural order with a
+// full-pivot rank-revealing fallback for degenerate rows. All are O(eps)-level perturbations
+// of an FP64 computation; masks, rms and float residuals are checked against the oracle.
 #include "lsqfit_poly.cuh"
+#include "device_common.cuh"
+
+#include <float.h>
+#include <map>
+#include <mutex>
+
 namespace sakura_b200 {
-bool PolyFastSupported(size_t, size_t, size_t, size_t, void const *, void const *, void const *,
-		void const *, void const *) {
-	return false;
+
+namespace {
+
+constexpr int kMaxPolyK = 8;
+constexpr int kMaxMoments = 2 * kMaxPolyK - 1;
+
+struct PolyConst {
+	double h; // 1/(n-1)
+	double hpow[kMaxMoments]; // h^k
+	double s_all[kMaxMoments]; // sum_{i=0}^{n-1} (i h)^k, correctly rounded
+	double factor[kMaxPolyK]; // (n-1)^k by repeated multiplication (baseline.cc:1313-1318)
+};
+
+template<int K, int NT>
+struct Shared {
+	static constexpr int NW = NT / 32;
+	static constexpr int NV = 3 * K - 1; // 2K-1 power sums + K data moments
+	double stat[2][NW][3]; // count,sum,sq partials, double-buffered by iteration parity
+	double wtot[NW][NV]; // per-warp moment totals
+	double S[2 * K - 1];
+	double T[K];
+	double cz[K]; // model coefficients in the channel-index variable: c_k h^k
+	double cx[K]; // solution in x = i/(n-1) (the reference's coeff_full)
+	double A[K * K]; // fallback solver workspace
+	int perm[2 * K];
+	int icnt[NW];
+	int wclip[NW]; // per-warp number of channels clipped in this pass
+	int exit_flag;
+	int num_unmasked;
+};
+
+__device__ __forceinline__ double u32_to_double(uint32_t v) {
+	// exact, without the (slow) conversion pipe
+	return __hiloint2double(0x43300000, static_cast<int>(v)) - 4503599627370496.0;
 }
-cudaError_t LaunchPolyFit(PolyFitParams const &, int, cudaStream_t, int *) {
-	return cudaErrorNotSupported;
+
+// ---- moments over the channels whose bit is set in `bits` (this thread's channel slots) ----
+// Accumulates sum x^k (k < 2K-1) and, if WITH_T, sum y x^k (k < K), x = z*h, then reduces the
+// per-lane partials inside the warp by transposing them through `scratch` (NV rows of 33
+// doubles): lane k adds row k in lane order -- deterministic, no atomics, no shuffles.
+// Result: wtot[k] for k < NV (zeros when no lane of the warp has a bit set).
+template<int K, int NT, bool WITH_T>
+__device__ __forceinline__ void WarpBitMoments(uint32_t bits, double zbase, double h,
+		float const *sdata, int tid, double *scratch, double *wtot) {
+	constexpr int NS = 2 * K - 1;
+	constexpr int NV = 3 * K - 1;
+	int const lane = tid & 31;
+	bool const any = __any_sync(0xffffffffu, bits != 0u);
+	if (!any) {
+		if (lane < NV) {
+			wtot[lane] = 0.0;
+		}
+		return;
+	}
+	double ps[NS];
+	double pt[K];
+#pragma unroll
+	for (int k = 0; k < NS; ++k) {
+		ps[k] = 0.0;
+	}
+#pragma unroll
+	for (int k = 0; k < K; ++k) {
+		pt[k] = 0.0;
+	}
+	while (bits != 0u) {
+		int const s = __ffs(bits) - 1;
+		bits &= bits - 1u;
+		uint32_t const off = static_cast<uint32_t>((s >> 2) * (4 * NT) + (s & 3));
+		double const x = (zbase + u32_to_double(off)) * h;
+		double yd = 0.0;
+		if (WITH_T) {
+			yd = static_cast<double>(sdata[4 * tid + off]);
+		}
+		double pw = 1.0;
+#pragma unroll
+		for (int k = 0; k < NS; ++k) {
+			ps[k] += pw;
+			if (WITH_T && k < K) {
+				pt[k] = fma(yd, pw, pt[k]);
+			}
+			pw *= x;
+		}
+	}
+#pragma unroll
+	for (int k = 0; k < NS; ++k) {
+		scratch[k * 33 + lane] = ps[k];
+	}
+#pragma unroll
+	for (int k = 0; k < K; ++k) {
+		scratch[(NS + k) * 33 + lane] = pt[k];
+	}
+	__syncwarp();
+	if (lane < NV) {
+		double const *rowp = scratch + lane * 33;
+		double t0 = 0.0, t1 = 0.0;
+#pragma unroll
+		for (int l = 0; l < 32; l += 2) {
+			t0 += rowp[l];
+			t1 += rowp[l + 1];
+		}
+		wtot[lane] = t0 + t1;
+	}
+	__syncwarp();
 }
+
+// ---- solve G c = T, G[j][k] = S[j+k], entirely in registers (every lane the same work) -------
+// LDL^T / Gaussian elimination in natural order on the upper triangle. G is a Gram matrix:
+// symmetric positive definite unless the row is degenerate. Returns false when a pivot is not
+// safely positive; the caller then uses the full-pivot rank-revealing solver.
+template<int K>
+__device__ __forceinline__ bool SolveLDLT(double const *S, double const *T, double *c_out) {
+	double a[K][K];
+	double c[K];
+	double rcp[K];
+#pragma unroll
+	for (int i = 0; i < K; ++i) {
+#pragma unroll
+		for (int j = i; j < K; ++j) {
+			a[i][j] = S[i + j];
+		}
+		c[i] = T[i];
+	}
+	double maxpivot = 0.0;
+	bool ok = true;
+#pragma unroll
+	for (int k = 0; k < K; ++k) {
+		double const pivot = a[k][k];
+		maxpivot = fmax(maxpivot, fabs(pivot));
+		ok = ok && (pivot > maxpivot * (DBL_EPSILON * K));
+		rcp[k] = 1.0 / pivot;
+#pragma unroll
+		for (int i = k + 1; i < K; ++i) {
+			double const l = a[k][i] * rcp[k];
+#pragma unroll
+			for (int j = i; j < K; ++j) {
+				a[i][j] = fma(-l, a[k][j], a[i][j]);
+			}
+			c[i] = fma(-l, c[k], c[i]);
+		}
+	}
+#pragma unroll
+	for (int j = K - 1; j >= 0; --j) {
+		c[j] *= rcp[j];
+#pragma unroll
+		for (int i = 0; i < j; ++i) {
+			c[i] = fma(-a[i][j], c[j], c[i]);
+		}
+	}
+#pragma unroll
+	for (int i = 0; i < K; ++i) {
+		c_out[i] = c[i];
+	}
+	return ok;
 }
+
+// Full-pivot LU within one warp on a K x K matrix in shared memory; same algorithm as
+// lsq_device.cuh::SolveFullPivLU (Eigen FullPivLU semantics), used for degenerate rows.
+template<int K>
+__device__ void WarpSolveFullPivLU(double const *S, double const *T, double *A, int *perm,
+		double *cx) {
+	int const lane = threadIdx.x & 31;
+	int *row_tr = perm;
+	int *col_tr = perm + K;
+	for (int e = lane; e < K * K; e += 32) {
+		A[e] = S[e / K + e % K];
+	}
+	double c = (lane < K) ? T[lane] : 0.0; // lane i holds c[i]
+	__syncwarp();
+	double maxpivot = 0.0;
+	int nonzero_pivots = K;
+	for (int k = 0; k < K; ++k) {
+		int const m = K - k;
+		double best_v = -1.0;
+		int best_i = 0x7fffffff;
+		for (int idx = lane; idx < m * m; idx += 32) {
+			int const j = k + idx / m;
+			int const i = k + idx % m;
+			double const v = fabs(A[i * K + j]);
+			if (v > best_v) {
+				best_v = v;
+				best_i = idx;
+			}
+		}
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			double const ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+			int const oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+			if (ov > best_v || (ov == best_v && oi < best_i)) {
+				best_v = ov;
+				best_i = oi;
+			}
+		}
+		if (best_v == 0.0) {
+			nonzero_pivots = k;
+			if (lane >= k && lane < K) {
+				row_tr[lane] = lane;
+				col_tr[lane] = lane;
+			}
+			break;
+		}
+		maxpivot = fmax(maxpivot, best_v);
+		int const pcol = k + best_i / m;
+		int const prow = k + best_i % m;
+		if (lane == 0) {
+			row_tr[k] = prow;
+			col_tr[k] = pcol;
+		}
+		if (prow != k) {
+			if (lane < K) {
+				double const t = A[k * K + lane];
+				A[k * K + lane] = A[prow * K + lane];
+				A[prow * K + lane] = t;
+			}
+			double const ck = __shfl_sync(0xffffffffu, c, k);
+			double const cp = __shfl_sync(0xffffffffu, c, prow);
+			if (lane == k) {
+				c = cp;
+			} else if (lane == prow) {
+				c = ck;
+			}
+			__syncwarp();
+		}
+		if (pcol != k) {
+			if (lane < K) {
+				double const t = A[lane * K + k];
+				A[lane * K + k] = A[lane * K + pcol];
+				A[lane * K + pcol] = t;
+			}
+			__syncwarp();
+		}
+		if (k < K - 1) {
+			double const pivot = A[k * K + k];
+			double l = 0.0;
+			if (lane > k && lane < K) {
+				l = A[lane * K + k] / pivot;
+				A[lane * K + k] = l;
+			}
+			double const ck = __shfl_sync(0xffffffffu, c, k);
+			if (lane > k && lane < K) {
+				c = fma(-l, ck, c);
+			}
+			__syncwarp();
+			int const mm = m - 1;
+			for (int idx = lane; idx < mm * mm; idx += 32) {
+				int const i = k + 1 + idx / mm;
+				int const j = k + 1 + idx % mm;
+				A[i * K + j] = fma(-A[i * K + k], A[k * K + j], A[i * K + j]);
+			}
+			__syncwarp();
+		}
+	}
+	__syncwarp();
+	double const threshold = fabs(maxpivot) * (DBL_EPSILON * static_cast<double>(K));
+	int rank = 0;
+	for (int i = 0; i < nonzero_pivots; ++i) {
+		rank += (fabs(A[i * K + i]) > threshold) ? 1 : 0;
+	}
+	for (int j = rank - 1; j >= 0; --j) {
+		double cj = c;
+		if (lane == j) {
+			cj = c / A[j * K + j];
+			c = cj;
+		}
+		cj = __shfl_sync(0xffffffffu, cj, j);
+		if (lane < j) {
+			c = fma(-A[lane * K + j], cj, c);
+		}
+	}
+	if (lane < K) {
+		cx[lane] = 0.0;
+	}
+	__syncwarp();
+	if (lane == 0) {
+		int q[K];
+		for (int i = 0; i < K; ++i) {
+			q[i] = i;
+		}
+		for (int k = 0; k < K; ++k) {
+			int const t = q[k];
+			q[k] = q[col_tr[k]];
+			q[col_tr[k]] = t;
+		}
+		for (int i = 0; i < K; ++i) {
+			row_tr[i] = q[i];
+		}
+	}
+	__syncwarp();
+	if (lane < rank) {
+		cx[row_tr[lane]] = c;
+	}
+	__syncwarp();
+}
+
+template<int K, int NT>
+__device__ __forceinline__ void WarpSolve(Shared<K, NT> &sh, PolyConst const &pc) {
+	int const lane = threadIdx.x & 31;
+	double c[K];
+	bool const ok = SolveLDLT<K>(sh.S, sh.T, c);
+	if (ok) {
+		if (lane == 0) {
+#pragma unroll
+			for (int k = 0; k < K; ++k) {
+				sh.cx[k] = c[k];
+				sh.cz[k] = c[k] * pc.hpow[k];
+			}
+		}
+	} else { // warp-uniform: every lane solved the same system
+		WarpSolveFullPivLU<K>(sh.S, sh.T, sh.A, sh.perm, sh.cx);
+		if (lane < K) {
+			sh.cz[lane] = sh.cx[lane] * pc.hpow[lane];
+		}
+	}
+}
+
+template<int K, int NT>
+__host__ __device__ constexpr size_t ResidualBytes(int n) {
+	// the residual buffer doubles as per-warp reduction scratch: NW x NV x 33 doubles
+	size_t const need = static_cast<size_t>(NT / 32) * (3 * K - 1) * 33 * sizeof(double);
+	size_t const res = static_cast<size_t>(n) * 4;
+	size_t const m = res > need ? res : need;
+	return (m + 15) / 16 * 16;
+}
+
+template<int K, int NT>
+__host__ __device__ constexpr size_t SharedOffset(int n) {
+	size_t const off = (static_cast<size_t>(n) * 4 + 15) / 16 * 16 + ResidualBytes<K, NT>(n);
+	return (off + 15) / 16 * 16;
+}
+
+constexpr int kMinBlocks128 = 6;
+constexpr int kMinBlocks256 = 3;
+
+template<int K, int NT>
+__global__ void __launch_bounds__(NT, (NT == 128 ? (K >= 7 ? 4 : kMinBlocks128) :
+		(K >= 7 ? 2 : kMinBlocks256)))
+PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
+	constexpr int NW = NT / 32;
+	constexpr int NS = 2 * K - 1;
+	constexpr int NV = 3 * K - 1;
+	extern __shared__ __align__(16) unsigned char smem_raw[];
+	int const n = p.n;
+	int const ng = n / 4;
+	// layout: data[n] | residual[n] (also reduction scratch) | Shared
+	float *sdata = reinterpret_cast<float *>(smem_raw);
+	float *sres = reinterpret_cast<float *>(smem_raw + (static_cast<size_t>(n) * 4 + 15) / 16 * 16);
+	Shared<K, NT> &sh = *reinterpret_cast<Shared<K, NT> *>(smem_raw + SharedOffset<K, NT>(n));
+
+	int const tid = threadIdx.x;
+	int const lane = tid & 31;
+	int const warp = tid >> 5;
+	// The residual is dead whenever moments are reduced (before the first fit, and between a
+	// clip pass and the next model evaluation), so the two share storage.
+	double *scratch = reinterpret_cast<double *>(sres) + warp * (NV * 33);
+	double const zbase = static_cast<double>(4 * tid);
+	float const clip = p.clip_threshold_sigma;
+	// bit s = 4*j + e of a thread's mask word <-> channel 4*(tid + NT*j) + e
+	int const nslots = (tid < ng) ? 4 * ((ng - 1 - tid) / NT + 1) : 0;
+	uint32_t const slot_mask = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);
+
+	for (size_t row = blockIdx.x; row < p.num_spectra; row += gridDim.x) {
+		float4 const *gdata = reinterpret_cast<float4 const *>(p.data + row * p.data_stride);
+		uint32_t const *gmask = reinterpret_cast<uint32_t const *>(p.mask + row * p.mask_stride);
+		__syncthreads(); // the previous row's shared state is dead
+
+		// ---- prologue: load the row, valid bits, data moments in z = channel index ----------
+		uint32_t vbits = 0u;
+		double t[K];
+#pragma unroll
+		for (int k = 0; k < K; ++k) {
+			t[k] = 0.0;
+		}
+		{
+			double zg = zbase;
+			int j4 = 0;
+			for (int g = tid; g < ng; g += NT, j4 += 4) {
+				float4 const y = __ldg(gdata + g);
+				uint32_t m = __ldg(gmask + g);
+				reinterpret_cast<float4 *>(sdata)[g] = y;
+				m = __vcmpne4(m, 0u) & 0x01010101u; // any non-zero byte is "true"
+				uint32_t const nib = (m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xfu;
+				vbits |= nib << j4;
+				float const ye[4] = { y.x, y.y, y.z, y.w };
+#pragma unroll
+				for (int e = 0; e < 4; ++e) {
+					if (nib & (1u << e)) {
+						double const z = zg + static_cast<double>(e);
+						double const yd = static_cast<double>(ye[e]);
+						t[0] += yd;
+						double pw = z;
+#pragma unroll
+						for (int k = 1; k < K; ++k) {
+							t[k] = fma(yd, pw, t[k]);
+							pw *= z;
+						}
+					}
+				}
+				zg += static_cast<double>(4 * NT);
+			}
+		}
+		int cnt = warp_sum(__popc(vbits));
+		if (lane == 0) {
+			sh.icnt[warp] = cnt;
+		}
+		__syncthreads();
+		int num_valid = 0;
+#pragma unroll
+		for (int w = 0; w < NW; ++w) {
+			num_valid += sh.icnt[w];
+		}
+
+		if (p.num_fitting_max == 0) { // baseline.cc:1295-1296: kOK, nothing written
+			if (tid == 0) {
+				p.status[row] = kStatusOK;
+				p.lsqfit_status[row] = kLsqOK;
+			}
+			continue;
+		}
+		if (num_valid < K) { // baseline.cc:1147-1150
+			if (tid == 0) {
+				p.status[row] = kStatusNG;
+				p.lsqfit_status[row] = kLsqNotEnoughData;
+			}
+			continue;
+		}
+
+		// ---- first normal equations ------------------------------------------------------------
+		// S over the valid channels = constant over all channels - sum over the flagged ones
+		// (or the direct sum when more than half of the row is flagged).
+		bool const complement = (2 * num_valid >= n);
+		WarpBitMoments<K, NT, false>(complement ? (~vbits & slot_mask) : vbits, zbase, pc.h, sdata,
+				tid, scratch, sh.wtot[warp]);
+		// data moments: reuse the T rows of wtot (the call above left them zero)
+#pragma unroll
+		for (int k = 0; k < K; ++k) {
+			t[k] = warp_sum(t[k]);
+		}
+		__syncwarp();
+		if (lane == 0) {
+#pragma unroll
+			for (int k = 0; k < K; ++k) {
+				sh.wtot[warp][NS + k] = t[k];
+			}
+		}
+		__syncthreads();
+		if (warp == 0) {
+			if (lane < NV) {
+				double tot = 0.0;
+#pragma unroll
+				for (int w = 0; w < NW; ++w) {
+					tot += sh.wtot[w][lane];
+				}
+				if (lane < NS) {
+					sh.S[lane] = complement ? (pc.s_all[lane] - tot) : tot;
+				} else {
+					sh.T[lane - NS] = tot * pc.hpow[lane - NS];
+				}
+			}
+			__syncwarp();
+			WarpSolve<K, NT>(sh, pc);
+		}
+		__syncthreads();
+
+		// ---- clip iterations ----------------------------------------------------------------------
+		int num_unmasked = n; // baseline.cc:1152 (sic)
+		double rms_d = 0.0;
+		bool failed = false;
+		for (int iter = 1; iter <= p.num_fitting_max; ++iter) {
+			if (num_unmasked < K) { // baseline.cc:1162-1165
+				failed = true;
+				break;
+			}
+			// pass A: model, residual, statistics
+			double cz[K];
+#pragma unroll
+			for (int k = 0; k < K; ++k) {
+				cz[k] = sh.cz[k];
+			}
+			double sum = 0.0, sq = 0.0;
+			{
+				double zg = zbase;
+				uint32_t vb = vbits;
+				for (int g = tid; g < ng; g += NT) {
+					float4 const y = reinterpret_cast<float4 const *>(sdata)[g];
+					float const ye[4] = { y.x, y.y, y.z, y.w };
+					float re[4];
+#pragma unroll
+					for (int e = 0; e < 4; ++e) {
+						double const z = zg + static_cast<double>(e);
+						double acc = cz[K - 1];
+#pragma unroll
+						for (int k = K - 2; k >= 0; --k) {
+							acc = fma(acc, z, cz[k]);
+						}
+						float const mf = static_cast<float>(acc);
+						float const r = __fsub_rn(ye[e], mf);
+						re[e] = r;
+						if (vb & (1u << e)) {
+							double const rd = static_cast<double>(r);
+							sum += rd;
+							sq = fma(rd, rd, sq);
+						}
+					}
+					reinterpret_cast<float4 *>(sres)[g] = make_float4(re[0], re[1], re[2], re[3]);
+					zg += static_cast<double>(4 * NT);
+					vb >>= 4;
+				}
+			}
+			int c = warp_sum(__popc(vbits));
+			sum = warp_sum(sum);
+			sq = warp_sum(sq);
+			int const buf = iter & 1;
+			if (lane == 0) {
+				sh.stat[buf][warp][0] = static_cast<double>(c);
+				sh.stat[buf][warp][1] = sum;
+				sh.stat[buf][warp][2] = sq;
+			}
+			__syncthreads();
+			double cd = 0.0;
+			sum = 0.0;
+			sq = 0.0;
+#pragma unroll
+			for (int w = 0; w < NW; ++w) {
+				cd += sh.stat[buf][w][0];
+				sum += sh.stat[buf][w][1];
+				sq += sh.stat[buf][w][2];
+			}
+			c = static_cast<int>(cd);
+			ClipThresholds const th = make_thresholds(c, sum, sq, clip);
+			rms_d = th.rms;
+			if (iter == p.num_fitting_max) {
+				break;
+			}
+			// pass B: clip. The last channel is never examined (baseline.cc:1081-1096).
+			uint32_t clipped = 0u;
+			{
+				uint32_t vb = vbits;
+				int j4 = 0;
+				for (int g = tid; g < ng; g += NT, j4 += 4) {
+					float4 const r4 = reinterpret_cast<float4 const *>(sres)[g];
+					float const re[4] = { r4.x, r4.y, r4.z, r4.w };
+					uint32_t cl = 0u;
+#pragma unroll
+					for (int e = 0; e < 4; ++e) {
+						if (is_clipped(re[e], th.lower, th.upper)) {
+							cl |= (1u << e);
+						}
+					}
+					cl &= vb & 0xfu;
+					if (g == ng - 1) {
+						cl &= 0x7u;
+					}
+					clipped |= cl << j4;
+					vb >>= 4;
+				}
+			}
+			vbits &= ~clipped;
+			int const nclip = warp_sum(__popc(clipped));
+			__syncthreads(); // every warp is done with the residual: it becomes scratch
+			WarpBitMoments<K, NT, true>(clipped, zbase, pc.h, sdata, tid, scratch, sh.wtot[warp]);
+			if (lane == 0) {
+				sh.wclip[warp] = nclip;
+			}
+			__syncthreads();
+			if (warp == 0) {
+				int num_clipped = 0;
+#pragma unroll
+				for (int w = 0; w < NW; ++w) {
+					num_clipped += sh.wclip[w];
+				}
+				if (num_clipped == 0) {
+					if (lane == 0) {
+						sh.exit_flag = 1;
+					}
+				} else {
+					if (lane < NV) {
+						double tot = 0.0;
+#pragma unroll
+						for (int w = 0; w < NW; ++w) {
+							tot += sh.wtot[w][lane];
+						}
+						if (lane < NS) {
+							sh.S[lane] -= tot;
+						} else {
+							sh.T[lane - NS] -= tot;
+						}
+					}
+					if (lane == 0) {
+						sh.exit_flag = 0;
+						sh.num_unmasked = c - num_clipped;
+					}
+					__syncwarp();
+					if (c - num_clipped >= K) {
+						WarpSolve<K, NT>(sh, pc);
+					}
+				}
+			}
+			__syncthreads();
+			if (sh.exit_flag) {
+				break;
+			}
+			num_unmasked = sh.num_unmasked;
+		}
+
+		// ---- final mask (bits -> bytes) ------------------------------------------------------------
+		uint32_t *gfmask = reinterpret_cast<uint32_t *>(p.final_mask + row * p.mask_stride);
+		{
+			uint32_t vb = vbits;
+			for (int g = tid; g < ng; g += NT) {
+				uint32_t const b = vb & 0xfu;
+				gfmask[g] = (b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21);
+				vb >>= 4;
+			}
+		}
+		if (failed) {
+			// the reference has already clipped final_mask in place (SURVEY A-13 ii)
+			if (tid == 0) {
+				p.status[row] = kStatusNG;
+				p.lsqfit_status[row] = kLsqNotEnoughData;
+				if (p.flags != nullptr) {
+					p.flags[row] = 2;
+				}
+			}
+			continue;
+		}
+		// ---- outputs (baseline.cc:1310-1328) ---------------------------------------------------
+		// The residual in shared memory is intact here: the reduction scratch that aliases it
+		// is only written by a warp that clipped something, and then another fit follows.
+		bool const residual_dirty = false;
+		if (p.residual != nullptr || p.best_fit != nullptr) {
+			float4 *outr = p.residual ? reinterpret_cast<float4 *>(p.residual + row * p.data_stride) :
+					nullptr;
+			float4 *outb = p.best_fit ? reinterpret_cast<float4 *>(p.best_fit + row * p.data_stride) :
+					nullptr;
+			if (outb == nullptr && !residual_dirty) {
+				for (int g = tid; g < ng; g += NT) {
+					outr[g] = reinterpret_cast<float4 const *>(sres)[g];
+				}
+			} else {
+				double cz[K];
+#pragma unroll
+				for (int k = 0; k < K; ++k) {
+					cz[k] = sh.cz[k];
+				}
+				double zg = zbase;
+				for (int g = tid; g < ng; g += NT) {
+					float4 const y = reinterpret_cast<float4 const *>(sdata)[g];
+					float const ye[4] = { y.x, y.y, y.z, y.w };
+					float me[4], re[4];
+#pragma unroll
+					for (int e = 0; e < 4; ++e) {
+						double const z = zg + static_cast<double>(e);
+						double acc = cz[K - 1];
+#pragma unroll
+						for (int k = K - 2; k >= 0; --k) {
+							acc = fma(acc, z, cz[k]);
+						}
+						me[e] = static_cast<float>(acc);
+						re[e] = __fsub_rn(ye[e], me[e]);
+					}
+					if (outb != nullptr) {
+						outb[g] = make_float4(me[0], me[1], me[2], me[3]);
+					}
+					if (outr != nullptr) {
+						outr[g] = make_float4(re[0], re[1], re[2], re[3]);
+					}
+					zg += static_cast<double>(4 * NT);
+				}
+			}
+		}
+		if (p.coeff != nullptr && tid < K) {
+			p.coeff[row * K + tid] = sh.cx[tid] / pc.factor[tid];
+		}
+		if (tid == 0) {
+			p.rms[row] = static_cast<float>(rms_d);
+			p.status[row] = kStatusOK;
+			p.lsqfit_status[row] = kLsqOK;
+			if (p.flags != nullptr) {
+				p.flags[row] = 3;
+			}
+		}
+	}
+}
+
+template<int K, int NT>
+size_t PolySharedBytes(int n) {
+	return SharedOffset<K, NT>(n) + sizeof(Shared<K, NT>) + 16;
+}
+
+PolyConst const &GetPolyConst(int n) {
+	static std::mutex mu;
+	static std::map<int, PolyConst> cache;
+	std::lock_guard<std::mutex> lock(mu);
+	auto it = cache.find(n);
+	if (it != cache.end()) {
+		return it->second;
+	}
+	PolyConst pc;
+	double const max_x = static_cast<double>(n - 1);
+	pc.h = 1.0 / max_x;
+	long double hp = 1.0L;
+	for (int k = 0; k < kMaxMoments; ++k) {
+		pc.hpow[k] = static_cast<double>(hp);
+		hp *= static_cast<long double>(pc.h);
+	}
+	// sum_i x_i^k with x_i = fl(i*h) exactly as the device forms it, Kahan-accumulated in
+	// extended precision so that the constant is correctly rounded to double
+	long double acc[kMaxMoments];
+	long double comp[kMaxMoments];
+	for (int k = 0; k < kMaxMoments; ++k) {
+		acc[k] = 0.0L;
+		comp[k] = 0.0L;
+	}
+	for (int i = 0; i < n; ++i) {
+		double const x = static_cast<double>(i) * pc.h;
+		long double pw = 1.0L;
+		for (int k = 0; k < kMaxMoments; ++k) {
+			long double const yk = pw - comp[k];
+			long double const tk = acc[k] + yk;
+			comp[k] = (tk - acc[k]) - yk;
+			acc[k] = tk;
+			pw *= static_cast<long double>(x);
+		}
+	}
+	for (int k = 0; k < kMaxMoments; ++k) {
+		pc.s_all[k] = static_cast<double>(acc[k]);
+	}
+	double factor = 1.0;
+	for (int k = 0; k < kMaxPolyK; ++k) {
+		pc.factor[k] = factor;
+		factor *= max_x;
+	}
+	return cache.emplace(n, pc).first->second;
+}
+
+template<int K, int NT>
+cudaError_t LaunchKN(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
+	size_t const smem = PolySharedBytes<K, NT>(p.n);
+	static int per_sm_cache_n = -1;
+	static int per_sm_cache = 0;
+	cudaError_t err = cudaFuncSetAttribute(PolyFitKernel<K, NT>,
+			cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+	if (err != cudaSuccess) {
+		return err;
+	}
+	int per_sm = per_sm_cache;
+	if (per_sm_cache_n != p.n) {
+		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, PolyFitKernel<K, NT>, NT, smem);
+		if (err != cudaSuccess) {
+			return err;
+		}
+		per_sm_cache = per_sm;
+		per_sm_cache_n = p.n;
+	}
+	if (per_sm < 1) {
+		return cudaErrorInvalidConfiguration;
+	}
+	size_t grid = static_cast<size_t>(num_sms) * per_sm;
+	if (grid > p.num_spectra) {
+		grid = p.num_spectra;
+	}
+	PolyFitKernel<K, NT><<<static_cast<unsigned>(grid), NT, smem, stream>>>(p, GetPolyConst(p.n));
+	return cudaGetLastError();
+}
+
+template<int K>
+cudaError_t LaunchK(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
+	if (p.n <= 32 * 128) {
+		return LaunchKN<K, 128>(p, num_sms, stream);
+	}
+	return LaunchKN<K, 256>(p, num_sms, stream);
+}
+
+} // namespace
+
+bool PolyFastSupported(size_t n, size_t K, size_t data_stride, size_t mask_stride, void const *data,
+		void const *mask, void const *best_fit, void const *residual, void const *final_mask) {
+	if (K < 1 || K > static_cast<size_t>(kMaxPolyK)) {
+		return false;
+	}
+	if (n < 16 || n % 4 != 0 || n > 32 * 256 || n < K) {
+		return false;
+	}
+	if (data_stride % 4 != 0 || mask_stride % 4 != 0) {
+		return false;
+	}
+	auto a16 = [](void const *q) {return q == nullptr || (reinterpret_cast<uintptr_t>(q) % 16) == 0;};
+	auto a4 = [](void const *q) {return (reinterpret_cast<uintptr_t>(q) % 4) == 0;};
+	return a16(data) && a16(best_fit) && a16(residual) && a4(mask) && a4(final_mask);
+}
+
+cudaError_t LaunchPolyFit(PolyFitParams const &p, int num_sms, cudaStream_t stream, int *launches) {
+	*launches += 1;
+	switch (p.K) {
+	case 1:
+		return LaunchK<1>(p, num_sms, stream);
+	case 2:
+		return LaunchK<2>(p, num_sms, stream);
+	case 3:
+		return LaunchK<3>(p, num_sms, stream);
+	case 4:
+		return LaunchK<4>(p, num_sms, stream);
+	case 5:
+		return LaunchK<5>(p, num_sms, stream);
+	case 6:
+		return LaunchK<6>(p, num_sms, stream);
+	case 7:
+		return LaunchK<7>(p, num_sms, stream);
+	case 8:
+		return LaunchK<8>(p, num_sms, stream);
+	default:
+		return cudaErrorInvalidValue;
+	}
+}
+
+} // namespace sakura_b200
