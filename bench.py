@@ -1,0 +1,434 @@
+#!/usr/bin/env python
+"""Headline benchmark: masked LSQ baseline fit with sigma-clipping (BASELINE.json north_star).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A "step" is ONE pass of the hot path over the whole synthetic batch resident in HBM:
+one call of sakura_LSQFitPolynomialFloatBatchDevice = one launch of the fit kernel.
+Workload (BASELINE.json configs[1]): 1,048,576 spectra x 4,096 channels float32 + bool mask,
+polynomial order 5, num_fitting_max = 5 clip iterations at 3 sigma; outputs coeff, residual,
+final_mask, rms, status.  The 3-iteration figure named in the metric string is reported
+next to it under "also".  Rows are independent: with N ranks every rank fits its own
+1M-row shard (weak scaling), no data-path collective; timing is the max over ranks.
+
+`--impl reference` times the reference's own CPU code (oracle/_ref, built from
+/root/reference by oracle/Makefile; falls back to the C restatement) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+METRIC = "baseline-fit spectra/s (4096ch, poly-5, 3 clip iters); % of HBM roofline"
+UNIT = "spectra/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=1 << 20, help="spectra per GPU")
+    ap.add_argument("--nchan", type=int, default=4096)
+    ap.add_argument("--order", type=int, default=5)
+    ap.add_argument("--nfit", type=int, default=5, help="num_fitting_max of the headline value")
+    ap.add_argument("--clip", type=float, default=3.0)
+    ap.add_argument("--e2e-rows", type=int, default=1 << 18, help="spectra per e2e step (host buffers)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--cpu-rows", type=int, default=1 << 16, help="spectra in the CPU sample")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-also", action="store_true")
+    return ap.parse_args()
+
+
+def bytes_per_spectrum(n: int, ncoeff: int, residual: bool = True) -> int:
+    """Algorithmic HBM bytes of one whole fit: data + mask in, final_mask
+    (+ residual) + coeff + rms + status out; independent of the iteration count."""
+    return n * 4 + n + n + (n * 4 if residual else 0) + 8 * ncoeff + 4 + 4
+
+
+def measured_peak_gbs():
+    path = os.path.join(HERE, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)),
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------- synthetic data
+def generate_on_device(torch, rows: int, n: int, seed: int, device):
+    """Synthetic spectra of SURVEY 8(d) generated on the GPU (quintic continuum, Gaussian
+    emission lines, single-channel spikes, N(0,1) noise; edges + 2 % random flags + one flagged
+    block).  Returns (data float32 [rows, n], mask bool [rows, n])."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    data = torch.empty(rows, n, dtype=torch.float32, device=device)
+    mask = torch.empty(rows, n, dtype=torch.bool, device=device)
+    x = torch.linspace(0.0, 1.0, n, dtype=torch.float64, device=device)
+    chan = torch.arange(n, dtype=torch.float32, device=device)[None, :]
+    step = 16384
+    for r0 in range(0, rows, step):
+        r = min(step, rows - r0)
+        co = (torch.rand(r, 6, dtype=torch.float64, device=device, generator=g) - 0.5) * 10.0
+        y = torch.zeros(r, n, dtype=torch.float64, device=device)
+        for k in range(5, -1, -1):
+            y = y * x + co[:, k:k + 1]
+        y = y.float()
+        y += torch.randn(r, n, dtype=torch.float32, device=device, generator=g)
+        nl = torch.randint(0, 4, (r, 1), device=device, generator=g)
+        for j in range(3):
+            peak = 5.0 + 45.0 * torch.rand(r, 1, device=device, generator=g)
+            fwhm = 4.0 + 60.0 * torch.rand(r, 1, device=device, generator=g)
+            cen = (n - 1.0) * torch.rand(r, 1, device=device, generator=g)
+            sig = fwhm / 2.354820045
+            y += torch.where(nl > j, peak * torch.exp(-0.5 * ((chan - cen) / sig) ** 2),
+                             torch.zeros((), device=device))
+        ns = torch.randint(0, 9, (r,), device=device, generator=g)
+        rows_idx = torch.arange(r, device=device)
+        for j in range(8):
+            pos = torch.randint(0, n, (r,), device=device, generator=g)
+            amp = (10.0 + 90.0 * torch.rand(r, device=device, generator=g)) * \
+                (torch.randint(0, 2, (r,), device=device, generator=g).float() * 2.0 - 1.0)
+            y[rows_idx, pos] += torch.where(ns > j, amp, torch.zeros((), device=device))
+        data[r0:r0 + r] = y
+        m = torch.rand(r, n, device=device, generator=g) >= 0.02
+        m[:, :32] = False
+        m[:, n - 32:] = False
+        blk = torch.randint(0, 257, (r, 1), device=device, generator=g)
+        start = torch.randint(0, n, (r, 1), device=device, generator=g)
+        ci = torch.arange(n, device=device)[None, :]
+        m &= ~((ci >= start) & (ci < start + blk))
+        mask[r0:r0 + r] = m
+        del y, m
+    return data, mask
+
+
+def generate_on_host(rows: int, n: int, seed: int):
+    from sakura_b200 import synth
+    return synth.make_spectra(rows, n, seed=seed)
+
+
+# ----------------------------------------------------------------------------- reference arm
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle.refbind import Oracle
+    try:
+        ora = Oracle()
+    except OSError as exc:
+        print(json.dumps({"impl": "reference", "unavailable": str(exc).splitlines()[0]}))
+        return
+    n, K = args.nchan, args.order + 1
+    rows = min(args.cpu_rows, args.rows)
+    data, mask = generate_on_host(rows, n, seed=20240611)
+    threads = ora.max_threads()
+    for _ in range(max(args.warmup, 1)):
+        ora.lsqfit_polynomial_batch(args.order, data[:4096], mask[:4096], args.clip, args.nfit)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        ora.lsqfit_polynomial_batch(args.order, data, mask, args.clip, args.nfit)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = rows / dt
+    sample = (f"{rows} spectra x {n} ch of the same synthetic workload per step, "
+              f"OpenMP over rows, one context per thread")
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "impl": "reference",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, rows_per_step=rows),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": ora.kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(args, rows_per_step=None) -> dict:
+    return {
+        "workload": ("BASELINE configs[1]: ALMA-TP-like spectra x 4096 ch float32 + bool mask, "
+                     "sakura_LSQFitPolynomialFloat semantics, polynomial order 5, 5 clip iterations "
+                     "(num_fitting_max=5) at 3 sigma; outputs coeff+residual+final_mask+rms+status"),
+        "spectra_per_gpu": args.rows if rows_per_step is None else rows_per_step,
+        "num_data": args.nchan, "order": args.order, "num_fitting_max": args.nfit,
+        "clip_threshold_sigma": args.clip,
+        "l2": "inputs (20 GiB per step) far exceed the 126 MB L2; no explicit flush needed",
+        "parallelism": "rows sharded per GPU, no collective",
+    }
+
+
+# ----------------------------------------------------------------------------- our arm
+def run_ours(args) -> None:
+    import torch
+    from sakura_b200.capi import SakuraLib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist_mod.init_process_group("nccl", device_id=device)
+        dist = dist_mod
+
+    lib = SakuraLib()
+    n, order, K = args.nchan, args.order, args.order + 1
+    rows = args.rows
+    data, mask = generate_on_device(torch, rows, n, seed=20240611 + rank, device=device)
+    coeff = torch.empty(rows, K, dtype=torch.float64, device=device)
+    resid = torch.empty(rows, n, dtype=torch.float32, device=device)
+    fmask = torch.empty(rows, n, dtype=torch.bool, device=device)
+    rms = torch.empty(rows, dtype=torch.float32, device=device)
+    status = torch.empty(rows, dtype=torch.int32, device=device)
+    lsq = torch.empty(rows, dtype=torch.int32, device=device)
+    st, ctx = lib.create_polynomial_context(order, n)
+    assert st == 0
+    stream = torch.cuda.current_stream(device)
+
+    def step(nfit):
+        rc = lib.lib.sakura_LSQFitPolynomialFloatBatchDevice(
+            ctx, order, rows, n, data.data_ptr(), n, mask.data_ptr(), n, args.clip, nfit, K,
+            coeff.data_ptr(), None, resid.data_ptr(), fmask.data_ptr(), rms.data_ptr(),
+            status.data_ptr(), lsq.data_ptr(), stream.cuda_stream)
+        if rc != 0:
+            raise RuntimeError(f"fit call failed: {rc} {lib.last_error()}")
+
+    def barrier():
+        torch.cuda.synchronize(device)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(device)
+
+    def timed(nfit, steps, warmup):
+        for _ in range(warmup):
+            step(nfit)
+        barrier()
+        launches0 = lib.kernel_launch_count()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step(nfit)
+        e1.record(stream)
+        barrier()
+        ms = e0.elapsed_time(e1) / steps
+        launches = lib.kernel_launch_count() - launches0
+        if dist is not None:
+            t = torch.tensor([ms], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_step, launches = timed(args.nfit, args.steps, max(args.warmup, 3))
+    clocks = sampler.stop() if rank == 0 else None
+    kernel_name = lib.last_kernel_name()
+    ok_rows = int((status == 0).sum().item())
+    mean_clipped = float((mask & ~fmask).sum(dim=1).float().mean().item())
+    # snapshot of the headline run's results for the parity check against the CPU sample
+    snap_rows = min(args.cpu_rows, rows)
+    snap_fmask = fmask[:snap_rows].cpu().numpy().copy()
+    snap_status = status[:snap_rows].cpu().numpy().copy()
+    snap_rms = rms[:snap_rows].cpu().numpy().copy()
+
+    also = {}
+    if not args.no_also and args.nfit != 3:
+        ms3, _ = timed(3, max(args.steps // 2, 2), 3)
+        also["num_fitting_max_3"] = {
+            "value": world * rows / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3,
+            "hbm_frac": rows * bytes_per_spectrum(n, K) / (ms3 * 1e-3) / 1e9 / measured_peak_gbs()[0]}
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region --------------
+    e2e = None
+    if not args.no_e2e:
+        er = min(args.e2e_rows, rows)
+        h_data = torch.empty(er, n, dtype=torch.float32, pin_memory=True)
+        h_mask = torch.empty(er, n, dtype=torch.bool, pin_memory=True)
+        h_data.copy_(data[:er])
+        h_mask.copy_(mask[:er])
+        h_coeff = torch.empty(er, K, dtype=torch.float64, pin_memory=True)
+        h_resid = torch.empty(er, n, dtype=torch.float32, pin_memory=True)
+        h_fmask = torch.empty(er, n, dtype=torch.bool, pin_memory=True)
+        h_rms = torch.empty(er, dtype=torch.float32, pin_memory=True)
+        h_status = torch.empty(er, dtype=torch.int32, pin_memory=True)
+        h_lsq = torch.empty(er, dtype=torch.int32, pin_memory=True)
+        st2, ctx2 = lib.create_polynomial_context(order, n)
+        assert st2 == 0
+
+        def e2e_step():
+            rc = lib.lib.sakura_LSQFitPolynomialFloatBatch(
+                ctx2, order, er, n, h_data.data_ptr(), n, h_mask.data_ptr(), n, args.clip, args.nfit,
+                K, h_coeff.data_ptr(), None, h_resid.data_ptr(), h_fmask.data_ptr(), h_rms.data_ptr(),
+                h_status.data_ptr(), h_lsq.data_ptr())
+            if rc != 0:
+                raise RuntimeError(f"e2e fit call failed: {rc} {lib.last_error()}")
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize(device)
+        dt = (time.perf_counter() - t0) / args.e2e_steps
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": world * er / dt, "unit": UNIT,
+               "h2d_bytes_per_step": er * (n * 4 + n),
+               "d2h_bytes_per_step": er * (n * 4 + n + 8 * K + 4 + 4 + 4),
+               "spectra_per_step": er, "ms_per_step": dt * 1e3,
+               "api": "sakura_LSQFitPolynomialFloatBatch (pinned host buffers, 3-slot copy/compute pipeline)",
+               "rows_ok_match_device_path": bool(torch.equal(h_status, status[:er].cpu()))}
+        lib.destroy_context(ctx2)
+        del h_data, h_mask, h_resid, h_fmask
+
+    # ---- CPU baseline: the reference's own code on this box's host cores ---------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        try:
+            from oracle.refbind import Oracle
+            ora = Oracle()
+            cr = min(args.cpu_rows, rows)
+            cd = data[:cr].cpu().numpy()
+            cm = mask[:cr].cpu().numpy()
+            ora.lsqfit_polynomial_batch(order, cd[:2048], cm[:2048], args.clip, args.nfit)
+            best = None
+            for _ in range(2):
+                t0 = time.perf_counter()
+                o = ora.lsqfit_polynomial_batch(order, cd, cm, args.clip, args.nfit)
+                dt = time.perf_counter() - t0
+                best = dt if best is None else min(best, dt)
+            gm = fmask[:cr].cpu().numpy()
+            good = o["status"] == 0
+            cpu = {"value": cr / best, "unit": UNIT, "cores": ora.max_threads(), "kind": ora.kind,
+                   "sample": f"first {cr} spectra of the same workload, OpenMP over rows, best of 2",
+                   "final_mask_mismatches_vs_gpu": int((gm[good] != o["final_mask"][good]).sum()),
+                   "status_equal": bool(np.array_equal(o["status"], status[:cr].cpu().numpy()))}
+        except OSError as exc:
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(exc)}
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        bps = bytes_per_spectrum(n, K)
+        achieved = rows * bps / (ms_step * 1e-3) / 1e9
+        traffic = None
+        tpath = os.path.join(HERE, "profiles", "traffic_per_launch.json")
+        if os.path.exists(tpath):
+            try:
+                with open(tpath) as fh:
+                    traffic = json.load(fh)
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": world * rows / (ms_step * 1e-3), "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "clocks": clocks,
+            "e2e": e2e,
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "kernel": kernel_name, "bytes_per_spectrum": bps,
+                         "spectra_per_launch": rows},
+            "cpu_baseline": cpu,
+            "also": also,
+            "check": {"rows_ok": ok_rows, "rows": rows, "mean_clipped_channels": mean_clipped},
+        }
+        print(json.dumps(line))
+    lib.destroy_context(ctx)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -130,6 +130,30 @@ sakura_Status CurrentDevice(DeviceInfo *info) {
 	return sakura_Status_kOK;
 }
 
+constexpr int kPipelineSlots = 3;
+
+/** One stage of the host-buffer pipeline: a stream and the device buffers of one chunk. */
+struct PipelineSlot {
+	cudaStream_t stream = nullptr;
+	DeviceBuffer data, mask, coeff, best_fit, residual, final_mask, small;
+	std::vector<int32_t> h_flags;
+	size_t row0 = 0;
+	size_t rows = 0; // non-zero while a chunk is in flight in this slot
+	void Release() {
+		data.Release();
+		mask.Release();
+		coeff.Release();
+		best_fit.Release();
+		residual.Release();
+		final_mask.Release();
+		small.Release();
+		if (stream != nullptr) {
+			cudaStreamDestroy(stream);
+			stream = nullptr;
+		}
+	}
+};
+
 } // namespace
 
 // ---------------------------------------------------------------- context
@@ -153,6 +177,7 @@ struct sakura_LSQFitContextFloat {
 	DeviceBuffer s_data, s_mask, s_coeff, s_best_fit, s_residual, s_final_mask, s_rms,
 			s_status, s_lsq, s_flags, s_boundary;
 	std::vector<int32_t> *h_flags;
+	PipelineSlot *slots; // kPipelineSlots entries, created on first pipelined call
 };
 
 namespace {
@@ -203,6 +228,11 @@ void ReleaseDeviceState(Context *c) {
 		c->s_lsq.Release();
 		c->s_flags.Release();
 		c->s_boundary.Release();
+		if (c->slots != nullptr) {
+			for (int s = 0; s < kPipelineSlots; ++s) {
+				c->slots[s].Release();
+			}
+		}
 		if (prev != c->device) {
 			cudaSetDevice(prev);
 		}
@@ -234,6 +264,7 @@ sakura_Status CreateContext(int type, uint16_t param, size_t num_data, Context *
 	c->num_lsq_bases_max = lsq_max;
 	c->device = -1;
 	c->h_flags = nullptr;
+	c->slots = nullptr;
 	c->h_basis = static_cast<double *>(g_allocator(sizeof(double) * num_bases * num_data));
 	if (c->h_basis == nullptr) {
 		c->~Context();
@@ -412,7 +443,189 @@ struct HostFitArgs {
 	size_t *boundary;
 };
 
+sakura_Status RunHostBatchSerial(Context *c, FitCall f, HostFitArgs const &h);
+
+// Pipelined variant for the polynomial hot path: the batch is cut into chunks that cycle
+// through kPipelineSlots (stream, device buffers) slots, so that the host->device copy of
+// chunk i+1, the kernel of chunk i and the device->host copy of chunk i-1 overlap on the
+// copy engines and the SMs. With pinned host buffers every copy is truly asynchronous.
 sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
+	if (f.num_spectra == 0) {
+		return sakura_Status_kOK;
+	}
+	size_t const n = f.num_data;
+	size_t const R = f.num_spectra;
+	size_t const dstride = RoundUp(n, 32);
+	bool const fast = (f.type == kFitPolynomial) && PolyFastSupported(n, f.K, dstride, dstride,
+			nullptr, nullptr, nullptr, nullptr, nullptr);
+	size_t chunk_rows = (static_cast<size_t>(96) << 20) / (dstride * sizeof(float));
+	if (chunk_rows < 1) {
+		chunk_rows = 1;
+	}
+	if (!fast || R <= chunk_rows) {
+		return RunHostBatchSerial(c, f, h);
+	}
+	DeviceInfo info;
+	sakura_Status st = CurrentDevice(&info);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	if (c->device >= 0 && c->device != info.device) {
+		ReleaseDeviceState(c);
+	}
+	c->device = info.device;
+	if (c->slots == nullptr) {
+		c->slots = new PipelineSlot[kPipelineSlots];
+	}
+	size_t const hds = f.data_stride, hms = f.mask_stride;
+	size_t const num_chunks = (R + chunk_rows - 1) / chunk_rows;
+	for (int s = 0; s < kPipelineSlots; ++s) {
+		PipelineSlot &sl = c->slots[s];
+		if (sl.stream == nullptr) {
+			CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+		}
+		CUDA_TRY(sl.data.Reserve(chunk_rows * dstride * sizeof(float)));
+		CUDA_TRY(sl.mask.Reserve(chunk_rows * dstride));
+		CUDA_TRY(sl.final_mask.Reserve(chunk_rows * dstride));
+		CUDA_TRY(sl.small.Reserve(chunk_rows * (sizeof(float) + 3 * sizeof(int32_t))));
+		if (h.coeff != nullptr) {
+			CUDA_TRY(sl.coeff.Reserve(chunk_rows * f.coeff_stride * sizeof(double)));
+		}
+		if (h.best_fit != nullptr) {
+			CUDA_TRY(sl.best_fit.Reserve(chunk_rows * dstride * sizeof(float)));
+		}
+		if (h.residual != nullptr) {
+			CUDA_TRY(sl.residual.Reserve(chunk_rows * dstride * sizeof(float)));
+		}
+		sl.h_flags.resize(chunk_rows);
+		sl.rows = 0;
+	}
+	auto finish = [&](PipelineSlot &sl) -> sakura_Status {
+		// flags of this slot's chunk are on the host once its stream has drained
+		CUDA_TRY(cudaStreamSynchronize(sl.stream));
+		size_t const r0 = sl.row0, rows = sl.rows;
+		float *d_rms = sl.small.As<float>();
+		bool all_published = true;
+		for (size_t r = 0; r < rows; ++r) {
+			if ((sl.h_flags[r] & 3) != 3) {
+				all_published = false;
+				break;
+			}
+		}
+		if (all_published) {
+			if (h.coeff != nullptr) {
+				CUDA_TRY(cudaMemcpyAsync(h.coeff + r0 * f.coeff_stride, sl.coeff.ptr,
+						rows * f.coeff_stride * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
+			}
+			if (h.best_fit != nullptr) {
+				CUDA_TRY(cudaMemcpy2DAsync(h.best_fit + r0 * hds, hds * sizeof(float), sl.best_fit.ptr,
+						dstride * sizeof(float), n * sizeof(float), rows, cudaMemcpyDeviceToHost,
+						sl.stream));
+			}
+			if (h.residual != nullptr) {
+				CUDA_TRY(cudaMemcpy2DAsync(h.residual + r0 * hds, hds * sizeof(float), sl.residual.ptr,
+						dstride * sizeof(float), n * sizeof(float), rows, cudaMemcpyDeviceToHost,
+						sl.stream));
+			}
+			CUDA_TRY(cudaMemcpy2DAsync(h.final_mask + r0 * hms, hms, sl.final_mask.ptr, dstride, n,
+					rows, cudaMemcpyDeviceToHost, sl.stream));
+			CUDA_TRY(cudaMemcpyAsync(h.rms + r0, d_rms, rows * sizeof(float), cudaMemcpyDeviceToHost,
+					sl.stream));
+		} else {
+			for (size_t r = 0; r < rows; ++r) {
+				int const fl = sl.h_flags[r];
+				if (fl & 1) {
+					if (h.coeff != nullptr) {
+						CUDA_TRY(cudaMemcpyAsync(h.coeff + (r0 + r) * f.coeff_stride,
+								sl.coeff.As<double>() + r * f.coeff_stride,
+								f.coeff_stride * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
+					}
+					if (h.best_fit != nullptr) {
+						CUDA_TRY(cudaMemcpyAsync(h.best_fit + (r0 + r) * hds,
+								sl.best_fit.As<float>() + r * dstride, n * sizeof(float),
+								cudaMemcpyDeviceToHost, sl.stream));
+					}
+					if (h.residual != nullptr) {
+						CUDA_TRY(cudaMemcpyAsync(h.residual + (r0 + r) * hds,
+								sl.residual.As<float>() + r * dstride, n * sizeof(float),
+								cudaMemcpyDeviceToHost, sl.stream));
+					}
+					CUDA_TRY(cudaMemcpyAsync(h.rms + r0 + r, d_rms + r, sizeof(float),
+							cudaMemcpyDeviceToHost, sl.stream));
+				}
+				if (fl & 2) {
+					CUDA_TRY(cudaMemcpyAsync(h.final_mask + (r0 + r) * hms,
+							sl.final_mask.As<uint8_t>() + r * dstride, n, cudaMemcpyDeviceToHost,
+							sl.stream));
+				}
+			}
+		}
+		sl.rows = 0;
+		return sakura_Status_kOK;
+	};
+	for (size_t ci = 0; ci < num_chunks; ++ci) {
+		PipelineSlot &sl = c->slots[ci % kPipelineSlots];
+		if (sl.rows != 0) {
+			st = finish(sl);
+			if (st != sakura_Status_kOK) {
+				return st;
+			}
+		}
+		size_t const r0 = ci * chunk_rows;
+		size_t const rows = (r0 + chunk_rows <= R) ? chunk_rows : (R - r0);
+		sl.row0 = r0;
+		sl.rows = rows;
+		float *d_rms = sl.small.As<float>();
+		int32_t *d_status = reinterpret_cast<int32_t *>(d_rms + chunk_rows);
+		int32_t *d_lsq = d_status + chunk_rows;
+		int32_t *d_flags = d_lsq + chunk_rows;
+		CUDA_TRY(cudaMemcpy2DAsync(sl.data.ptr, dstride * sizeof(float), h.data + r0 * hds,
+				hds * sizeof(float), n * sizeof(float), rows, cudaMemcpyHostToDevice, sl.stream));
+		CUDA_TRY(cudaMemcpy2DAsync(sl.mask.ptr, dstride, h.mask + r0 * hms, hms, n, rows,
+				cudaMemcpyHostToDevice, sl.stream));
+		CUDA_TRY(cudaMemsetAsync(d_flags, 0, rows * sizeof(int32_t), sl.stream));
+		FitCall fc = f;
+		fc.num_spectra = rows;
+		fc.data = sl.data.As<float>();
+		fc.mask = sl.mask.As<uint8_t>();
+		fc.data_stride = dstride;
+		fc.mask_stride = dstride;
+		fc.coeff = h.coeff ? sl.coeff.As<double>() : nullptr;
+		fc.best_fit = h.best_fit ? sl.best_fit.As<float>() : nullptr;
+		fc.residual = h.residual ? sl.residual.As<float>() : nullptr;
+		fc.final_mask = sl.final_mask.As<uint8_t>();
+		fc.rms = d_rms;
+		fc.status = d_status;
+		fc.lsq = d_lsq;
+		fc.flags = d_flags;
+		fc.boundary = nullptr;
+		st = LaunchFit(c, fc, sl.stream);
+		if (st != sakura_Status_kOK) {
+			return st;
+		}
+		CUDA_TRY(cudaMemcpyAsync(h.status + r0, d_status, rows * sizeof(int32_t),
+				cudaMemcpyDeviceToHost, sl.stream));
+		CUDA_TRY(cudaMemcpyAsync(h.lsq + r0, d_lsq, rows * sizeof(int32_t), cudaMemcpyDeviceToHost,
+				sl.stream));
+		CUDA_TRY(cudaMemcpyAsync(sl.h_flags.data(), d_flags, rows * sizeof(int32_t),
+				cudaMemcpyDeviceToHost, sl.stream));
+	}
+	for (size_t k = 0; k < static_cast<size_t>(kPipelineSlots); ++k) {
+		PipelineSlot &sl = c->slots[(num_chunks + k) % kPipelineSlots];
+		if (sl.rows != 0) {
+			st = finish(sl);
+			if (st != sakura_Status_kOK) {
+				return st;
+			}
+		}
+	}
+	for (int s = 0; s < kPipelineSlots; ++s) {
+		CUDA_TRY(cudaStreamSynchronize(c->slots[s].stream));
+	}
+	return sakura_Status_kOK;
+}
+
+sakura_Status RunHostBatchSerial(Context *c, FitCall f, HostFitArgs const &h) {
 	if (f.num_spectra == 0) {
 		return sakura_Status_kOK;
 	}
@@ -738,6 +951,8 @@ sakura_Status sakura_DestroyLSQFitContextFloat(struct sakura_LSQFitContextFloat 
 	CHECK_ARGS(context->magic == kContextMagic);
 	ReleaseDeviceState(context);
 	delete context->h_flags;
+	delete[] context->slots;
+	context->slots = nullptr;
 	context->h_flags = nullptr;
 	if (context->h_basis != nullptr) {
 		g_deallocator(context->h_basis);
