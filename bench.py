@@ -358,7 +358,10 @@ def run_ours(args) -> None:
                "d2h_bytes_per_step": er * (n * 4 + n + 8 * K + 4 + 4 + 4),
                "spectra_per_step": er, "ms_per_step": dt * 1e3,
                "api": "sakura_LSQFitPolynomialFloatBatch (pinned host buffers, 3-slot copy/compute pipeline)",
-               "rows_ok_match_device_path": bool(torch.equal(h_status, status[:er].cpu()))}
+               "status_match_device_path": bool(np.array_equal(h_status.numpy()[:snap_rows],
+                                                                 snap_status[:er])),
+               "final_mask_match_device_path": bool(np.array_equal(h_fmask.numpy()[:snap_rows],
+                                                                     snap_fmask[:er]))}
         lib.destroy_context(ctx2)
         del h_data, h_mask, h_resid, h_fmask
 
@@ -378,12 +381,14 @@ def run_ours(args) -> None:
                 o = ora.lsqfit_polynomial_batch(order, cd, cm, args.clip, args.nfit)
                 dt = time.perf_counter() - t0
                 best = dt if best is None else min(best, dt)
-            gm = fmask[:cr].cpu().numpy()
             good = o["status"] == 0
             cpu = {"value": cr / best, "unit": UNIT, "cores": ora.max_threads(), "kind": ora.kind,
                    "sample": f"first {cr} spectra of the same workload, OpenMP over rows, best of 2",
-                   "final_mask_mismatches_vs_gpu": int((gm[good] != o["final_mask"][good]).sum()),
-                   "status_equal": bool(np.array_equal(o["status"], status[:cr].cpu().numpy()))}
+                   "final_mask_mismatches_vs_gpu": int((snap_fmask[good] != o["final_mask"][good]).sum()),
+                   "channels_compared": int(good.sum()) * n,
+                   "rms_max_rel_diff_vs_gpu": float(np.max(np.abs(snap_rms[good] - o["rms"][good])
+                                                           / np.abs(o["rms"][good]))),
+                   "status_equal": bool(np.array_equal(o["status"], snap_status))}
         except OSError as exc:
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "unavailable", "sample": str(exc)}
 
