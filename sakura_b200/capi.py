@@ -307,5 +307,9 @@ class SakuraLib:
         result = aligned_empty((1,), STAT_DTYPE)
         fn = (self.lib.sakura_ComputeAccurateStatisticsFloat if accurate
               else self.lib.sakura_ComputeStatisticsFloat)
-        st = fn(data.size, _ptr(data), _ptr(mask), _ptr(result))
+        n = data.size
+        if n == 0:  # numpy gives empty arrays arbitrary addresses; hand over aligned ones
+            data = aligned_empty(8, np.float32)
+            mask = aligned_empty(8, np.bool_)
+        st = fn(n, _ptr(data), _ptr(mask), _ptr(result))
         return st, result[0]

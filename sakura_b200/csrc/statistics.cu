@@ -23,16 +23,30 @@ struct Acc {
 	long long count;
 	double sum;
 	double sq;
+	double sum_lo; // low parts of the double-double accumulators
+	double sq_lo;
 	float mn;
 	float mx;
 	long long imn;
 	long long imx;
 };
 
+// (hi, lo) += (v, v_lo) with the rounding error of the high-part addition kept in lo
+// (Knuth two-sum): sums stay accurate to ~1e-32 relative whatever the order.
+__device__ __forceinline__ void two_sum_acc(double &hi, double &lo, double v, double v_lo) {
+	double const s = hi + v;
+	double const bb = s - hi;
+	double const err = (hi - (s - bb)) + (v - bb);
+	hi = s;
+	lo += err + v_lo;
+}
+
 __device__ __forceinline__ void acc_clear(Acc &a) {
 	a.count = 0;
 	a.sum = 0.0;
 	a.sq = 0.0;
+	a.sum_lo = 0.0;
+	a.sq_lo = 0.0;
 	a.mn = __int_as_float(0x7fc00000);
 	a.mx = __int_as_float(0x7fc00000);
 	a.imn = -1;
@@ -41,8 +55,8 @@ __device__ __forceinline__ void acc_clear(Acc &a) {
 
 __device__ __forceinline__ void acc_merge(Acc &a, Acc const &b) {
 	a.count += b.count;
-	a.sum += b.sum;
-	a.sq += b.sq;
+	two_sum_acc(a.sum, a.sum_lo, b.sum, b.sum_lo);
+	two_sum_acc(a.sq, a.sq_lo, b.sq, b.sq_lo);
 	if (b.imn >= 0 && (a.imn < 0 || b.mn < a.mn || (b.mn == a.mn && b.imn < a.imn))) {
 		a.mn = b.mn;
 		a.imn = b.imn;
@@ -58,6 +72,8 @@ __device__ __forceinline__ Acc acc_shfl_xor(Acc const &a, int o) {
 	b.count = __shfl_xor_sync(0xffffffffu, a.count, o);
 	b.sum = __shfl_xor_sync(0xffffffffu, a.sum, o);
 	b.sq = __shfl_xor_sync(0xffffffffu, a.sq, o);
+	b.sum_lo = __shfl_xor_sync(0xffffffffu, a.sum_lo, o);
+	b.sq_lo = __shfl_xor_sync(0xffffffffu, a.sq_lo, o);
 	b.mn = __shfl_xor_sync(0xffffffffu, a.mn, o);
 	b.mx = __shfl_xor_sync(0xffffffffu, a.mx, o);
 	b.imn = __shfl_xor_sync(0xffffffffu, a.imn, o);
@@ -67,8 +83,8 @@ __device__ __forceinline__ Acc acc_shfl_xor(Acc const &a, int o) {
 
 __device__ __forceinline__ void store_result(StatResult *r, Acc const &a) {
 	r->count = static_cast<unsigned long long>(a.count);
-	r->sum = a.sum;
-	r->square_sum = a.sq;
+	r->sum = a.sum + a.sum_lo;
+	r->square_sum = a.sq + a.sq_lo;
 	r->min = a.mn;
 	r->max = a.mx;
 	r->index_of_min = a.imn;
@@ -76,6 +92,7 @@ __device__ __forceinline__ void store_result(StatResult *r, Acc const &a) {
 }
 
 // One CTA reduces chunk `c` of row `r`: elements [c*chunk_len, min(n,(c+1)*chunk_len)).
+template<bool COMPENSATED>
 __global__ void __launch_bounds__(kStatThreads)
 StatsKernel(size_t num_rows, size_t n, size_t chunks, size_t chunk_len, float const *data,
 		size_t data_stride, uint8_t const *mask, size_t mask_stride, StatResult *result,
@@ -96,8 +113,13 @@ StatsKernel(size_t num_rows, size_t n, size_t chunks, size_t chunk_len, float co
 				float const v = d[i];
 				double const vd = static_cast<double>(v);
 				a.count += 1;
-				a.sum += vd;
-				a.sq = fma(vd, vd, a.sq);
+				if (COMPENSATED) {
+					two_sum_acc(a.sum, a.sum_lo, vd, 0.0);
+					two_sum_acc(a.sq, a.sq_lo, vd * vd, 0.0); // exact: 24-bit squared
+				} else {
+					a.sum += vd;
+					a.sq = fma(vd, vd, a.sq);
+				}
 				if (v == v) {
 					if (a.imn < 0 || v < a.mn) {
 						a.mn = v;
@@ -177,9 +199,17 @@ cudaError_t LaunchStats(size_t num_rows, size_t n, float const *data, size_t dat
 	if (grid > total) {
 		grid = total;
 	}
-	StatsKernel<<<static_cast<unsigned>(grid), kStatThreads, 0, stream>>>(num_rows, n, chunks,
-			chunk_len, data, data_stride, mask, mask_stride, result,
-			static_cast<Acc *>(partial_ws));
+	// long rows (the 1e8-element accuracy case of the reference's tests): double-double sums;
+	// short rows: plain FP64 per thread (<= a few hundred addends), double-double in the tree
+	if (chunks > 1) {
+		StatsKernel<true><<<static_cast<unsigned>(grid), kStatThreads, 0, stream>>>(num_rows, n,
+				chunks, chunk_len, data, data_stride, mask, mask_stride, result,
+				static_cast<Acc *>(partial_ws));
+	} else {
+		StatsKernel<false><<<static_cast<unsigned>(grid), kStatThreads, 0, stream>>>(num_rows, n,
+				chunks, chunk_len, data, data_stride, mask, mask_stride, result,
+				static_cast<Acc *>(partial_ws));
+	}
 	*launches += 1;
 	cudaError_t err = cudaGetLastError();
 	if (err != cudaSuccess || chunks == 1) {

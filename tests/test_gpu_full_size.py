@@ -12,7 +12,7 @@ import numpy as np
 import pytest
 
 from sakura_b200.capi import STATUS_OK
-from tests.parity import compare_fit
+from parity import compare_fit
 
 pytestmark = pytest.mark.gpu
 

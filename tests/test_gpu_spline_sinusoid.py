@@ -7,7 +7,7 @@ import pytest
 
 from sakura_b200 import synth
 from sakura_b200.capi import STATUS_NG, STATUS_OK, aligned_copy, aligned_empty
-from tests.parity import compare_fit
+from parity import compare_fit
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -28,7 +28,7 @@ def check_spline(g, o, data, clip):
     # reference itself differ by up to 1.8e-3 relative there, so parity is
     # gated on status / boundary / mask / rms / best_fit / residual and coefficients are bounded
     # against that spread.
-    reported = compare_fit(g, o, data, clip, check_coeff=False)
+    reported = compare_fit(g, o, data, clip, check_coeff=False, resid_atol=2e-5)
     good = o["status"] == STATUS_OK
     assert np.array_equal(g["boundary"][good], o["boundary"][good])
     gc, oc = g["coeff"][good], o["coeff"][good]
@@ -141,21 +141,24 @@ def test_subtract_functions(lib, oracle):
     reproduces the fit's residual (baseline.cc:1423-1501)."""
     n = 1024
     data, mask = synth.make_spectra(4, n, seed=81, ripple=True)
+    rows = [aligned_copy(data[r]) for r in range(4)]
+    out = aligned_empty(n, np.float32)
     st, ctx = lib.create_polynomial_context(5, n)
     g = lib.lsqfit_polynomial_batch(ctx, 5, data, mask, 3.0, 3)
-    out = aligned_empty(n, np.float32)
     for r in range(4):
-        rc = lib.lib.sakura_SubtractPolynomialFloat(ctx, n, aligned_copy(data[r]).ctypes.data, 6,
-                                                    aligned_copy(g["coeff"][r]).ctypes.data, out.ctypes.data)
+        co = aligned_copy(g["coeff"][r])
+        rc = lib.lib.sakura_SubtractPolynomialFloat(ctx, n, rows[r].ctypes.data, 6, co.ctypes.data,
+                                                    out.ctypes.data)
         assert rc == STATUS_OK
         assert np.allclose(out, g["residual"][r], rtol=1e-5, atol=2e-5)
     lib.destroy_context(ctx)
     st, ctx = lib.create_cubicspline_context(5, n)
     g = lib.lsqfit_cubicspline_batch(ctx, 5, data, mask, 3.0, 3)
     for r in range(4):
-        rc = lib.lib.sakura_SubtractCubicSplineFloat(ctx, n, aligned_copy(data[r]).ctypes.data, 5,
-                                                     aligned_copy(g["coeff"][r]).ctypes.data,
-                                                     aligned_copy(g["boundary"][r]).ctypes.data, out.ctypes.data)
+        co = aligned_copy(g["coeff"][r])
+        bd = aligned_copy(g["boundary"][r])
+        rc = lib.lib.sakura_SubtractCubicSplineFloat(ctx, n, rows[r].ctypes.data, 5, co.ctypes.data,
+                                                     bd.ctypes.data, out.ctypes.data)
         assert rc == STATUS_OK
         assert np.allclose(out, g["residual"][r], rtol=1e-5, atol=2e-5)
     lib.destroy_context(ctx)
@@ -163,8 +166,9 @@ def test_subtract_functions(lib, oracle):
     nw = aligned_copy(np.arange(5, dtype=np.uint64))
     g = lib.lsqfit_sinusoid_batch(ctx, list(range(5)), data, mask, 3.0, 3)
     for r in range(4):
-        rc = lib.lib.sakura_SubtractSinusoidFloat(ctx, n, aligned_copy(data[r]).ctypes.data, 5, nw.ctypes.data,
-                                                  9, aligned_copy(g["coeff"][r]).ctypes.data, out.ctypes.data)
+        co = aligned_copy(g["coeff"][r])
+        rc = lib.lib.sakura_SubtractSinusoidFloat(ctx, n, rows[r].ctypes.data, 5, nw.ctypes.data, 9,
+                                                  co.ctypes.data, out.ctypes.data)
         assert rc == STATUS_OK
         assert np.array_equal(out, g["residual"][r])
     lib.destroy_context(ctx)
