@@ -50,6 +50,13 @@ def compare_fit(g, o, data, clip, poly_rescale_n=None, coeff_rtol=1e-5, coeff_at
     exact_rows = good.copy()
     for r, _, _, _ in reported:
         exact_rows[r] = False  # a flipped channel legitimately perturbs that row's fit
+    # rows that failed keep their outputs untouched (NaN-prefilled by the bindings)
+    failed = ~good
+    if failed.any():
+        for key in ("coeff", "residual", "best_fit"):
+            if g.get(key) is not None:
+                assert np.all(np.isnan(g[key][failed])), key
+        assert np.all(np.isnan(g["rms"][failed]))
     if exact_rows.any():
         # 1e-6 relative; rows that interpolate their few valid channels have rms ~ float
         # rounding noise of the model, hence the ulp-of-data absolute floor
@@ -68,13 +75,27 @@ def compare_fit(g, o, data, clip, poly_rescale_n=None, coeff_rtol=1e-5, coeff_at
             diff = np.abs(got.astype(np.float64) - ref.astype(np.float64))
             # a NaN sitting under the mask propagates to the same residual channel on both sides
             both_nan = np.isnan(got) & np.isnan(ref)
-            assert np.all((diff <= tol) | both_nan), (key, float(np.nanmax(diff)))
+            # Channels that constrain the fit (final_mask true) are always compared. Flagged
+            # channels are compared too unless the fitted model runs away across a flagged gap
+            # (|model| > 10x the range of the valid data): there the curve is an unconstrained
+            # extrapolation whose value is not determined to 1e-5 by the data (the reference's own
+            # rebuild-vs-downdate paths, baseline.cc:1166, differ there as well).
+            d_rows = data[exact_rows].astype(np.float64)
+            fm_rows = o["final_mask"][exact_rows]
+            model = d_rows - o["residual"][exact_rows] if o.get("residual") is not None else ref
+            valid_range = np.nanmax(np.abs(np.where(fm_rows, d_rows, 0.0)), axis=1, keepdims=True)
+            runaway = np.nanmax(np.abs(np.where(np.isnan(model), 0.0, model)), axis=1,
+                                keepdims=True) > 10.0 * np.maximum(valid_range, 1e-30)
+            skip = runaway & ~fm_rows
+            assert np.all((diff <= tol) | both_nan | skip), (key, float(np.nanmax(np.where(skip, 0, diff))))
         if check_coeff and g.get("coeff") is not None and o.get("coeff") is not None:
             # Rows with only a handful of valid channels interpolate them: their normal equations
             # are (nearly) singular and the coefficients are not determined to 1e-5 by ANY solver;
             # those rows are gated through best_fit / residual above.
             K = g["coeff"].shape[-1] if g["coeff"].ndim == 2 else g["coeff"].shape[-2] + 3
             populated = exact_rows & (o["final_mask"].sum(axis=1) >= 8 * K)
+            if not populated.any():
+                return reported
             gc = g["coeff"][populated].astype(np.float64)
             oc = o["coeff"][populated].astype(np.float64)
             if poly_rescale_n is not None:
@@ -87,11 +108,4 @@ def compare_fit(g, o, data, clip, poly_rescale_n=None, coeff_rtol=1e-5, coeff_at
             norm = np.abs(oc).reshape(oc.shape[0], -1).max(axis=1).reshape((-1,) + (1,) * (oc.ndim - 1))
             ok = (diff <= coeff_atol) | (diff <= coeff_rtol * np.abs(oc)) | (diff <= coeff_rtol * norm)
             assert np.all(ok), float(diff.max())
-    # rows that failed keep their outputs untouched (NaN-prefilled by the bindings)
-    failed = ~good
-    if failed.any():
-        for key in ("coeff", "residual", "best_fit"):
-            if g.get(key) is not None:
-                assert np.all(np.isnan(g[key][failed])), key
-        assert np.all(np.isnan(g["rms"][failed]))
     return reported
