@@ -130,11 +130,14 @@ sakura_Status CurrentDevice(DeviceInfo *info) {
 	return sakura_Status_kOK;
 }
 
-constexpr int kPipelineSlots = 3;
+constexpr int kPipelineSlots = 4;
 
 /** One stage of the host-buffer pipeline: a stream and the device buffers of one chunk. */
 struct PipelineSlot {
-	cudaStream_t stream = nullptr;
+	cudaStream_t stream = nullptr; // upload + kernel + per-row status download
+	cudaStream_t down = nullptr; // bulk result download, so that it never blocks the next upload
+	cudaEvent_t flags_ready = nullptr; // kernel done and per-row flags on the host
+	cudaEvent_t down_done = nullptr; // result buffers of this slot may be overwritten
 	DeviceBuffer data, mask, coeff, best_fit, residual, final_mask, small;
 	std::vector<int32_t> h_flags;
 	size_t row0 = 0;
@@ -150,6 +153,18 @@ struct PipelineSlot {
 		if (stream != nullptr) {
 			cudaStreamDestroy(stream);
 			stream = nullptr;
+		}
+		if (down != nullptr) {
+			cudaStreamDestroy(down);
+			down = nullptr;
+		}
+		if (flags_ready != nullptr) {
+			cudaEventDestroy(flags_ready);
+			flags_ready = nullptr;
+		}
+		if (down_done != nullptr) {
+			cudaEventDestroy(down_done);
+			down_done = nullptr;
 		}
 	}
 };
@@ -445,6 +460,16 @@ struct HostFitArgs {
 
 sakura_Status RunHostBatchSerial(Context *c, FitCall f, HostFitArgs const &h);
 
+/** Row-strided copy; a single 1-D copy when both sides are tightly packed (faster on the
+ *  copy engines than the pitched form). */
+cudaError_t CopyRows(void *dst, size_t dpitch, void const *src, size_t spitch, size_t width,
+		size_t rows, cudaMemcpyKind kind, cudaStream_t stream) {
+	if (dpitch == width && spitch == width) {
+		return cudaMemcpyAsync(dst, src, width * rows, kind, stream);
+	}
+	return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, stream);
+}
+
 // Pipelined variant for the polynomial hot path: the batch is cut into chunks that cycle
 // through kPipelineSlots (stream, device buffers) slots, so that the host->device copy of
 // chunk i+1, the kernel of chunk i and the device->host copy of chunk i-1 overlap on the
@@ -483,6 +508,9 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 		PipelineSlot &sl = c->slots[s];
 		if (sl.stream == nullptr) {
 			CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+			CUDA_TRY(cudaStreamCreateWithFlags(&sl.down, cudaStreamNonBlocking));
+			CUDA_TRY(cudaEventCreateWithFlags(&sl.flags_ready, cudaEventDisableTiming));
+			CUDA_TRY(cudaEventCreateWithFlags(&sl.down_done, cudaEventDisableTiming));
 		}
 		CUDA_TRY(sl.data.Reserve(chunk_rows * dstride * sizeof(float)));
 		CUDA_TRY(sl.mask.Reserve(chunk_rows * dstride));
@@ -501,8 +529,8 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 		sl.rows = 0;
 	}
 	auto finish = [&](PipelineSlot &sl) -> sakura_Status {
-		// flags of this slot's chunk are on the host once its stream has drained
-		CUDA_TRY(cudaStreamSynchronize(sl.stream));
+		// the kernel of this slot's chunk is done and its per-row flags are on the host
+		CUDA_TRY(cudaEventSynchronize(sl.flags_ready));
 		size_t const r0 = sl.row0, rows = sl.rows;
 		float *d_rms = sl.small.As<float>();
 		bool all_published = true;
@@ -515,22 +543,22 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 		if (all_published) {
 			if (h.coeff != nullptr) {
 				CUDA_TRY(cudaMemcpyAsync(h.coeff + r0 * f.coeff_stride, sl.coeff.ptr,
-						rows * f.coeff_stride * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
+						rows * f.coeff_stride * sizeof(double), cudaMemcpyDeviceToHost, sl.down));
 			}
 			if (h.best_fit != nullptr) {
-				CUDA_TRY(cudaMemcpy2DAsync(h.best_fit + r0 * hds, hds * sizeof(float), sl.best_fit.ptr,
+				CUDA_TRY(CopyRows(h.best_fit + r0 * hds, hds * sizeof(float), sl.best_fit.ptr,
 						dstride * sizeof(float), n * sizeof(float), rows, cudaMemcpyDeviceToHost,
-						sl.stream));
+						sl.down));
 			}
 			if (h.residual != nullptr) {
-				CUDA_TRY(cudaMemcpy2DAsync(h.residual + r0 * hds, hds * sizeof(float), sl.residual.ptr,
+				CUDA_TRY(CopyRows(h.residual + r0 * hds, hds * sizeof(float), sl.residual.ptr,
 						dstride * sizeof(float), n * sizeof(float), rows, cudaMemcpyDeviceToHost,
-						sl.stream));
+						sl.down));
 			}
-			CUDA_TRY(cudaMemcpy2DAsync(h.final_mask + r0 * hms, hms, sl.final_mask.ptr, dstride, n,
-					rows, cudaMemcpyDeviceToHost, sl.stream));
+			CUDA_TRY(CopyRows(h.final_mask + r0 * hms, hms, sl.final_mask.ptr, dstride, n, rows,
+					cudaMemcpyDeviceToHost, sl.down));
 			CUDA_TRY(cudaMemcpyAsync(h.rms + r0, d_rms, rows * sizeof(float), cudaMemcpyDeviceToHost,
-					sl.stream));
+					sl.down));
 		} else {
 			for (size_t r = 0; r < rows; ++r) {
 				int const fl = sl.h_flags[r];
@@ -538,28 +566,29 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 					if (h.coeff != nullptr) {
 						CUDA_TRY(cudaMemcpyAsync(h.coeff + (r0 + r) * f.coeff_stride,
 								sl.coeff.As<double>() + r * f.coeff_stride,
-								f.coeff_stride * sizeof(double), cudaMemcpyDeviceToHost, sl.stream));
+								f.coeff_stride * sizeof(double), cudaMemcpyDeviceToHost, sl.down));
 					}
 					if (h.best_fit != nullptr) {
 						CUDA_TRY(cudaMemcpyAsync(h.best_fit + (r0 + r) * hds,
 								sl.best_fit.As<float>() + r * dstride, n * sizeof(float),
-								cudaMemcpyDeviceToHost, sl.stream));
+								cudaMemcpyDeviceToHost, sl.down));
 					}
 					if (h.residual != nullptr) {
 						CUDA_TRY(cudaMemcpyAsync(h.residual + (r0 + r) * hds,
 								sl.residual.As<float>() + r * dstride, n * sizeof(float),
-								cudaMemcpyDeviceToHost, sl.stream));
+								cudaMemcpyDeviceToHost, sl.down));
 					}
 					CUDA_TRY(cudaMemcpyAsync(h.rms + r0 + r, d_rms + r, sizeof(float),
-							cudaMemcpyDeviceToHost, sl.stream));
+							cudaMemcpyDeviceToHost, sl.down));
 				}
 				if (fl & 2) {
 					CUDA_TRY(cudaMemcpyAsync(h.final_mask + (r0 + r) * hms,
 							sl.final_mask.As<uint8_t>() + r * dstride, n, cudaMemcpyDeviceToHost,
-							sl.stream));
+							sl.down));
 				}
 			}
 		}
+		CUDA_TRY(cudaEventRecord(sl.down_done, sl.down));
 		sl.rows = 0;
 		return sakura_Status_kOK;
 	};
@@ -579,10 +608,12 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 		int32_t *d_status = reinterpret_cast<int32_t *>(d_rms + chunk_rows);
 		int32_t *d_lsq = d_status + chunk_rows;
 		int32_t *d_flags = d_lsq + chunk_rows;
-		CUDA_TRY(cudaMemcpy2DAsync(sl.data.ptr, dstride * sizeof(float), h.data + r0 * hds,
+		CUDA_TRY(CopyRows(sl.data.ptr, dstride * sizeof(float), h.data + r0 * hds,
 				hds * sizeof(float), n * sizeof(float), rows, cudaMemcpyHostToDevice, sl.stream));
-		CUDA_TRY(cudaMemcpy2DAsync(sl.mask.ptr, dstride, h.mask + r0 * hms, hms, n, rows,
+		CUDA_TRY(CopyRows(sl.mask.ptr, dstride, h.mask + r0 * hms, hms, n, rows,
 				cudaMemcpyHostToDevice, sl.stream));
+		// the kernel overwrites this slot's result buffers: wait for their previous download
+		CUDA_TRY(cudaStreamWaitEvent(sl.stream, sl.down_done, 0));
 		CUDA_TRY(cudaMemsetAsync(d_flags, 0, rows * sizeof(int32_t), sl.stream));
 		FitCall fc = f;
 		fc.num_spectra = rows;
@@ -609,6 +640,8 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 				sl.stream));
 		CUDA_TRY(cudaMemcpyAsync(sl.h_flags.data(), d_flags, rows * sizeof(int32_t),
 				cudaMemcpyDeviceToHost, sl.stream));
+		CUDA_TRY(cudaEventRecord(sl.flags_ready, sl.stream));
+		CUDA_TRY(cudaStreamWaitEvent(sl.down, sl.flags_ready, 0));
 	}
 	for (size_t k = 0; k < static_cast<size_t>(kPipelineSlots); ++k) {
 		PipelineSlot &sl = c->slots[(num_chunks + k) % kPipelineSlots];
@@ -621,6 +654,7 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 	}
 	for (int s = 0; s < kPipelineSlots; ++s) {
 		CUDA_TRY(cudaStreamSynchronize(c->slots[s].stream));
+		CUDA_TRY(cudaStreamSynchronize(c->slots[s].down));
 	}
 	return sakura_Status_kOK;
 }

@@ -10,14 +10,15 @@
 // Per row:
 //   prologue  : load; count valid channels; data moments T_k = sum_valid y z^k (FP64, z = channel)
 //               power sums over the flagged channels -> S_k = (all-channel constant) - flagged
-//   warp 0    : Hankel normal equations G[j][k] = S[j+k]; in-register LDL^T solve
+//   every warp: Hankel normal equations G[j][k] = S[j+k]; in-register LDL^T solve (redundantly
+//               in all warps: cheaper than a broadcast through shared memory + a barrier)
 //   iteration : pass A  model (FP64 Horner) -> float, residual = y - model (float),
 //                       count / sum / sum-of-squares over valid channels (FP64)
 //               thresholds exactly as baseline.cc:1200-1207 (rounded to float)
 //               pass B  clip predicate of baseline.cc:1088 in float; channel n-1 never examined;
 //                       S_k, T_k contributions of the clipped channels only (downdate, the
 //                       reference's own strategy: numeric_operation.cc:283-314, 448-479)
-//               warp 0  downdate, re-solve
+//               two block barriers per iteration (statistics, moments)
 //
 // What differs from the reference's arithmetic (see DESIGN.md "Arithmetic contract"): the
 // Gram matrix is assembled from 2K-1 power sums instead of K*K per-channel products, sums are
@@ -50,18 +51,49 @@ struct Shared {
 	static constexpr int NW = NT / 32;
 	static constexpr int NV = 3 * K - 1; // 2K-1 power sums + K data moments
 	double stat[2][NW][3]; // count,sum,sq partials, double-buffered by iteration parity
-	double wtot[NW][NV]; // per-warp moment totals
-	double S[2 * K - 1];
-	double T[K];
-	double cz[K]; // model coefficients in the channel-index variable: c_k h^k
-	double cx[K]; // solution in x = i/(n-1) (the reference's coeff_full)
+	double wtot[2][NW][NV]; // per-warp moment totals, double-buffered
+	double st[NW][NV + 1]; // per-warp copy of S (2K-1) and T (K) for the in-register solve
+	double cx[K]; // fallback solver result
 	double A[K * K]; // fallback solver workspace
 	int perm[2 * K];
 	int icnt[NW];
-	int wclip[NW]; // per-warp number of channels clipped in this pass
-	int exit_flag;
-	int num_unmasked;
+	int wclip[2][NW]; // per-warp number of channels clipped in this pass
 };
+
+constexpr int kSlotGroups = 8; // float4 groups per thread: 32 channel slots, one mask bit each
+
+/** value if `keep` is non-zero, else +0.0f -- as an integer select on the bit pattern, so that
+ *  the compiler cannot move it behind a float->double conversion (where it would cost two). */
+__device__ __forceinline__ float select_or_zero(float value, uint32_t keep) {
+	return __int_as_float(keep != 0u ? __float_as_int(value) : 0);
+}
+
+/** sum += rd, sq += rd*rd when `keep` is non-zero, as predicated FP64 instructions (no selects). */
+__device__ __forceinline__ void masked_accumulate(double &sum, double &sq, double rd, uint32_t keep) {
+	asm("{\n\t"
+			".reg .pred p;\n\t"
+			"setp.ne.u32 p, %3, 0;\n\t"
+			"@p add.rn.f64 %0, %0, %2;\n\t"
+			"@p fma.rn.f64 %1, %2, %2, %1;\n\t"
+			"}" : "+d"(sum), "+d"(sq) : "d"(rd), "r"(keep));
+}
+
+/** Coefficients of p(zb + u) in powers of u from those of p(z) in powers of z
+ *  (repeated synthetic division: K(K-1)/2 FMAs). */
+template<int K>
+__device__ __forceinline__ void TaylorShift(double const *c, double zb, double *d) {
+#pragma unroll
+	for (int k = 0; k < K; ++k) {
+		d[k] = c[k];
+	}
+#pragma unroll
+	for (int i = 0; i < K - 1; ++i) {
+#pragma unroll
+		for (int j = K - 2; j >= i; --j) {
+			d[j] = fma(zb, d[j + 1], d[j]);
+		}
+	}
+}
 
 __device__ __forceinline__ double u32_to_double(uint32_t v) {
 	// exact, without the (slow) conversion pipe
@@ -71,70 +103,87 @@ __device__ __forceinline__ double u32_to_double(uint32_t v) {
 // ---- moments over the channels whose bit is set in `bits` (this thread's channel slots) ----
 // Accumulates sum x^k (k < 2K-1) and, if WITH_T, sum y x^k (k < K), x = z*h, then reduces the
 // per-lane partials inside the warp by transposing them through `scratch` (NV rows of 33
-// doubles): lane k adds row k in lane order -- deterministic, no atomics, no shuffles.
-// Result: wtot[k] for k < NV (zeros when no lane of the warp has a bit set).
+// doubles): lane k adds row k over the lanes that had any bit, in lane order -- deterministic,
+// no atomics, no shuffles. Result: wtot[k] for k < NV (zeros when the warp has no bit set).
 template<int K, int NT, bool WITH_T>
 __device__ __forceinline__ void WarpBitMoments(uint32_t bits, double zbase, double h,
 		float const *sdata, int tid, double *scratch, double *wtot) {
 	constexpr int NS = 2 * K - 1;
 	constexpr int NV = 3 * K - 1;
 	int const lane = tid & 31;
-	bool const any = __any_sync(0xffffffffu, bits != 0u);
-	if (!any) {
+	uint32_t const active = __ballot_sync(0xffffffffu, bits != 0u);
+	if (active == 0u) {
 		if (lane < NV) {
 			wtot[lane] = 0.0;
 		}
 		return;
 	}
-	double ps[NS];
-	double pt[K];
-#pragma unroll
-	for (int k = 0; k < NS; ++k) {
-		ps[k] = 0.0;
-	}
-#pragma unroll
-	for (int k = 0; k < K; ++k) {
-		pt[k] = 0.0;
-	}
-	while (bits != 0u) {
-		int const s = __ffs(bits) - 1;
-		bits &= bits - 1u;
-		uint32_t const off = static_cast<uint32_t>((s >> 2) * (4 * NT) + (s & 3));
-		double const x = (zbase + u32_to_double(off)) * h;
-		double yd = 0.0;
-		if (WITH_T) {
-			yd = static_cast<double>(sdata[4 * tid + off]);
-		}
-		double pw = 1.0;
+	if (bits != 0u) {
+		double ps[NS];
+		double pt[K];
 #pragma unroll
 		for (int k = 0; k < NS; ++k) {
-			ps[k] += pw;
-			if (WITH_T && k < K) {
-				pt[k] = fma(yd, pw, pt[k]);
-			}
-			pw *= x;
+			ps[k] = 0.0;
 		}
-	}
 #pragma unroll
-	for (int k = 0; k < NS; ++k) {
-		scratch[k * 33 + lane] = ps[k];
-	}
+		for (int k = 0; k < K; ++k) {
+			pt[k] = 0.0;
+		}
+		do {
+			int const s = __ffs(bits) - 1;
+			bits &= bits - 1u;
+			uint32_t const off = static_cast<uint32_t>((s >> 2) * (4 * NT) + (s & 3));
+			double const x = (zbase + u32_to_double(off)) * h;
+			double yd = 0.0;
+			if (WITH_T) {
+				yd = static_cast<double>(sdata[4 * tid + off]);
+			}
+			double pw = 1.0;
 #pragma unroll
-	for (int k = 0; k < K; ++k) {
-		scratch[(NS + k) * 33 + lane] = pt[k];
+			for (int k = 0; k < NS; ++k) {
+				ps[k] += pw;
+				if (WITH_T && k < K) {
+					pt[k] = fma(yd, pw, pt[k]);
+				}
+				pw *= x;
+			}
+		} while (bits != 0u);
+#pragma unroll
+		for (int k = 0; k < NS; ++k) {
+			scratch[k * 33 + lane] = ps[k];
+		}
+		if (WITH_T) {
+#pragma unroll
+			for (int k = 0; k < K; ++k) {
+				scratch[(NS + k) * 33 + lane] = pt[k];
+			}
+		}
 	}
 	__syncwarp();
 	if (lane < NV) {
-		double const *rowp = scratch + lane * 33;
-		double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-		for (int l = 0; l < 32; l += 2) {
-			t0 += rowp[l];
-			t1 += rowp[l + 1];
+		double tot = 0.0;
+		if (WITH_T || lane < NS) {
+			double const *rowp = scratch + lane * 33;
+			for (uint32_t m = active; m != 0u; m &= m - 1u) {
+				tot += rowp[__ffs(m) - 1];
+			}
 		}
-		wtot[lane] = t0 + t1;
+		wtot[lane] = tot;
 	}
 	__syncwarp();
+}
+
+// Reciprocal of a positive, normal double: hardware estimate + two Newton steps (5 instructions
+// instead of the ~25 of an IEEE division; measured DDIV throughput on B200 is 2.6 /clk/SM).
+// Accurate to ~1 ulp, which is all the elimination below needs.
+__device__ __forceinline__ double fast_rcp(double x) {
+	double r;
+	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+	double e = fma(-x, r, 1.0);
+	r = fma(r, e, r);
+	e = fma(-x, r, 1.0);
+	r = fma(r, e, r);
+	return r;
 }
 
 // ---- solve G c = T, G[j][k] = S[j+k], entirely in registers (every lane the same work) -------
@@ -161,7 +210,7 @@ __device__ __forceinline__ bool SolveLDLT(double const *S, double const *T, doub
 		double const pivot = a[k][k];
 		maxpivot = fmax(maxpivot, fabs(pivot));
 		ok = ok && (pivot > maxpivot * (DBL_EPSILON * K));
-		rcp[k] = 1.0 / pivot;
+		rcp[k] = fast_rcp(pivot);
 #pragma unroll
 		for (int i = k + 1; i < K; ++i) {
 			double const l = a[k][i] * rcp[k];
@@ -326,27 +375,6 @@ __device__ void WarpSolveFullPivLU(double const *S, double const *T, double *A, 
 }
 
 template<int K, int NT>
-__device__ __forceinline__ void WarpSolve(Shared<K, NT> &sh, PolyConst const &pc) {
-	int const lane = threadIdx.x & 31;
-	double c[K];
-	bool const ok = SolveLDLT<K>(sh.S, sh.T, c);
-	if (ok) {
-		if (lane == 0) {
-#pragma unroll
-			for (int k = 0; k < K; ++k) {
-				sh.cx[k] = c[k];
-				sh.cz[k] = c[k] * pc.hpow[k];
-			}
-		}
-	} else { // warp-uniform: every lane solved the same system
-		WarpSolveFullPivLU<K>(sh.S, sh.T, sh.A, sh.perm, sh.cx);
-		if (lane < K) {
-			sh.cz[lane] = sh.cx[lane] * pc.hpow[lane];
-		}
-	}
-}
-
-template<int K, int NT>
 __host__ __device__ constexpr size_t ResidualBytes(int n) {
 	// the residual buffer doubles as per-warp reduction scratch: NW x NV x 33 doubles
 	size_t const need = static_cast<size_t>(NT / 32) * (3 * K - 1) * 33 * sizeof(double);
@@ -363,6 +391,62 @@ __host__ __device__ constexpr size_t SharedOffset(int n) {
 
 constexpr int kMinBlocks128 = 6;
 constexpr int kMinBlocks256 = 3;
+
+// Every warp keeps the current S (2K-1) and T (K) in its own shared-memory slot, applies the
+// block-wide moment totals to it (lane k owns entry k), reads all of it back and solves in
+// registers. All warps compute identical bits (same operands, same order), so no barrier and no
+// broadcast is needed afterwards. `cx` = solution in x = i/(n-1); `cz` = c_k h^k for Horner in
+// the channel index. Returns false when the full-pivot fallback has to be used.
+template<int K, int NT, bool FIRST>
+__device__ __forceinline__ bool UpdateAndSolve(Shared<K, NT> &sh, PolyConst const &pc, int buf,
+		bool complement, int warp, int lane, double *cz) {
+	constexpr int NW = NT / 32;
+	constexpr int NS = 2 * K - 1;
+	constexpr int NV = 3 * K - 1;
+	double *mine = sh.st[warp];
+	if (lane < NV) {
+		double tot = 0.0;
+#pragma unroll
+		for (int w = 0; w < NW; ++w) {
+			tot += sh.wtot[buf][w][lane];
+		}
+		double v;
+		if (FIRST) {
+			if (lane < NS) {
+				v = complement ? (pc.s_all[lane] - tot) : tot;
+			} else {
+				v = tot * pc.hpow[lane - NS];
+			}
+		} else {
+			v = mine[lane] - tot;
+		}
+		mine[lane] = v;
+	}
+	__syncwarp();
+	double S[NS];
+	double T[K];
+#pragma unroll
+	for (int k = 0; k < NS; ++k) {
+		S[k] = mine[k];
+	}
+#pragma unroll
+	for (int k = 0; k < K; ++k) {
+		T[k] = mine[NS + k];
+	}
+	double cx[K];
+	bool const ok = SolveLDLT<K>(S, T, cx);
+#pragma unroll
+	for (int k = 0; k < K; ++k) {
+		cz[k] = cx[k] * pc.hpow[k];
+	}
+	if (warp == 0 && lane == 0) {
+#pragma unroll
+		for (int k = 0; k < K; ++k) {
+			sh.cx[k] = cx[k]; // read back only when the row's outputs are written
+		}
+	}
+	return ok;
+}
 
 template<int K, int NT>
 __global__ void __launch_bounds__(NT, (NT == 128 ? (K >= 7 ? 4 : kMinBlocks128) :
@@ -397,41 +481,49 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 		__syncthreads(); // the previous row's shared state is dead
 
 		// ---- prologue: load the row, valid bits, data moments in z = channel index ----------
+		// A thread's channels are zb + u with zb = 4*tid and u = 4*NT*j + e (j < 8, e < 4): the
+		// offsets u and their powers are compile-time constants, so local moments sum y u^k cost
+		// one FMA each with an immediate operand; they are shifted to the global variable
+		// z = zb + u once per thread (binomial transform, no cancellation: all terms >= 0).
 		uint32_t vbits = 0u;
 		double t[K];
 #pragma unroll
 		for (int k = 0; k < K; ++k) {
 			t[k] = 0.0;
 		}
-		{
-			double zg = zbase;
-			int j4 = 0;
-			for (int g = tid; g < ng; g += NT, j4 += 4) {
+#pragma unroll
+		for (int j = 0; j < kSlotGroups; ++j) {
+			int const g = tid + NT * j;
+			if (g < ng) {
 				float4 const y = __ldg(gdata + g);
 				uint32_t m = __ldg(gmask + g);
 				reinterpret_cast<float4 *>(sdata)[g] = y;
 				m = __vcmpne4(m, 0u) & 0x01010101u; // any non-zero byte is "true"
 				uint32_t const nib = (m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xfu;
-				vbits |= nib << j4;
+				vbits |= nib << (4 * j);
 				float const ye[4] = { y.x, y.y, y.z, y.w };
 #pragma unroll
 				for (int e = 0; e < 4; ++e) {
-					if (nib & (1u << e)) {
-						double const z = zg + static_cast<double>(e);
-						double const yd = static_cast<double>(ye[e]);
-						t[0] += yd;
-						double pw = z;
+					// select (on the bits), not multiply: a NaN/Inf under the mask must not leak
+					double const yd = static_cast<double>(select_or_zero(ye[e], nib & (1u << e)));
+					double const u = static_cast<double>(4 * NT * j + e);
+					double upow = 1.0;
 #pragma unroll
-						for (int k = 1; k < K; ++k) {
-							t[k] = fma(yd, pw, t[k]);
-							pw *= z;
-						}
+					for (int k = 0; k < K; ++k) {
+						t[k] = (k == 0) ? (t[0] + yd) : fma(yd, upow, t[k]);
+						upow *= u;
 					}
 				}
-				zg += static_cast<double>(4 * NT);
 			}
 		}
-		int cnt = warp_sum(__popc(vbits));
+#pragma unroll
+		for (int i = 0; i < K - 1; ++i) {
+#pragma unroll
+			for (int j = K - 1; j > i; --j) {
+				t[j] = fma(zbase, t[j - 1], t[j]);
+			}
+		}
+		int const cnt = warp_sum(__popc(vbits));
 		if (lane == 0) {
 			sh.icnt[warp] = cnt;
 		}
@@ -462,37 +554,27 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 		// (or the direct sum when more than half of the row is flagged).
 		bool const complement = (2 * num_valid >= n);
 		WarpBitMoments<K, NT, false>(complement ? (~vbits & slot_mask) : vbits, zbase, pc.h, sdata,
-				tid, scratch, sh.wtot[warp]);
-		// data moments: reuse the T rows of wtot (the call above left them zero)
+				tid, scratch, sh.wtot[0][warp]);
 #pragma unroll
 		for (int k = 0; k < K; ++k) {
 			t[k] = warp_sum(t[k]);
 		}
-		__syncwarp();
+		__syncwarp(); // the T rows of wtot were zeroed by other lanes just above
 		if (lane == 0) {
 #pragma unroll
 			for (int k = 0; k < K; ++k) {
-				sh.wtot[warp][NS + k] = t[k];
+				sh.wtot[0][warp][NS + k] = t[k];
 			}
 		}
 		__syncthreads();
-		if (warp == 0) {
-			if (lane < NV) {
-				double tot = 0.0;
-#pragma unroll
-				for (int w = 0; w < NW; ++w) {
-					tot += sh.wtot[w][lane];
-				}
-				if (lane < NS) {
-					sh.S[lane] = complement ? (pc.s_all[lane] - tot) : tot;
-				} else {
-					sh.T[lane - NS] = tot * pc.hpow[lane - NS];
-				}
-			}
-			__syncwarp();
-			WarpSolve<K, NT>(sh, pc);
+		// d: model coefficients re-centred on this thread's first channel (see pass A)
+		double d[K];
+		bool solved;
+		{
+			double cz[K];
+			solved = UpdateAndSolve<K, NT, true>(sh, pc, 0, complement, warp, lane, cz);
+			TaylorShift<K>(cz, zbase, d);
 		}
-		__syncthreads();
 
 		// ---- clip iterations ----------------------------------------------------------------------
 		int num_unmasked = n; // baseline.cc:1152 (sic)
@@ -503,40 +585,44 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 				failed = true;
 				break;
 			}
-			// pass A: model, residual, statistics
-			double cz[K];
+			if (!solved) { // block-uniform: every warp solved the same system
+				if (warp == 0) {
+					WarpSolveFullPivLU<K>(sh.st[0], sh.st[0] + NS, sh.A, sh.perm, sh.cx);
+				}
+				__syncthreads();
+				double cz[K];
 #pragma unroll
-			for (int k = 0; k < K; ++k) {
-				cz[k] = sh.cz[k];
+				for (int k = 0; k < K; ++k) {
+					cz[k] = sh.cx[k] * pc.hpow[k];
+				}
+				TaylorShift<K>(cz, zbase, d);
 			}
+			// pass A: model, residual, statistics
+			// The model polynomial is re-centred on this thread's first channel (Taylor shift,
+			// K(K-1)/2 FMAs per thread) so that the Horner variable of every channel is a
+			// compile-time constant: no per-channel index arithmetic or int->double conversion.
 			double sum = 0.0, sq = 0.0;
-			{
-				double zg = zbase;
-				uint32_t vb = vbits;
-				for (int g = tid; g < ng; g += NT) {
+#pragma unroll
+			for (int j = 0; j < kSlotGroups; ++j) {
+				int const g = tid + NT * j;
+				if (g < ng) {
 					float4 const y = reinterpret_cast<float4 const *>(sdata)[g];
 					float const ye[4] = { y.x, y.y, y.z, y.w };
 					float re[4];
 #pragma unroll
 					for (int e = 0; e < 4; ++e) {
-						double const z = zg + static_cast<double>(e);
-						double acc = cz[K - 1];
+						double const u = static_cast<double>(4 * NT * j + e);
+						double acc = d[K - 1];
 #pragma unroll
 						for (int k = K - 2; k >= 0; --k) {
-							acc = fma(acc, z, cz[k]);
+							acc = fma(acc, u, d[k]);
 						}
 						float const mf = static_cast<float>(acc);
 						float const r = __fsub_rn(ye[e], mf);
 						re[e] = r;
-						if (vb & (1u << e)) {
-							double const rd = static_cast<double>(r);
-							sum += rd;
-							sq = fma(rd, rd, sq);
-						}
+						masked_accumulate(sum, sq, static_cast<double>(r), vbits & (1u << (4 * j + e)));
 					}
 					reinterpret_cast<float4 *>(sres)[g] = make_float4(re[0], re[1], re[2], re[3]);
-					zg += static_cast<double>(4 * NT);
-					vb >>= 4;
 				}
 			}
 			int c = warp_sum(__popc(vbits));
@@ -566,73 +652,50 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 			}
 			// pass B: clip. The last channel is never examined (baseline.cc:1081-1096).
 			uint32_t clipped = 0u;
-			{
-				uint32_t vb = vbits;
-				int j4 = 0;
-				for (int g = tid; g < ng; g += NT, j4 += 4) {
+#pragma unroll
+			for (int j = 0; j < kSlotGroups; ++j) {
+				int const g = tid + NT * j;
+				if (g < ng) {
 					float4 const r4 = reinterpret_cast<float4 const *>(sres)[g];
 					float const re[4] = { r4.x, r4.y, r4.z, r4.w };
-					uint32_t cl = 0u;
 #pragma unroll
 					for (int e = 0; e < 4; ++e) {
 						if (is_clipped(re[e], th.lower, th.upper)) {
-							cl |= (1u << e);
+							clipped |= (1u << (4 * j + e));
 						}
 					}
-					cl &= vb & 0xfu;
 					if (g == ng - 1) {
-						cl &= 0x7u;
+						clipped &= ~(8u << (4 * j)); // channel n-1
 					}
-					clipped |= cl << j4;
-					vb >>= 4;
 				}
 			}
+			clipped &= vbits;
 			vbits &= ~clipped;
 			int const nclip = warp_sum(__popc(clipped));
-			__syncthreads(); // every warp is done with the residual: it becomes scratch
-			WarpBitMoments<K, NT, true>(clipped, zbase, pc.h, sdata, tid, scratch, sh.wtot[warp]);
+			// A warp only turns its slice of the residual buffer into scratch when it clipped
+			// something, i.e. when another fit (which rewrites the residual) is certain to follow.
+			// Other warps may still be reading the residual in pass B: the scratch slices of
+			// different warps are disjoint, but they alias residual channels owned by other
+			// threads, hence the barrier.
+			if (__syncthreads_or(nclip) == 0) {
+				break; // nothing clipped anywhere: the fit has converged (baseline.cc:1211-1213)
+			}
+			WarpBitMoments<K, NT, true>(clipped, zbase, pc.h, sdata, tid, scratch, sh.wtot[buf][warp]);
 			if (lane == 0) {
-				sh.wclip[warp] = nclip;
+				sh.wclip[buf][warp] = nclip;
 			}
 			__syncthreads();
-			if (warp == 0) {
-				int num_clipped = 0;
+			int num_clipped = 0;
 #pragma unroll
-				for (int w = 0; w < NW; ++w) {
-					num_clipped += sh.wclip[w];
-				}
-				if (num_clipped == 0) {
-					if (lane == 0) {
-						sh.exit_flag = 1;
-					}
-				} else {
-					if (lane < NV) {
-						double tot = 0.0;
-#pragma unroll
-						for (int w = 0; w < NW; ++w) {
-							tot += sh.wtot[w][lane];
-						}
-						if (lane < NS) {
-							sh.S[lane] -= tot;
-						} else {
-							sh.T[lane - NS] -= tot;
-						}
-					}
-					if (lane == 0) {
-						sh.exit_flag = 0;
-						sh.num_unmasked = c - num_clipped;
-					}
-					__syncwarp();
-					if (c - num_clipped >= K) {
-						WarpSolve<K, NT>(sh, pc);
-					}
-				}
+			for (int w = 0; w < NW; ++w) {
+				num_clipped += sh.wclip[buf][w];
 			}
-			__syncthreads();
-			if (sh.exit_flag) {
-				break;
+			num_unmasked = c - num_clipped;
+			if (num_unmasked >= K) {
+				double cz[K];
+				solved = UpdateAndSolve<K, NT, false>(sh, pc, buf, false, warp, lane, cz);
+				TaylorShift<K>(cz, zbase, d);
 			}
-			num_unmasked = sh.num_unmasked;
 		}
 
 		// ---- final mask (bits -> bytes) ------------------------------------------------------------
@@ -658,46 +721,39 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 		}
 		// ---- outputs (baseline.cc:1310-1328) ---------------------------------------------------
 		// The residual in shared memory is intact here: the reduction scratch that aliases it
-		// is only written by a warp that clipped something, and then another fit follows.
-		bool const residual_dirty = false;
-		if (p.residual != nullptr || p.best_fit != nullptr) {
+		// is only written after a clip pass that clipped something, and then another fit follows.
+		if (p.residual != nullptr && p.best_fit == nullptr) {
+			float4 *outr = reinterpret_cast<float4 *>(p.residual + row * p.data_stride);
+			for (int g = tid; g < ng; g += NT) {
+				outr[g] = reinterpret_cast<float4 const *>(sres)[g];
+			}
+		} else if (p.best_fit != nullptr) {
 			float4 *outr = p.residual ? reinterpret_cast<float4 *>(p.residual + row * p.data_stride) :
 					nullptr;
-			float4 *outb = p.best_fit ? reinterpret_cast<float4 *>(p.best_fit + row * p.data_stride) :
-					nullptr;
-			if (outb == nullptr && !residual_dirty) {
-				for (int g = tid; g < ng; g += NT) {
-					outr[g] = reinterpret_cast<float4 const *>(sres)[g];
-				}
-			} else {
-				double cz[K];
+			float4 *outb = reinterpret_cast<float4 *>(p.best_fit + row * p.data_stride);
+			// d is the one pass A last used: identical arithmetic, identical model values
 #pragma unroll
-				for (int k = 0; k < K; ++k) {
-					cz[k] = sh.cz[k];
-				}
-				double zg = zbase;
-				for (int g = tid; g < ng; g += NT) {
+			for (int j = 0; j < kSlotGroups; ++j) {
+				int const g = tid + NT * j;
+				if (g < ng) {
 					float4 const y = reinterpret_cast<float4 const *>(sdata)[g];
 					float const ye[4] = { y.x, y.y, y.z, y.w };
 					float me[4], re[4];
 #pragma unroll
 					for (int e = 0; e < 4; ++e) {
-						double const z = zg + static_cast<double>(e);
-						double acc = cz[K - 1];
+						double const u = static_cast<double>(4 * NT * j + e);
+						double acc = d[K - 1];
 #pragma unroll
 						for (int k = K - 2; k >= 0; --k) {
-							acc = fma(acc, z, cz[k]);
+							acc = fma(acc, u, d[k]);
 						}
 						me[e] = static_cast<float>(acc);
 						re[e] = __fsub_rn(ye[e], me[e]);
 					}
-					if (outb != nullptr) {
-						outb[g] = make_float4(me[0], me[1], me[2], me[3]);
-					}
+					outb[g] = make_float4(me[0], me[1], me[2], me[3]);
 					if (outr != nullptr) {
 						outr[g] = make_float4(re[0], re[1], re[2], re[3]);
 					}
-					zg += static_cast<double>(4 * NT);
 				}
 			}
 		}
