@@ -11,6 +11,7 @@
 #include "lsq_blocks.cuh"
 #include "lsqfit_general.cuh"
 #include "lsqfit_poly.cuh"
+#include "lsqfit_sinusoid.cuh"
 #include "statistics.cuh"
 
 #include <cuda_runtime.h>
@@ -188,6 +189,13 @@ struct sakura_LSQFitContextFloat {
 	int device;
 	DeviceBuffer d_basis;
 	DeviceBuffer ws_residual, ws_best_fit, ws_spline;
+	// sinusoid fast path: extended trigonometric table (1, sin/cos(m theta) for m <= 2*nwave),
+	// its column sums over all channels, the per-call compact basis table and scratch
+	std::vector<double> *h_ext;
+	std::vector<double> *h_ext_all;
+	int ext_cols;
+	DeviceBuffer d_ext, d_ext_all, d_table, d_useidx, d_fallback, ws_mask, ws_sin_residual,
+			ws_sin_best_fit;
 	// staging for the host-pointer entry points
 	DeviceBuffer s_data, s_mask, s_coeff, s_best_fit, s_residual, s_final_mask, s_rms,
 			s_status, s_lsq, s_flags, s_boundary;
@@ -232,6 +240,14 @@ void ReleaseDeviceState(Context *c) {
 		c->ws_residual.Release();
 		c->ws_best_fit.Release();
 		c->ws_spline.Release();
+		c->d_ext.Release();
+		c->d_ext_all.Release();
+		c->d_table.Release();
+		c->d_useidx.Release();
+		c->d_fallback.Release();
+		c->ws_mask.Release();
+		c->ws_sin_residual.Release();
+		c->ws_sin_best_fit.Release();
 		c->s_data.Release();
 		c->s_mask.Release();
 		c->s_coeff.Release();
@@ -280,6 +296,9 @@ sakura_Status CreateContext(int type, uint16_t param, size_t num_data, Context *
 	c->device = -1;
 	c->h_flags = nullptr;
 	c->slots = nullptr;
+	c->h_ext = nullptr;
+	c->h_ext_all = nullptr;
+	c->ext_cols = 0;
 	c->h_basis = static_cast<double *>(g_allocator(sizeof(double) * num_bases * num_data));
 	if (c->h_basis == nullptr) {
 		c->~Context();
@@ -296,6 +315,30 @@ sakura_Status CreateContext(int type, uint16_t param, size_t num_data, Context *
 		break;
 	default:
 		FillSinusoidTable(num_data, param, c->h_basis);
+		if (num_data > 1 && param >= 1 && 4 * static_cast<size_t>(param) + 1 <= 96) {
+			// same expression as the reference's table (baseline.cc:356-362), up to 2*nwave
+			int const cols = 4 * param + 1;
+			c->ext_cols = cols;
+			c->h_ext = new std::vector<double>(static_cast<size_t>(num_data) * cols);
+			c->h_ext_all = new std::vector<double>(cols);
+			std::vector<long double> acc(cols, 0.0L);
+			double const norm = 2.0 * M_PI / static_cast<double>(num_data - 1);
+			for (size_t i = 0; i < num_data; ++i) {
+				double *row = c->h_ext->data() + i * cols;
+				row[0] = 1.0;
+				for (int m = 1; m <= 2 * param; ++m) {
+					double const x = static_cast<double>(i) * static_cast<double>(m) * norm;
+					row[2 * m - 1] = sin(x);
+					row[2 * m] = cos(x);
+				}
+				for (int e = 0; e < cols; ++e) {
+					acc[e] += static_cast<long double>(row[e]);
+				}
+			}
+			for (int e = 0; e < cols; ++e) {
+				(*c->h_ext_all)[e] = static_cast<double>(acc[e]);
+			}
+		}
 		break;
 	}
 	*out = c;
@@ -314,7 +357,19 @@ sakura_Status BindDevice(Context *c, DeviceInfo const &info, cudaStream_t stream
 	size_t const bytes = sizeof(double) * c->num_bases * c->num_data;
 	CUDA_TRY(c->d_basis.Reserve(bytes));
 	CUDA_TRY(cudaMemcpyAsync(c->d_basis.ptr, c->h_basis, bytes, cudaMemcpyHostToDevice, stream));
+	if (c->h_ext != nullptr) {
+		CUDA_TRY(c->d_ext.Reserve(c->h_ext->size() * sizeof(double)));
+		CUDA_TRY(c->d_ext_all.Reserve(c->h_ext_all->size() * sizeof(double)));
+		CUDA_TRY(cudaMemcpyAsync(c->d_ext.ptr, c->h_ext->data(), c->h_ext->size() * sizeof(double),
+				cudaMemcpyHostToDevice, stream));
+		CUDA_TRY(cudaMemcpyAsync(c->d_ext_all.ptr, c->h_ext_all->data(),
+				c->h_ext_all->size() * sizeof(double), cudaMemcpyHostToDevice, stream));
+	}
 	return sakura_Status_kOK;
+}
+
+size_t RoundUp(size_t v, size_t m) {
+	return (v + m - 1) / m * m;
 }
 
 // ---------------------------------------------------------------- fit dispatch
@@ -388,13 +443,102 @@ sakura_Status LaunchFit(Context *c, FitCall const &f, cudaStream_t stream) {
 		}
 		return sakura_Status_kOK;
 	}
+	// ---- sinusoid with many bases: 32-row tiles, tensor-core contractions; rows whose normal
+	// equations are not safely positive definite are handed to the general kernel below
+	int32_t const *fb_index = nullptr;
+	int32_t const *fb_count = nullptr;
+	if (f.type == kFitSinusoid && c->h_ext != nullptr && f.num_data % 32 == 0 && f.num_data >= 64
+			&& f.K >= 1 && f.K <= static_cast<size_t>(kSinMaxKp) && f.data_stride % 4 == 0
+			&& f.mask_stride % 8 == 0 && f.num_spectra <= static_cast<size_t>(INT32_MAX)
+			&& (reinterpret_cast<uintptr_t>(f.data) % 16) == 0
+			&& (reinterpret_cast<uintptr_t>(f.mask) % 8) == 0
+			&& (reinterpret_cast<uintptr_t>(f.final_mask) % 8) == 0
+			&& (reinterpret_cast<uintptr_t>(f.residual) % 16) == 0
+			&& (reinterpret_cast<uintptr_t>(f.best_fit) % 16) == 0) {
+		SinusoidFitParams sp;
+		memset(&sp, 0, sizeof(sp));
+		size_t const n = f.num_data;
+		sp.num_spectra = f.num_spectra;
+		sp.n = static_cast<int>(n);
+		sp.K = static_cast<int>(f.K);
+		sp.Kp = static_cast<int>(RoundUp(f.K, 8));
+		sp.next = c->ext_cols;
+		bool columns_ok = true;
+		for (size_t k = 0; k < f.K; ++k) {
+			int const col = f.use_idx[k];
+			sp.kind[k] = static_cast<int8_t>(col == 0 ? 0 : ((col & 1) ? 1 : 2));
+			sp.wave[k] = static_cast<int16_t>((col + 1) / 2);
+			columns_ok = columns_ok && (col >= 0 && static_cast<size_t>(col) < c->num_bases);
+		}
+		if (columns_ok) {
+			size_t tiles = (f.num_spectra + kSinRowsPerTile - 1) / kSinRowsPerTile;
+			size_t sgrid = static_cast<size_t>(info.num_sms);
+			if (sgrid > tiles) {
+				sgrid = tiles;
+			}
+			CUDA_TRY(c->d_table.Reserve(n * sp.Kp * sizeof(double)));
+			CUDA_TRY(c->d_useidx.Reserve(kMaxBases * sizeof(int16_t)));
+			CUDA_TRY(c->d_fallback.Reserve((f.num_spectra + 1) * sizeof(int32_t)));
+			CUDA_TRY(c->ws_mask.Reserve(sgrid * kSinRowsPerTile * n));
+			CUDA_TRY(c->ws_sin_residual.Reserve(sgrid * kSinRowsPerTile * n * sizeof(float)));
+			if (f.best_fit != nullptr) {
+				CUDA_TRY(c->ws_sin_best_fit.Reserve(sgrid * kSinRowsPerTile * n * sizeof(float)));
+			}
+			CUDA_TRY(cudaMemcpyAsync(c->d_useidx.ptr, f.use_idx, kMaxBases * sizeof(int16_t),
+					cudaMemcpyHostToDevice, stream));
+			cudaError_t e = LaunchGatherTable(c->d_basis.As<double>(), static_cast<int>(c->num_bases),
+					sp.n, sp.K, sp.Kp, c->d_useidx.As<int16_t>(), c->d_table.As<double>(), stream);
+			g_launch_count += 1;
+			if (e != cudaSuccess) {
+				SetError("LaunchGatherTable", e);
+				return sakura_Status_kUnknownError;
+			}
+			int32_t *fb = c->d_fallback.As<int32_t>();
+			CUDA_TRY(cudaMemsetAsync(fb, 0, sizeof(int32_t), stream));
+			sp.table = c->d_table.As<double>();
+			sp.ext = c->d_ext.As<double>();
+			sp.ext_all = c->d_ext_all.As<double>();
+			sp.data = f.data;
+			sp.data_stride = f.data_stride;
+			sp.mask = f.mask;
+			sp.mask_stride = f.mask_stride;
+			sp.clip_threshold_sigma = f.clip;
+			sp.num_fitting_max = f.nfit;
+			sp.coeff = f.coeff;
+			sp.best_fit = f.best_fit;
+			sp.residual = f.residual;
+			sp.final_mask = f.final_mask;
+			sp.rms = f.rms;
+			sp.status = f.status;
+			sp.lsqfit_status = f.lsq;
+			sp.flags = f.flags;
+			sp.ws_residual = c->ws_sin_residual.As<float>();
+			sp.ws_best_fit = f.best_fit ? c->ws_sin_best_fit.As<float>() : nullptr;
+			sp.ws_mask = c->ws_mask.As<uint8_t>();
+			sp.fallback_count = fb;
+			sp.fallback_rows = fb + 1;
+			e = LaunchSinusoidFit(sp, static_cast<int>(sgrid), stream);
+			g_launch_count += 1;
+			if (e != cudaSuccess) {
+				SetError("LaunchSinusoidFit", e);
+				return sakura_Status_kUnknownError;
+			}
+			fb_count = fb;
+			fb_index = fb + 1;
+		}
+	}
 	// ---- general path
 	size_t grid = static_cast<size_t>(info.num_sms) * 4;
+	if (fb_index != nullptr) {
+		grid = static_cast<size_t>(info.num_sms);
+	}
 	if (grid > f.num_spectra) {
 		grid = f.num_spectra;
 	}
 	GeneralFitParams p;
 	memset(&p, 0, sizeof(p));
+	p.row_index = fb_index;
+	p.row_count = fb_count;
 	p.fit_type = f.type;
 	p.num_spectra = f.num_spectra;
 	p.n = static_cast<int>(f.num_data);
@@ -432,7 +576,7 @@ sakura_Status LaunchFit(Context *c, FitCall const &f, cudaStream_t stream) {
 	}
 	cudaError_t e = LaunchGeneralFit(p, static_cast<int>(grid), stream);
 	g_launch_count += 1;
-	g_last_kernel = "general";
+	g_last_kernel = (fb_index != nullptr) ? "sinusoid_dmma" : "general";
 	if (e != cudaSuccess) {
 		SetError("LaunchGeneralFit", e);
 		return sakura_Status_kUnknownError;
@@ -440,9 +584,6 @@ sakura_Status LaunchFit(Context *c, FitCall const &f, cudaStream_t stream) {
 	return sakura_Status_kOK;
 }
 
-size_t RoundUp(size_t v, size_t m) {
-	return (v + m - 1) / m * m;
-}
 
 // Host-pointer batch: stage through device buffers owned by the context.
 struct HostFitArgs {
@@ -985,6 +1126,8 @@ sakura_Status sakura_DestroyLSQFitContextFloat(struct sakura_LSQFitContextFloat 
 	CHECK_ARGS(context->magic == kContextMagic);
 	ReleaseDeviceState(context);
 	delete context->h_flags;
+	delete context->h_ext;
+	delete context->h_ext_all;
 	delete[] context->slots;
 	context->slots = nullptr;
 	context->h_flags = nullptr;

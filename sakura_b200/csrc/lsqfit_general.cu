@@ -194,7 +194,11 @@ GeneralFitKernel(GeneralFitParams const p) {
 	int const K = p.K;
 	bool const spline = (p.fit_type == kFitCubicSpline);
 
-	for (size_t row = blockIdx.x; row < p.num_spectra; row += gridDim.x) {
+	// Optional indirection: fit only the rows listed in row_index[0 .. *row_count) (used for the
+	// rows a specialised kernel hands over, e.g. nearly singular normal equations).
+	size_t const total_rows = p.row_count ? static_cast<size_t>(*p.row_count) : p.num_spectra;
+	for (size_t it = blockIdx.x; it < total_rows; it += gridDim.x) {
+		size_t const row = p.row_index ? static_cast<size_t>(p.row_index[it]) : it;
 		float const *data = p.data + row * p.data_stride;
 		uint8_t const *mask = p.mask + row * p.mask_stride;
 		uint8_t *fmask = p.final_mask + row * p.mask_stride;

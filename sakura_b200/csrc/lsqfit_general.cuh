@@ -41,6 +41,8 @@ struct GeneralFitParams {
 	float *ws_best_fit; // [gridDim.x][n] per-CTA staging of the model (when best_fit != NULL)
 	double *ws_spline_basis; // [gridDim.x][n][nb_row] scratch (spline only)
 	int16_t use_idx[kMaxBases]; // column of the context table for each fitted basis
+	int32_t const *row_index; // optional: rows to fit (device), else NULL = all rows
+	int32_t const *row_count; // optional: number of entries of row_index (device)
 };
 
 size_t GeneralFitSharedBytes(int K, int npiece, int threads);

@@ -88,7 +88,7 @@ def test_config_c4_shape_8192ch_nwave20(lib, oracle):
     data, mask = synth.make_spectra(64, 8192, seed=62, ripple=True)
     synth.add_edge_case_rows(data, mask, 41)
     g, o = sinus_both(lib, oracle, list(range(21)), data, mask, 3.0, 3, 20)
-    assert lib.last_kernel_name() == "general"
+    assert lib.last_kernel_name() == "sinusoid_dmma"
     assert compare_fit(g, o, data, 3.0) == []
 
 
