@@ -192,9 +192,8 @@ struct sakura_LSQFitContextFloat {
 	// sinusoid fast path: extended trigonometric table (1, sin/cos(m theta) for m <= 2*nwave),
 	// its column sums over all channels, the per-call compact basis table and scratch
 	std::vector<double> *h_ext;
-	std::vector<double> *h_ext_all;
 	int ext_cols;
-	DeviceBuffer d_ext, d_ext_all, d_table, d_useidx, d_fallback, ws_mask, ws_sin_residual,
+	DeviceBuffer d_ext, d_table, d_useidx, d_fallback, ws_mask, ws_sin_residual,
 			ws_sin_best_fit;
 	// staging for the host-pointer entry points
 	DeviceBuffer s_data, s_mask, s_coeff, s_best_fit, s_residual, s_final_mask, s_rms,
@@ -241,7 +240,6 @@ void ReleaseDeviceState(Context *c) {
 		c->ws_best_fit.Release();
 		c->ws_spline.Release();
 		c->d_ext.Release();
-		c->d_ext_all.Release();
 		c->d_table.Release();
 		c->d_useidx.Release();
 		c->d_fallback.Release();
@@ -297,7 +295,6 @@ sakura_Status CreateContext(int type, uint16_t param, size_t num_data, Context *
 	c->h_flags = nullptr;
 	c->slots = nullptr;
 	c->h_ext = nullptr;
-	c->h_ext_all = nullptr;
 	c->ext_cols = 0;
 	c->h_basis = static_cast<double *>(g_allocator(sizeof(double) * num_bases * num_data));
 	if (c->h_basis == nullptr) {
@@ -318,25 +315,18 @@ sakura_Status CreateContext(int type, uint16_t param, size_t num_data, Context *
 		if (num_data > 1 && param >= 1 && 4 * static_cast<size_t>(param) + 1 <= 96) {
 			// same expression as the reference's table (baseline.cc:356-362), up to 2*nwave
 			int const cols = 4 * param + 1;
+			size_t const ld = static_cast<size_t>(SinusoidExtLd(cols)); // zero padded columns
 			c->ext_cols = cols;
-			c->h_ext = new std::vector<double>(static_cast<size_t>(num_data) * cols);
-			c->h_ext_all = new std::vector<double>(cols);
-			std::vector<long double> acc(cols, 0.0L);
+			c->h_ext = new std::vector<double>(static_cast<size_t>(num_data) * ld, 0.0);
 			double const norm = 2.0 * M_PI / static_cast<double>(num_data - 1);
 			for (size_t i = 0; i < num_data; ++i) {
-				double *row = c->h_ext->data() + i * cols;
+				double *row = c->h_ext->data() + i * ld;
 				row[0] = 1.0;
 				for (int m = 1; m <= 2 * param; ++m) {
 					double const x = static_cast<double>(i) * static_cast<double>(m) * norm;
 					row[2 * m - 1] = sin(x);
 					row[2 * m] = cos(x);
 				}
-				for (int e = 0; e < cols; ++e) {
-					acc[e] += static_cast<long double>(row[e]);
-				}
-			}
-			for (int e = 0; e < cols; ++e) {
-				(*c->h_ext_all)[e] = static_cast<double>(acc[e]);
 			}
 		}
 		break;
@@ -359,11 +349,8 @@ sakura_Status BindDevice(Context *c, DeviceInfo const &info, cudaStream_t stream
 	CUDA_TRY(cudaMemcpyAsync(c->d_basis.ptr, c->h_basis, bytes, cudaMemcpyHostToDevice, stream));
 	if (c->h_ext != nullptr) {
 		CUDA_TRY(c->d_ext.Reserve(c->h_ext->size() * sizeof(double)));
-		CUDA_TRY(c->d_ext_all.Reserve(c->h_ext_all->size() * sizeof(double)));
 		CUDA_TRY(cudaMemcpyAsync(c->d_ext.ptr, c->h_ext->data(), c->h_ext->size() * sizeof(double),
 				cudaMemcpyHostToDevice, stream));
-		CUDA_TRY(cudaMemcpyAsync(c->d_ext_all.ptr, c->h_ext_all->data(),
-				c->h_ext_all->size() * sizeof(double), cudaMemcpyHostToDevice, stream));
 	}
 	return sakura_Status_kOK;
 }
@@ -497,7 +484,7 @@ sakura_Status LaunchFit(Context *c, FitCall const &f, cudaStream_t stream) {
 			CUDA_TRY(cudaMemsetAsync(fb, 0, sizeof(int32_t), stream));
 			sp.table = c->d_table.As<double>();
 			sp.ext = c->d_ext.As<double>();
-			sp.ext_all = c->d_ext_all.As<double>();
+			sp.ext_ld = SinusoidExtLd(c->ext_cols);
 			sp.data = f.data;
 			sp.data_stride = f.data_stride;
 			sp.mask = f.mask;
@@ -1127,7 +1114,6 @@ sakura_Status sakura_DestroyLSQFitContextFloat(struct sakura_LSQFitContextFloat 
 	ReleaseDeviceState(context);
 	delete context->h_flags;
 	delete context->h_ext;
-	delete context->h_ext_all;
 	delete[] context->slots;
 	context->slots = nullptr;
 	context->h_flags = nullptr;

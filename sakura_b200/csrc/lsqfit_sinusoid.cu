@@ -2,19 +2,22 @@
 // LSQFit :1268 -> DoLSQFit :1115) for the high-basis-count configs (BASELINE C4: 8192 channels,
 // wave numbers 0..20 = 41 bases).
 //
-// One 256-thread CTA fits a tile of 32 spectra together, so that the FP64 basis table is read
-// once per tile instead of once per spectrum, and the two dense contractions run on the FP64
-// tensor cores (mma.sync m8n8k4 = DMMA):
+// One 256-thread CTA fits a tile of 32 spectra together, so that the FP64 tables are read once
+// per tile instead of once per spectrum, and every dense contraction runs on the FP64 tensor
+// cores (mma.sync m8n8k4 = DMMA):
+//   trig sums      t[r][e]   = sum_i  mask[r][i]     * ext[i][e]        (rows x channels x 2*mmax+1)
 //   data moments   b[r][k]   = sum_i  (mask*y)[r][i] * table[i][k]      (rows x channels x bases)
 //   model          m[r][i]   = sum_k  coeff[r][k]    * table[i][k]      (rows x bases x channels)
+//   LDL^T trailing updates of the per-row K x K solve (8 x 8 blocks)
 // The Gram matrix needs no per-channel outer products at all: with phi = {1, sin(w t), cos(w t)}
 //   sin a sin b = (cos(a-b) - cos(a+b))/2,  cos a cos b = (cos(a-b) + cos(a+b))/2,
 //   sin a cos b = (sin(a+b) + sin(a-b))/2
-// every entry is a combination of the masked sums C_m = sum_valid cos(m t_i), S_m = sum_valid
-// sin(m t_i), m <= 2*max wave. Those are (all-channel constants) - (sum over the flagged
-// channels), and a clip pass only subtracts the clipped channels (downdate, like the reference's
-// numeric_operation.cc:283-314). The K x K solve is an LDL^T per row in shared memory; a row whose
-// pivots are not safely positive is handed to the general kernel (full-pivot rank-revealing LU).
+// every entry is half the sum of two signed masked sums C_m = sum_valid cos(m t_i), S_m = sum_valid
+// sin(m t_i), m <= 2*max wave (the trig sums above; which two, and their signs, is a per-call
+// table built once per CTA). A clip pass only subtracts the clipped channels from the sums
+// (downdate, like the reference's numeric_operation.cc:283-314). The solve is a blocked LDL^T of
+// the matrix bordered by the right-hand side, one warp per row; a row whose pivots are not safely
+// positive is handed to the general kernel (full-pivot rank-revealing LU).
 //
 // Thresholds, the float clip predicate, "last channel never clipped", early exit, not-enough-data
 // and which outputs a failing row leaves untouched follow baseline.cc:1142-1224 exactly as in the
@@ -30,10 +33,17 @@ namespace {
 
 constexpr int RB = kSinRowsPerTile;
 constexpr int NWARP = kSinThreads / 32;
+constexpr unsigned kFull = 0xffffffffu;
 
 enum RowState : int {
 	kActive = 0, kConverged = 1, kFailedAfterClip = 2, kFailedBefore = 3, kFallback = 4, kNoRow = 5
 };
+
+// bits of a Gram table entry: which two trig sums, their signs, padding, and the (i, j) it fills
+constexpr unsigned kGramNeg1 = 1u << 16;
+constexpr unsigned kGramNeg2 = 1u << 17;
+constexpr unsigned kGramPadDiag = 1u << 18;
+constexpr unsigned kGramPad = 1u << 19;
 
 __device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
 	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -50,10 +60,30 @@ __device__ __forceinline__ double fast_rcp_pos(double x) {
 	return r;
 }
 
+__device__ __forceinline__ double select_f64(bool keep, double v) {
+	// v or +0.0 without a branch and without touching v's NaN payloads when dropped
+	return __hiloint2double(keep ? __double2hiint(v) : 0, keep ? __double2loint(v) : 0);
+}
+
+__host__ __device__ constexpr int SolveLd(int Kp) {
+	return Kp + 2;
+}
+__host__ __device__ constexpr int CoefLd(int Kp) {
+	return Kp + 4; // 2*ld mod 32 == 8 or 24: DMMA A-fragment loads without bank conflicts
+}
+__host__ __device__ inline int GwStride(int Kp) {
+	int const a = (Kp + 1) * SolveLd(Kp); // bordered matrix of the solve
+	int const b = RB * (Kp > 32 ? Kp : 32); // per-warp partial sums of the contractions
+	return a > b ? a : b;
+}
+__host__ __device__ inline int GramEntries(int Kp) {
+	return Kp * (Kp + 1) / 2;
+}
+
 struct Smem {
-	double *coef; // [RB][Kp]
+	double *coef; // [RB][CoefLd]
 	double *bvec; // [RB][Kp]
-	double *trig; // [RB][NEp]
+	double *trig; // [RB][ext_ld]
 	double *gw; // [NWARP][gw_stride]
 	double *stat; // [NWARP][RB][3]
 	double *rmsd; // [RB]
@@ -61,31 +91,20 @@ struct Smem {
 	float *hi; // [RB]
 	int *state; // [RB]
 	int *cnt; // [RB] valid channels (statistics count of the latest fit)
+	unsigned *gtab; // [Kp*(Kp+1)/2]
 	int gw_stride;
-	int NEp;
 };
 
-__host__ __device__ inline int GwStride(int Kp) {
-	int const a = Kp * (Kp + 1);
-	int const b = RB * Kp;
-	return a > b ? a : b;
-}
-
-__host__ __device__ inline int PadNE(int next) {
-	return (next + 3) / 4 * 4;
-}
-
-__device__ __forceinline__ Smem Carve(unsigned char *base, int Kp, int next) {
+__device__ __forceinline__ Smem Carve(unsigned char *base, int Kp, int ext_ld) {
 	Smem s;
-	s.NEp = PadNE(next);
 	s.gw_stride = GwStride(Kp);
 	double *d = reinterpret_cast<double *>(base);
 	s.coef = d;
-	d += RB * Kp;
+	d += RB * CoefLd(Kp);
 	s.bvec = d;
 	d += RB * Kp;
 	s.trig = d;
-	d += RB * s.NEp;
+	d += RB * ext_ld;
 	s.gw = d;
 	d += NWARP * s.gw_stride;
 	s.stat = d;
@@ -96,247 +115,361 @@ __device__ __forceinline__ Smem Carve(unsigned char *base, int Kp, int next) {
 	s.hi = s.lo + RB;
 	s.state = reinterpret_cast<int *>(s.hi + RB);
 	s.cnt = s.state + RB;
+	s.gtab = reinterpret_cast<unsigned *>(s.cnt + RB);
 	return s;
 }
 
-// masked trigonometric sums needed by basis pair (j, k): see the header comment
-__device__ __forceinline__ double GramEntry(double const *trig, int kj, int wj, int kk, int wk) {
-	auto C = [&](int m) {return trig[m == 0 ? 0 : 2 * m];};
-	auto S = [&](int m) {return m == 0 ? 0.0 : (m > 0 ? trig[2 * m - 1] : -trig[-2 * m - 1]);};
-	if (kj == 0 && kk == 0) {
-		return C(0);
+// Gram table entry for bases i >= j: G = (+-trig[i1] +- trig[i2]) / 2; `zero` is a column of the
+// trig sums that is identically zero (S_0)
+__device__ unsigned GramPack(SinusoidFitParams const &p, int i, int j, int zero) {
+	unsigned const pos = (static_cast<unsigned>(i) << 26) | (static_cast<unsigned>(j) << 20);
+	if (i >= p.K || j >= p.K) {
+		return pos | kGramPad | (i == j ? kGramPadDiag : 0u);
 	}
-	if (kj == 0) {
-		return kk == 1 ? S(wk) : C(wk);
+	int const ki = p.kind[i], wi = p.wave[i], kj = p.kind[j], wj = p.wave[j];
+	auto C = [](int m) {return static_cast<unsigned>(m == 0 ? 0 : 2 * m);};
+	auto S = [zero](int m) {return static_cast<unsigned>(m == 0 ? zero : 2 * (m < 0 ? -m : m) - 1);};
+	unsigned i1, i2, neg = 0u;
+	if (ki == 0 && kj == 0) {
+		i1 = i2 = C(0);
+	} else if (ki == 0 || kj == 0) {
+		int const k = (ki == 0) ? kj : ki;
+		int const w = (ki == 0) ? wj : wi;
+		i1 = i2 = (k == 1) ? S(w) : C(w);
+	} else {
+		int const d = wi > wj ? wi - wj : wj - wi;
+		if (ki == 1 && kj == 1) {
+			i1 = C(d);
+			i2 = C(wi + wj);
+			neg = kGramNeg2;
+		} else if (ki == 2 && kj == 2) {
+			i1 = C(d);
+			i2 = C(wi + wj);
+		} else { // one sine (wave a), one cosine (wave b): (S_{a+b} + S_{a-b}) / 2
+			int const a = (ki == 1) ? wi : wj;
+			int const b = (ki == 1) ? wj : wi;
+			i1 = S(a + b);
+			i2 = S(a - b);
+			neg = (a - b < 0) ? kGramNeg2 : 0u;
+		}
 	}
-	if (kk == 0) {
-		return kj == 1 ? S(wj) : C(wj);
-	}
-	int const d = wj > wk ? wj - wk : wk - wj;
-	if (kj == 1 && kk == 1) {
-		return 0.5 * (C(d) - C(wj + wk));
-	}
-	if (kj == 2 && kk == 2) {
-		return 0.5 * (C(d) + C(wj + wk));
-	}
-	// one sine (wave a), one cosine (wave b): (S_{a+b} + S_{a-b}) / 2
-	int const a = (kj == 1) ? wj : wk;
-	int const b = (kj == 1) ? wk : wj;
-	return 0.5 * (S(a + b) + S(a - b));
+	return pos | neg | i1 | (i2 << 8);
 }
 
-// LDL^T of the K x K Gram matrix of one row in this warp's workspace, then the solve.
-// Returns false (warp-uniform) when a pivot is not safely positive.
-__device__ bool WarpSolveRow(SinusoidFitParams const &p, double const *trig, double const *bvec,
-		double *A, double *x) {
-	int const lane = threadIdx.x & 31;
-	int const K = p.K;
-	int const Kp = p.Kp + 1; // leading dimension, odd number of doubles: no bank conflicts
-	// lower triangle of G
-	for (int e = lane; e < K * K; e += 32) {
-		int const i = e / K;
-		int const j = e - i * K;
-		if (j <= i) {
-			A[i * Kp + j] = GramEntry(trig, p.kind[i], p.wave[i], p.kind[j], p.wave[j]);
+// acc[mt][nt] += sum over the warp's channel groups of A[8 mt + r][ch] * B[ch][8 nt + c], where
+// A = mask (WITH_Y: mask * y). 16 channels per step; lane (r8, c4) feeds channels c0 + 4 c4 + s.
+template<int NTC, bool WITH_Y, bool NORMALIZE>
+__device__ __forceinline__ void MaskedContract(double (&acc)[4][NTC][2], SinusoidFitParams const &p,
+		size_t row0, uint8_t *wmask, double const *B, int ldb, int warp, int lane) {
+	int const r8 = lane >> 2;
+	int const c4 = lane & 3;
+	int const n = p.n;
+	float const *yrow[4];
+	uint8_t const *mrow[4];
+	bool live[4];
+#pragma unroll
+	for (int mt = 0; mt < 4; ++mt) {
+		size_t row = row0 + 8 * mt + r8;
+		live[mt] = row < p.num_spectra;
+		row = live[mt] ? row : p.num_spectra - 1;
+		yrow[mt] = p.data + row * p.data_stride;
+		mrow[mt] = NORMALIZE ? p.mask + row * p.mask_stride : wmask + static_cast<size_t>(8 * mt + r8) * n;
+	}
+	for (int c0 = warp * 16; c0 < n; c0 += 16 * NWARP) {
+		int const ch = c0 + 4 * c4;
+		unsigned mw[4];
+		float4 yv[4];
+#pragma unroll
+		for (int mt = 0; mt < 4; ++mt) {
+			mw[mt] = *reinterpret_cast<unsigned const *>(mrow[mt] + ch);
+			if (WITH_Y) {
+				yv[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + ch);
+			}
 		}
+		if (NORMALIZE) {
+#pragma unroll
+			for (int mt = 0; mt < 4; ++mt) {
+				mw[mt] = live[mt] ? (__vcmpne4(mw[mt], 0u) & 0x01010101u) : 0u;
+				*reinterpret_cast<unsigned *>(wmask + static_cast<size_t>(8 * mt + r8) * n + ch) = mw[mt];
+			}
+		}
+		double const *brow = B + static_cast<size_t>(ch) * ldb + r8;
+#pragma unroll
+		for (int s = 0; s < 4; ++s) {
+			double b[NTC];
+#pragma unroll
+			for (int nt = 0; nt < NTC; ++nt) {
+				b[nt] = brow[s * ldb + 8 * nt];
+			}
+			double a[4];
+#pragma unroll
+			for (int mt = 0; mt < 4; ++mt) {
+				bool const m = ((mw[mt] >> (8 * s)) & 0xffu) != 0u;
+				if (WITH_Y) {
+					float const y = s == 0 ? yv[mt].x : (s == 1 ? yv[mt].y : (s == 2 ? yv[mt].z : yv[mt].w));
+					a[mt] = static_cast<double>(__int_as_float(m ? __float_as_int(y) : 0));
+				} else {
+					a[mt] = m ? 1.0 : 0.0;
+				}
+			}
+#pragma unroll
+			for (int nt = 0; nt < NTC; ++nt) {
+#pragma unroll
+				for (int mt = 0; mt < 4; ++mt) {
+					dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+				}
+			}
+		}
+	}
+}
+
+// per-warp partial sums -> shared memory -> dst[r * ld_dst + col0 + c], summed over the warps
+template<int NTC>
+__device__ __forceinline__ void ReducePartials(double const (&acc)[4][NTC][2], Smem const &s,
+		double *dst, int ld_dst, int col0, int warp, int lane, int tid) {
+	constexpr int W = 8 * NTC;
+	double *mine = s.gw + warp * s.gw_stride;
+#pragma unroll
+	for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+		for (int nt = 0; nt < NTC; ++nt) {
+			int const r = 8 * mt + (lane >> 2);
+			int const k = 8 * nt + 2 * (lane & 3);
+			*reinterpret_cast<double2 *>(mine + r * W + k) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
+		}
+	}
+	__syncthreads();
+	for (int e = tid; e < RB * W; e += kSinThreads) {
+		double tot = 0.0;
+#pragma unroll
+		for (int w = 0; w < NWARP; ++w) {
+			tot += s.gw[w * s.gw_stride + e];
+		}
+		int const r = e / W;
+		dst[r * ld_dst + col0 + (e - r * W)] = tot;
+	}
+	__syncthreads();
+}
+
+// Solve of one row by this warp: fills the bordered matrix [[G, .], [b^T, .]] from the trig sums,
+// blocked LDL^T (8 x 8 blocks, trailing updates as DMMA), whose border row ends up as D^-1 L^-1 b,
+// then L^T x = z. Returns false (warp-uniform) when a pivot is not safely positive.
+template<int NT8>
+__device__ bool WarpSolveRow(unsigned const *gtab, double const *trig, double const *bvec, double *A,
+		double *xout, int K, int lane) {
+	constexpr int Kp = 8 * NT8;
+	constexpr int LD = SolveLd(Kp);
+	int const r8 = lane >> 2;
+	int const c4 = lane & 3;
+	int const l8 = lane & 7;
+	for (int e = lane; e < Kp * (Kp + 1) / 2; e += 32) {
+		unsigned const g = gtab[e];
+		double a1 = trig[g & 0xffu];
+		double a2 = trig[(g >> 8) & 0xffu];
+		a1 = (g & kGramNeg1) ? -a1 : a1;
+		a2 = (g & kGramNeg2) ? -a2 : a2;
+		double v = 0.5 * (a1 + a2);
+		if (g & kGramPad) {
+			v = (g & kGramPadDiag) ? 1.0 : 0.0;
+		}
+		A[(g >> 26) * LD + ((g >> 20) & 63u)] = v;
+	}
+	for (int j = lane; j < Kp; j += 32) {
+		A[Kp * LD + j] = bvec[j];
 	}
 	__syncwarp();
 	double maxd = 0.0;
+	double const tol = DBL_EPSILON * K;
 	bool ok = true;
-	for (int k = 0; k < K; ++k) {
-		double const d = A[k * Kp + k];
-		maxd = fmax(maxd, fabs(d));
-		ok = ok && (d > maxd * (DBL_EPSILON * K));
-		double const rcp = fast_rcp_pos(d);
-		// A[i][j] -= A[i][k] * A[j][k] / d for k < j <= i; row i owned by one lane
-		for (int i = k + 1 + lane; i < K; i += 32) {
-			double const l = A[i * Kp + k] * rcp;
-			for (int j = k + 1; j <= i; ++j) {
-				A[i * Kp + j] = fma(-l, A[j * Kp + k], A[i * Kp + j]);
+#pragma unroll 1
+	for (int kb = 0; kb < NT8; ++kb) {
+		int const c0 = 8 * kb;
+		// diagonal block: lane l8 owns row l8, columns in registers, pivots by shuffle
+		double row[8], dinv[8], dneg[8];
+#pragma unroll
+		for (int j = 0; j < 8; ++j) {
+			row[j] = A[(c0 + l8) * LD + c0 + j];
+		}
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			double const dk = __shfl_sync(kFull, row[k], k);
+			maxd = fmax(maxd, fabs(dk));
+			ok = ok && (dk > maxd * tol);
+			double const rk = fast_rcp_pos(dk);
+			dinv[k] = rk;
+			dneg[k] = -dk;
+			double const lk = row[k] * rk;
+#pragma unroll
+			for (int j = k + 1; j < 8; ++j) {
+				double const ajk = __shfl_sync(kFull, row[k], j);
+				row[j] = fma(-lk, ajk, row[j]);
+			}
+			row[k] = (l8 > k) ? lk : row[k];
+		}
+		if (lane < 8) {
+#pragma unroll
+			for (int j = 0; j < 7; ++j) {
+				if (j < lane) {
+					A[(c0 + lane) * LD + c0 + j] = row[j];
+				}
 			}
 		}
 		__syncwarp();
-		// scale the column afterwards (the update above needs the unscaled entries of other rows)
-		for (int i = k + 1 + lane; i < K; i += 32) {
-			A[i * Kp + k] *= rcp;
+		// panel below the block, border row included: w = a - sum_t w_t L_jt, L_ij = w_j / d_j
+		for (int i = c0 + 8 + lane; i <= Kp; i += 32) {
+			double w[8];
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				w[j] = A[i * LD + c0 + j];
+			}
+#pragma unroll
+			for (int j = 1; j < 8; ++j) {
+#pragma unroll
+				for (int t = 0; t < j; ++t) {
+					w[j] = fma(-w[t], A[(c0 + j) * LD + c0 + t], w[j]);
+				}
+			}
+#pragma unroll
+			for (int j = 0; j < 8; ++j) {
+				A[i * LD + c0 + j] = w[j] * dinv[j];
+			}
+		}
+		__syncwarp();
+		// trailing blocks (I, J), kb < J <= I: C -= (L_I D) L_J^T
+		double const nd0 = c4 == 0 ? dneg[0] : (c4 == 1 ? dneg[1] : (c4 == 2 ? dneg[2] : dneg[3]));
+		double const nd1 = c4 == 0 ? dneg[4] : (c4 == 1 ? dneg[5] : (c4 == 2 ? dneg[6] : dneg[7]));
+		for (int I = kb + 1; I < NT8; ++I) {
+			double const *ai = A + (8 * I + r8) * LD + c0 + c4;
+			double const a0 = ai[0] * nd0;
+			double const a1 = ai[4] * nd1;
+			for (int J = kb + 1; J <= I; ++J) {
+				double const *bj = A + (8 * J + r8) * LD + c0 + c4;
+				double *cp = A + (8 * I + r8) * LD + 8 * J + 2 * c4;
+				double x0 = cp[0];
+				double x1 = cp[1];
+				dmma(x0, x1, a0, bj[0]);
+				dmma(x0, x1, a1, bj[4]);
+				cp[0] = x0;
+				cp[1] = x1;
+			}
+		}
+		// border row
+		for (int j = c0 + 8 + lane; j < Kp; j += 32) {
+			double acc = A[Kp * LD + j];
+#pragma unroll
+			for (int t = 0; t < 8; ++t) {
+				acc = fma(A[Kp * LD + c0 + t] * dneg[t], A[j * LD + c0 + t], acc);
+			}
+			A[Kp * LD + j] = acc;
 		}
 		__syncwarp();
 	}
-	// L z = b (column oriented), z /= D, L^T x = z
-	for (int i = lane; i < K; i += 32) {
-		x[i] = bvec[i];
+	// L^T x = z; lane holds x[lane] and x[lane + 32]
+	double xa = (lane < Kp) ? A[Kp * LD + lane] : 0.0;
+	double xb = (Kp > 32 && lane + 32 < Kp) ? A[Kp * LD + lane + 32] : 0.0;
+	for (int k = Kp - 1; k >= 1; --k) {
+		double const xk = (k >= 32) ? __shfl_sync(kFull, xb, k - 32) : __shfl_sync(kFull, xa, k);
+		double const *Lk = A + k * LD;
+		if (lane < k) {
+			xa = fma(-Lk[lane], xk, xa);
+		}
+		if (Kp > 32 && lane + 32 < k) {
+			xb = fma(-Lk[lane + 32], xk, xb);
+		}
+	}
+	if (lane < Kp) {
+		xout[lane] = xa;
+	}
+	if (Kp > 32 && lane + 32 < Kp) {
+		xout[lane + 32] = xb;
 	}
 	__syncwarp();
-	for (int k = 0; k < K; ++k) {
-		double const xk = x[k];
-		for (int i = k + 1 + lane; i < K; i += 32) {
-			x[i] = fma(-A[i * Kp + k], xk, x[i]);
-		}
-		__syncwarp();
-	}
-	for (int i = lane; i < K; i += 32) {
-		x[i] = x[i] / A[i * Kp + i];
-	}
-	__syncwarp();
-	for (int k = K - 1; k >= 0; --k) {
-		double const xk = x[k];
-		for (int i = lane; i < k; i += 32) {
-			x[i] = fma(-A[k * Kp + i], xk, x[i]);
-		}
-		__syncwarp();
-	}
 	return ok;
 }
 
 template<int NT8>
 __global__ void __launch_bounds__(kSinThreads, 1)
 SinusoidFitKernel(SinusoidFitParams const p) {
+	constexpr int Kp = 8 * NT8;
+	constexpr int LDC = CoefLd(Kp);
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	Smem const s = Carve(smem_raw, p.Kp, p.next);
+	Smem const s = Carve(smem_raw, Kp, p.ext_ld);
 	int const tid = threadIdx.x;
 	int const lane = tid & 31;
 	int const warp = tid >> 5;
 	int const n = p.n;
 	int const K = p.K;
-	int const Kp = p.Kp;
-	int const next = p.next;
+	int const ext_ld = p.ext_ld;
 	size_t const num_tiles = (p.num_spectra + RB - 1) / RB;
 	float *wres = p.ws_residual + static_cast<size_t>(blockIdx.x) * RB * n;
 	float *wbest = p.ws_best_fit ? p.ws_best_fit + static_cast<size_t>(blockIdx.x) * RB * n : nullptr;
 	uint8_t *wmask = p.ws_mask + static_cast<size_t>(blockIdx.x) * RB * n;
 	float const clip = p.clip_threshold_sigma;
 
+	if (p.num_fitting_max == 0) { // baseline.cc:1295-1296: kOK, nothing written
+		for (size_t row = static_cast<size_t>(blockIdx.x) * kSinThreads + tid; row < p.num_spectra;
+				row += static_cast<size_t>(gridDim.x) * kSinThreads) {
+			p.status[row] = kStatusOK;
+			p.lsqfit_status[row] = kLsqOK;
+		}
+		return;
+	}
+	for (int e = tid; e < GramEntries(Kp); e += kSinThreads) {
+		int i = static_cast<int>((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+		while ((i + 1) * (i + 2) / 2 <= e) {
+			++i;
+		}
+		while (i * (i + 1) / 2 > e) {
+			--i;
+		}
+		s.gtab[e] = GramPack(p, i, e - i * (i + 1) / 2, p.next);
+	}
+
 	for (size_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 		size_t const row0 = tile * RB;
 		__syncthreads();
-		// ---- P0: working mask, valid counts, masked trigonometric sums (one warp per row) -------
-		for (int r = warp; r < RB; r += NWARP) {
-			size_t const row = row0 + r;
-			if (row >= p.num_spectra) {
-				if (lane == 0) {
-					s.state[r] = kNoRow;
+		// ---- P0: working mask + masked trigonometric sums t = mask x ext (column 0 = valid count) --
+		for (int col0 = 0; col0 < ext_ld; col0 += 32) {
+			double acc[4][4][2];
+#pragma unroll
+			for (int mt = 0; mt < 4; ++mt) {
+#pragma unroll
+				for (int nt = 0; nt < 4; ++nt) {
+					acc[mt][nt][0] = 0.0;
+					acc[mt][nt][1] = 0.0;
 				}
-				continue;
 			}
-			uint8_t const *gm = p.mask + row * p.mask_stride;
-			uint8_t *wm = wmask + static_cast<size_t>(r) * n;
-			int cnt = 0;
-			for (int i = lane * 8; i < n; i += 256) {
-				uint2 v = *reinterpret_cast<uint2 const *>(gm + i);
-				v.x = __vcmpne4(v.x, 0u) & 0x01010101u;
-				v.y = __vcmpne4(v.y, 0u) & 0x01010101u;
-				*reinterpret_cast<uint2 *>(wm + i) = v;
-				cnt += __popc(v.x) + __popc(v.y);
+			if (col0 == 0) {
+				MaskedContract<4, false, true>(acc, p, row0, wmask, p.ext, ext_ld, warp, lane);
+			} else {
+				MaskedContract<4, false, false>(acc, p, row0, wmask, p.ext + col0, ext_ld, warp, lane);
 			}
-			cnt = warp_sum(cnt);
-			__syncwarp();
+			ReducePartials<4>(acc, s, s.trig, ext_ld, col0, warp, lane, tid);
+		}
+		if (tid < RB) {
+			int const cnt = static_cast<int>(s.trig[tid * ext_ld]);
 			int st = kActive;
-			if (p.num_fitting_max == 0) {
-				st = kConverged; // baseline.cc:1295-1296: kOK, nothing written
+			if (row0 + tid >= p.num_spectra) {
+				st = kNoRow;
 			} else if (cnt < K) {
 				st = kFailedBefore; // baseline.cc:1147-1150
 			}
-			if (lane == 0) {
-				s.state[r] = st;
-				s.cnt[r] = cnt;
-			}
-			if (st != kActive) {
-				continue;
-			}
-			bool const complement = (2 * cnt >= n);
-			double acc[3] = { 0.0, 0.0, 0.0 }; // next <= 96 columns: three per lane
-			for (int base = 0; base < n; base += 32) {
-				bool const valid = wm[base + lane] != 0;
-				unsigned b = __ballot_sync(0xffffffffu, complement ? !valid : valid);
-				while (b != 0u) {
-					int const j = __ffs(b) - 1;
-					b &= b - 1u;
-					double const *er = p.ext + static_cast<size_t>(base + j) * next;
-#pragma unroll
-					for (int q = 0; q < 3; ++q) {
-						int const e = lane + 32 * q;
-						if (e < next) {
-							acc[q] += er[e];
-						}
-					}
-				}
-			}
-#pragma unroll
-			for (int q = 0; q < 3; ++q) {
-				int const e = lane + 32 * q;
-				if (e < next) {
-					s.trig[r * s.NEp + e] = complement ? (p.ext_all[e] - acc[q]) : acc[q];
-				}
-			}
+			s.state[tid] = st;
+			s.cnt[tid] = cnt;
 		}
-		__syncthreads();
-
-		// ---- P1: data moments b = (mask*y) x table on the tensor cores ---------------------------
+		// ---- P1: data moments b = (mask*y) x table ---------------------------------------------------
 		{
-			double c[4][NT8][2];
+			double acc[4][NT8][2];
 #pragma unroll
 			for (int mt = 0; mt < 4; ++mt) {
 #pragma unroll
 				for (int nt = 0; nt < NT8; ++nt) {
-					c[mt][nt][0] = 0.0;
-					c[mt][nt][1] = 0.0;
+					acc[mt][nt][0] = 0.0;
+					acc[mt][nt][1] = 0.0;
 				}
 			}
-			int const per_warp = n / NWARP; // n % 8 == 0 and NWARP == 8: a multiple of... see host check
-			int const c_begin = warp * per_warp;
-			int const arow = lane >> 2; // fragment row / column-of-B index
-			int const acol = lane & 3;
-			bool act1[4];
-#pragma unroll
-			for (int mt = 0; mt < 4; ++mt) {
-				act1[mt] = (s.state[8 * mt + arow] == kActive);
-			}
-			for (int c0 = c_begin; c0 < c_begin + per_warp; c0 += 4) {
-				int const ch = c0 + acol;
-				double a[4];
-#pragma unroll
-				for (int mt = 0; mt < 4; ++mt) {
-					int const r = 8 * mt + arow;
-					size_t const row = row0 + r;
-					double v = 0.0;
-					if (act1[mt]) {
-						float const y = p.data[row * p.data_stride + ch];
-						uint8_t const m = wmask[static_cast<size_t>(r) * n + ch];
-						v = static_cast<double>(__int_as_float(m ? __float_as_int(y) : 0));
-					}
-					a[mt] = v;
-				}
-				double const *trow = p.table + static_cast<size_t>(ch) * Kp + arow;
-#pragma unroll
-				for (int nt = 0; nt < NT8; ++nt) {
-					double const b = trow[8 * nt];
-#pragma unroll
-					for (int mt = 0; mt < 4; ++mt) {
-						dmma(c[mt][nt][0], c[mt][nt][1], a[mt], b);
-					}
-				}
-			}
-			double *mine = s.gw + warp * s.gw_stride; // [RB][Kp]
-#pragma unroll
-			for (int mt = 0; mt < 4; ++mt) {
-#pragma unroll
-				for (int nt = 0; nt < NT8; ++nt) {
-					int const r = 8 * mt + (lane >> 2);
-					int const k = 8 * nt + 2 * (lane & 3);
-					mine[r * Kp + k] = c[mt][nt][0];
-					mine[r * Kp + k + 1] = c[mt][nt][1];
-				}
-			}
-			__syncthreads();
-			for (int e = tid; e < RB * Kp; e += kSinThreads) {
-				double tot = 0.0;
-#pragma unroll
-				for (int w = 0; w < NWARP; ++w) {
-					tot += s.gw[w * s.gw_stride + e];
-				}
-				s.bvec[e] = tot;
-			}
-			__syncthreads();
+			MaskedContract<NT8, true, false>(acc, p, row0, wmask, p.table, Kp, warp, lane);
+			ReducePartials<NT8>(acc, s, s.bvec, Kp, 0, warp, lane, tid);
 		}
 
 		// ---- clip iterations -------------------------------------------------------------------------
@@ -348,8 +481,8 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 					continue;
 				}
 				any_active = true;
-				bool const ok = WarpSolveRow(p, s.trig + r * s.NEp, s.bvec + r * Kp,
-						s.gw + warp * s.gw_stride, s.coef + r * Kp);
+				bool const ok = WarpSolveRow<NT8>(s.gtab, s.trig + r * ext_ld, s.bvec + r * Kp,
+						s.gw + warp * s.gw_stride, s.coef + r * LDC, K, lane);
 				if (!ok) {
 					if (lane == 0) {
 						s.state[r] = kFallback;
@@ -357,68 +490,79 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 						p.fallback_rows[slot] = static_cast<int32_t>(row0 + r);
 					}
 				}
-				for (int k = K + lane; k < Kp; k += 32) {
-					s.coef[r * Kp + k] = 0.0;
-				}
 			}
 			if (__syncthreads_or(any_active ? 1 : 0) == 0) {
 				break;
 			}
-			// (b) model + residual + statistics: coeff x table on the tensor cores
+			// (b) model + residual + statistics: coeff x table, 16 channels per warp step; lane
+			// (r8, c4) ends up with channels c0 + 4 c4 .. + 3 of rows 8 mt + r8
 			{
 				int cnt[4] = { 0, 0, 0, 0 };
 				double sum[4] = { 0.0, 0.0, 0.0, 0.0 };
 				double sq[4] = { 0.0, 0.0, 0.0, 0.0 };
-				int const frow = lane >> 2;
-				int const fk = lane & 3;
+				int const r8 = lane >> 2;
+				int const c4 = lane & 3;
 				bool act[4];
+				float const *yrow[4];
 #pragma unroll
 				for (int mt = 0; mt < 4; ++mt) {
-					act[mt] = (s.state[8 * mt + frow] == kActive);
+					act[mt] = (s.state[8 * mt + r8] == kActive);
+					size_t const row = act[mt] ? row0 + 8 * mt + r8 : row0;
+					yrow[mt] = p.data + row * p.data_stride;
 				}
-				for (int c0 = warp * 8; c0 < n; c0 += 8 * NWARP) {
-					double c[4][2];
+				// B fragment: lane (n = r8, k = c4); column n of half h is channel 4 (n / 2) + (n & 1) + 2 h
+				int const bch = 4 * (r8 >> 1) + (r8 & 1);
+				for (int c0 = warp * 16; c0 < n; c0 += 16 * NWARP) {
+					int const ch = c0 + 4 * c4;
+					float4 yv[4];
+					unsigned mw[4];
 #pragma unroll
 					for (int mt = 0; mt < 4; ++mt) {
-						c[mt][0] = 0.0;
-						c[mt][1] = 0.0;
+						yv[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + ch);
+						mw[mt] = *reinterpret_cast<unsigned const *>(wmask + static_cast<size_t>(8 * mt + r8) * n + ch);
 					}
-					double const *tb = p.table + static_cast<size_t>(c0 + frow) * Kp + fk;
+					double c[4][2][2];
+#pragma unroll
+					for (int mt = 0; mt < 4; ++mt) {
+						c[mt][0][0] = c[mt][0][1] = c[mt][1][0] = c[mt][1][1] = 0.0;
+					}
+					double const *tb = p.table + static_cast<size_t>(c0 + bch) * Kp + c4;
+#pragma unroll
 					for (int ks = 0; ks < Kp; ks += 4) {
-						double const b = tb[ks];
+						double const b0 = tb[ks];
+						double const b1 = tb[2 * Kp + ks];
 #pragma unroll
 						for (int mt = 0; mt < 4; ++mt) {
-							double const a = s.coef[(8 * mt + frow) * Kp + ks + fk];
-							dmma(c[mt][0], c[mt][1], a, b);
+							double const a = s.coef[(8 * mt + r8) * LDC + ks + c4];
+							dmma(c[mt][0][0], c[mt][0][1], a, b0);
+							dmma(c[mt][1][0], c[mt][1][1], a, b1);
 						}
 					}
-					int const ch = c0 + 2 * fk;
 #pragma unroll
 					for (int mt = 0; mt < 4; ++mt) {
 						if (act[mt]) {
-							int const r = 8 * mt + frow;
-							size_t const row = row0 + r;
-							float2 const y = *reinterpret_cast<float2 const *>(p.data + row * p.data_stride + ch);
-							uchar2 const m = *reinterpret_cast<uchar2 const *>(wmask + static_cast<size_t>(r) * n + ch);
-							float const m0 = static_cast<float>(c[mt][0]);
-							float const m1 = static_cast<float>(c[mt][1]);
-							float const r0 = __fsub_rn(y.x, m0);
-							float const r1 = __fsub_rn(y.y, m1);
-							*reinterpret_cast<float2 *>(wres + static_cast<size_t>(r) * n + ch) = make_float2(r0, r1);
+							int const r = 8 * mt + r8;
+							float4 md, rd;
+							md.x = static_cast<float>(c[mt][0][0]);
+							md.y = static_cast<float>(c[mt][0][1]);
+							md.z = static_cast<float>(c[mt][1][0]);
+							md.w = static_cast<float>(c[mt][1][1]);
+							rd.x = __fsub_rn(yv[mt].x, md.x);
+							rd.y = __fsub_rn(yv[mt].y, md.y);
+							rd.z = __fsub_rn(yv[mt].z, md.z);
+							rd.w = __fsub_rn(yv[mt].w, md.w);
+							*reinterpret_cast<float4 *>(wres + static_cast<size_t>(r) * n + ch) = rd;
 							if (wbest != nullptr) {
-								*reinterpret_cast<float2 *>(wbest + static_cast<size_t>(r) * n + ch) = make_float2(m0, m1);
+								*reinterpret_cast<float4 *>(wbest + static_cast<size_t>(r) * n + ch) = md;
 							}
-							if (m.x) {
-								double const rd = static_cast<double>(r0);
-								++cnt[mt];
-								sum[mt] += rd;
-								sq[mt] = fma(rd, rd, sq[mt]);
-							}
-							if (m.y) {
-								double const rd = static_cast<double>(r1);
-								++cnt[mt];
-								sum[mt] += rd;
-								sq[mt] = fma(rd, rd, sq[mt]);
+							float const rv[4] = { rd.x, rd.y, rd.z, rd.w };
+#pragma unroll
+							for (int q = 0; q < 4; ++q) {
+								bool const m = ((mw[mt] >> (8 * q)) & 0xffu) != 0u;
+								double const v = static_cast<double>(__int_as_float(m ? __float_as_int(rv[q]) : 0));
+								cnt[mt] += m ? 1 : 0;
+								sum[mt] += v;
+								sq[mt] = fma(v, v, sq[mt]);
 							}
 						}
 					}
@@ -427,12 +571,12 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 				for (int mt = 0; mt < 4; ++mt) {
 #pragma unroll
 					for (int o = 1; o <= 2; o <<= 1) {
-						cnt[mt] += __shfl_xor_sync(0xffffffffu, cnt[mt], o);
-						sum[mt] += __shfl_xor_sync(0xffffffffu, sum[mt], o);
-						sq[mt] += __shfl_xor_sync(0xffffffffu, sq[mt], o);
+						cnt[mt] += __shfl_xor_sync(kFull, cnt[mt], o);
+						sum[mt] += __shfl_xor_sync(kFull, sum[mt], o);
+						sq[mt] += __shfl_xor_sync(kFull, sq[mt], o);
 					}
-					if (fk == 0) {
-						double *st = s.stat + (warp * RB + 8 * mt + frow) * 3;
+					if (c4 == 0) {
+						double *st = s.stat + (warp * RB + 8 * mt + r8) * 3;
 						st[0] = static_cast<double>(cnt[mt]);
 						st[1] = sum[mt];
 						st[2] = sq[mt];
@@ -459,7 +603,8 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 			if (iter == p.num_fitting_max) {
 				break;
 			}
-			// (c) clip + downdate, one warp per row, channels in ascending order
+			// (c) clip + downdate, one warp per row: 256 channels per step, clipped channels listed in
+			// shared memory, then subtracted four at a time from lane-private partial sums
 			for (int r = warp; r < RB; r += NWARP) {
 				if (s.state[r] != kActive) {
 					continue;
@@ -470,36 +615,106 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 				uint8_t *wm = wmask + static_cast<size_t>(r) * n;
 				float const *rr = wres + static_cast<size_t>(r) * n;
 				float const *yy = p.data + row * p.data_stride;
-				double *trig = s.trig + r * s.NEp;
-				double *bv = s.bvec + r * Kp;
+				int *list = reinterpret_cast<int *>(s.gw + warp * s.gw_stride);
+				double dt[3] = { 0.0, 0.0, 0.0 };
+				double db[2] = { 0.0, 0.0 };
 				int num_clipped = 0;
-				for (int base = 0; base < n; base += 32) {
-					int const i = base + lane;
-					bool clipped = false;
-					if (i < n - 1 && wm[i] != 0) { // the last channel is never examined
-						clipped = is_clipped(rr[i], lo, hi);
+				for (int cb0 = 0; cb0 < n; cb0 += 256) {
+					int const base = cb0 + lane * 8;
+					unsigned bits = 0u;
+					if (base < n) {
+						uint2 mv = *reinterpret_cast<uint2 const *>(wm + base);
+						float4 const ra = *reinterpret_cast<float4 const *>(rr + base);
+						float4 const rb = *reinterpret_cast<float4 const *>(rr + base + 4);
+						float const rv[8] = { ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w };
+#pragma unroll
+						for (int u = 0; u < 8; ++u) {
+							unsigned const m = ((u < 4 ? mv.x : mv.y) >> (8 * (u & 3))) & 0xffu;
+							// the last channel is never examined
+							bool const c = m != 0u && base + u < n - 1 && is_clipped(rv[u], lo, hi);
+							bits |= (c ? 1u : 0u) << u;
+						}
+						if (bits != 0u) {
+#pragma unroll
+							for (int u = 0; u < 8; ++u) {
+								unsigned const clear = ((bits >> u) & 1u) ? ~(0xffu << (8 * (u & 3))) : ~0u;
+								if (u < 4) {
+									mv.x &= clear;
+								} else {
+									mv.y &= clear;
+								}
+							}
+							*reinterpret_cast<uint2 *>(wm + base) = mv;
+						}
 					}
-					unsigned b = __ballot_sync(0xffffffffu, clipped);
-					if (clipped) {
-						wm[i] = 0;
+					int const mine = __popc(bits);
+					int incl = mine;
+#pragma unroll
+					for (int o = 1; o < 32; o <<= 1) {
+						int const v = __shfl_up_sync(kFull, incl, o);
+						incl += (lane >= o) ? v : 0;
 					}
-					num_clipped += __popc(b);
+					int const total = __shfl_sync(kFull, incl, 31);
+					if (total == 0) {
+						continue;
+					}
+					int at = incl - mine;
+					unsigned b = bits;
 					while (b != 0u) {
-						int const j = __ffs(b) - 1;
+						list[at++] = base + __ffs(b) - 1;
 						b &= b - 1u;
-						int const ch = base + j;
-						double const *er = p.ext + static_cast<size_t>(ch) * next;
-						for (int e = lane; e < next; e += 32) {
-							trig[e] -= er[e];
+					}
+					__syncwarp();
+					num_clipped += total;
+					for (int t = 0; t < total; t += 4) {
+						int ch[4];
+						bool v[4];
+						float y[4];
+						double e0[4], e1[4], e2[4], t0[4], t1[4];
+#pragma unroll
+						for (int q = 0; q < 4; ++q) {
+							v[q] = t + q < total;
+							ch[q] = list[v[q] ? t + q : t];
 						}
-						double const yd = static_cast<double>(yy[ch]);
-						double const *tr = p.table + static_cast<size_t>(ch) * Kp;
-						for (int k = lane; k < K; k += 32) {
-							bv[k] = fma(-yd, tr[k], bv[k]);
+#pragma unroll
+						for (int q = 0; q < 4; ++q) {
+							double const *er = p.ext + static_cast<size_t>(ch[q]) * ext_ld;
+							double const *tr = p.table + static_cast<size_t>(ch[q]) * Kp;
+							y[q] = yy[ch[q]];
+							e0[q] = er[lane];
+							e1[q] = (lane + 32 < ext_ld) ? er[lane + 32] : 0.0;
+							e2[q] = (lane + 64 < ext_ld) ? er[lane + 64] : 0.0;
+							t0[q] = (lane < Kp) ? tr[lane] : 0.0;
+							t1[q] = (Kp > 32 && lane + 32 < Kp) ? tr[lane + 32] : 0.0;
 						}
+#pragma unroll
+						for (int q = 0; q < 4; ++q) {
+							double const yd = select_f64(v[q], static_cast<double>(y[q]));
+							dt[0] += select_f64(v[q], e0[q]);
+							dt[1] += select_f64(v[q], e1[q]);
+							dt[2] += select_f64(v[q], e2[q]);
+							db[0] = fma(yd, t0[q], db[0]);
+							db[1] = fma(yd, t1[q], db[1]);
+						}
+					}
+					__syncwarp();
+				}
+				if (num_clipped != 0) {
+					double *trig = s.trig + r * ext_ld;
+					double *bv = s.bvec + r * Kp;
+#pragma unroll
+					for (int q = 0; q < 3; ++q) {
+						if (lane + 32 * q < ext_ld) {
+							trig[lane + 32 * q] -= dt[q];
+						}
+					}
+					if (lane < Kp) {
+						bv[lane] -= db[0];
+					}
+					if (Kp > 32 && lane + 32 < Kp) {
+						bv[lane + 32] -= db[1];
 					}
 				}
-				__syncwarp();
 				if (lane == 0) {
 					if (num_clipped == 0) {
 						s.state[r] = kConverged; // baseline.cc:1211-1213
@@ -523,13 +738,6 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 				if (lane == 0) {
 					p.status[row] = kStatusNG;
 					p.lsqfit_status[row] = kLsqNotEnoughData;
-				}
-				continue;
-			}
-			if (p.num_fitting_max == 0) {
-				if (lane == 0) {
-					p.status[row] = kStatusOK;
-					p.lsqfit_status[row] = kLsqOK;
 				}
 				continue;
 			}
@@ -564,7 +772,7 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 			}
 			if (p.coeff != nullptr) {
 				for (int k = lane; k < K; k += 32) {
-					p.coeff[row * K + k] = s.coef[r * Kp + k]; // no rescale for sinusoids
+					p.coeff[row * K + k] = s.coef[r * LDC + k]; // no rescale for sinusoids
 				}
 			}
 			if (lane == 0) {
@@ -592,10 +800,16 @@ __global__ void GatherTableKernel(double const *ctx_table, int nb_ctx, int n, in
 
 } // namespace
 
+int SinusoidExtLd(int next) {
+	return (next + 31) / 32 * 32;
+}
+
 size_t SinusoidSharedBytes(int Kp, int next) {
-	size_t doubles = static_cast<size_t>(2 * RB * Kp) + static_cast<size_t>(RB) * PadNE(next)
-			+ static_cast<size_t>(NWARP) * GwStride(Kp) + static_cast<size_t>(NWARP) * RB * 3 + RB;
-	return doubles * sizeof(double) + RB * (2 * sizeof(float) + 2 * sizeof(int)) + 32;
+	size_t doubles = static_cast<size_t>(RB) * CoefLd(Kp) + static_cast<size_t>(RB) * Kp
+			+ static_cast<size_t>(RB) * SinusoidExtLd(next) + static_cast<size_t>(NWARP) * GwStride(Kp)
+			+ static_cast<size_t>(NWARP) * RB * 3 + RB;
+	return doubles * sizeof(double) + RB * (2 * sizeof(float) + 2 * sizeof(int))
+			+ GramEntries(Kp) * sizeof(unsigned) + 32;
 }
 
 cudaError_t LaunchGatherTable(double const *ctx_table, int nb_ctx, int n, int K, int Kp,
@@ -617,6 +831,9 @@ static cudaError_t LaunchNT(SinusoidFitParams const &p, int grid, cudaStream_t s
 }
 
 cudaError_t LaunchSinusoidFit(SinusoidFitParams const &p, int grid, cudaStream_t stream) {
+	if (p.ext_ld != SinusoidExtLd(p.next) || p.ext_ld > 96) {
+		return cudaErrorInvalidValue;
+	}
 	switch (p.Kp / 8) {
 	case 1:
 		return LaunchNT<1>(p, grid, stream);

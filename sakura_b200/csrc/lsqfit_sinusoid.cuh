@@ -19,8 +19,8 @@ struct SinusoidFitParams {
 	int Kp; // K rounded up to a multiple of 8
 	int next; // columns of the extended trigonometric table: 2*mmax + 1
 	double const *table; // [n][Kp] selected basis columns (zero padded), built per call
-	double const *ext; // [n][next]: 1, then (sin, cos)(m theta_i) for m = 1..mmax
-	double const *ext_all; // [next]: column sums of ext over all channels (correctly rounded)
+	int ext_ld; // row stride of ext: SinusoidExtLd(next), the padding columns are zero
+	double const *ext; // [n][ext_ld]: 1, then (sin, cos)(m theta_i) for m = 1..mmax
 	// basis k is: kind[k] = 0 constant, 1 sin, 2 cos; wave[k] its wave number
 	int8_t kind[kSinMaxKp];
 	int16_t wave[kSinMaxKp];
@@ -46,6 +46,7 @@ struct SinusoidFitParams {
 };
 
 size_t SinusoidSharedBytes(int Kp, int next);
+int SinusoidExtLd(int next);
 
 /** Gathers the selected columns of the context table into the compact [n][Kp] table. */
 cudaError_t LaunchGatherTable(double const *ctx_table, int nb_ctx, int n, int K, int Kp,
