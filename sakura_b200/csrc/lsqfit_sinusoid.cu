@@ -33,6 +33,9 @@ namespace {
 
 constexpr int RB = kSinRowsPerTile;
 constexpr int NWARP = kSinThreads / 32;
+constexpr int NGROUP = 8; // warp groups that split the channels; also the solve workspaces
+constexpr int MT = 4 * NGROUP / NWARP; // 8-row groups of the tile handled by one warp
+static_assert(MT == 1 || MT == 2 || MT == 4, "warps of a group split the four 8-row groups");
 constexpr unsigned kFull = 0xffffffffu;
 
 enum RowState : int {
@@ -65,6 +68,26 @@ __device__ __forceinline__ double select_f64(bool keep, double v) {
 	return __hiloint2double(keep ? __double2hiint(v) : 0, keep ? __double2loint(v) : 0);
 }
 
+// dst[0..count) = src[0..count) by one warp, eight loads in flight per lane
+template<typename V>
+__device__ __forceinline__ void WarpCopy(V *__restrict__ dst, V const *__restrict__ src, int count, int lane) {
+	int i = lane;
+	for (; i + 7 * 32 < count; i += 8 * 32) {
+		V v[8];
+#pragma unroll
+		for (int u = 0; u < 8; ++u) {
+			v[u] = src[i + 32 * u];
+		}
+#pragma unroll
+		for (int u = 0; u < 8; ++u) {
+			dst[i + 32 * u] = v[u];
+		}
+	}
+	for (; i < count; i += 32) {
+		dst[i] = src[i];
+	}
+}
+
 __host__ __device__ constexpr int SolveLd(int Kp) {
 	return Kp + 2;
 }
@@ -84,8 +107,8 @@ struct Smem {
 	double *coef; // [RB][CoefLd]
 	double *bvec; // [RB][Kp]
 	double *trig; // [RB][ext_ld]
-	double *gw; // [NWARP][gw_stride]
-	double *stat; // [NWARP][RB][3]
+	double *gw; // [NGROUP][gw_stride]
+	double *stat; // [NGROUP][RB][3]
 	double *rmsd; // [RB]
 	float *lo; // [RB]
 	float *hi; // [RB]
@@ -106,9 +129,9 @@ __device__ __forceinline__ Smem Carve(unsigned char *base, int Kp, int ext_ld) {
 	s.trig = d;
 	d += RB * ext_ld;
 	s.gw = d;
-	d += NWARP * s.gw_stride;
+	d += NGROUP * s.gw_stride;
 	s.stat = d;
-	d += NWARP * RB * 3;
+	d += NGROUP * RB * 3;
 	s.rmsd = d;
 	d += RB;
 	s.lo = reinterpret_cast<float *>(d);
@@ -156,31 +179,35 @@ __device__ unsigned GramPack(SinusoidFitParams const &p, int i, int j, int zero)
 	return pos | neg | i1 | (i2 << 8);
 }
 
-// acc[mt][nt] += sum over the warp's channel groups of A[8 mt + r][ch] * B[ch][8 nt + c], where
-// A = mask (WITH_Y: mask * y). 16 channels per step; lane (r8, c4) feeds channels c0 + 4 c4 + s.
+// acc[m][nt] += sum over the warp's channel groups of A[8 (mt0 + m) + r][ch] * B[ch][8 nt + c],
+// where A = mask (WITH_Y: mask * y). A warp pair shares the channel groups and splits the four
+// 8-row groups of the tile (mt0 = 0 or 2). 16 channels per step; lane (r8, c4) feeds channels
+// c0 + 4 c4 + s.
 template<int NTC, bool WITH_Y, bool NORMALIZE>
-__device__ __forceinline__ void MaskedContract(double (&acc)[4][NTC][2], SinusoidFitParams const &p,
+__device__ __forceinline__ void MaskedContract(double (&acc)[MT][NTC][2], SinusoidFitParams const &p,
 		size_t row0, uint8_t *wmask, double const *B, int ldb, int warp, int lane) {
 	int const r8 = lane >> 2;
 	int const c4 = lane & 3;
 	int const n = p.n;
-	float const *yrow[4];
-	uint8_t const *mrow[4];
-	bool live[4];
+	int const mt0 = MT * (warp % (4 / MT));
+	float const *yrow[MT];
+	uint8_t const *mrow[MT];
+	bool live[MT];
 #pragma unroll
-	for (int mt = 0; mt < 4; ++mt) {
-		size_t row = row0 + 8 * mt + r8;
+	for (int mt = 0; mt < MT; ++mt) {
+		size_t row = row0 + 8 * (mt0 + mt) + r8;
 		live[mt] = row < p.num_spectra;
 		row = live[mt] ? row : p.num_spectra - 1;
 		yrow[mt] = p.data + row * p.data_stride;
-		mrow[mt] = NORMALIZE ? p.mask + row * p.mask_stride : wmask + static_cast<size_t>(8 * mt + r8) * n;
+		mrow[mt] = NORMALIZE ? p.mask + row * p.mask_stride
+				: wmask + static_cast<size_t>(8 * (mt0 + mt) + r8) * n;
 	}
-	for (int c0 = warp * 16; c0 < n; c0 += 16 * NWARP) {
+	for (int c0 = (warp / (4 / MT)) * 16; c0 < n; c0 += 16 * NGROUP) {
 		int const ch = c0 + 4 * c4;
-		unsigned mw[4];
-		float4 yv[4];
+		unsigned mw[MT];
+		float4 yv[MT];
 #pragma unroll
-		for (int mt = 0; mt < 4; ++mt) {
+		for (int mt = 0; mt < MT; ++mt) {
 			mw[mt] = *reinterpret_cast<unsigned const *>(mrow[mt] + ch);
 			if (WITH_Y) {
 				yv[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + ch);
@@ -188,9 +215,9 @@ __device__ __forceinline__ void MaskedContract(double (&acc)[4][NTC][2], Sinusoi
 		}
 		if (NORMALIZE) {
 #pragma unroll
-			for (int mt = 0; mt < 4; ++mt) {
+			for (int mt = 0; mt < MT; ++mt) {
 				mw[mt] = live[mt] ? (__vcmpne4(mw[mt], 0u) & 0x01010101u) : 0u;
-				*reinterpret_cast<unsigned *>(wmask + static_cast<size_t>(8 * mt + r8) * n + ch) = mw[mt];
+				*reinterpret_cast<unsigned *>(wmask + static_cast<size_t>(8 * (mt0 + mt) + r8) * n + ch) = mw[mt];
 			}
 		}
 		double const *brow = B + static_cast<size_t>(ch) * ldb + r8;
@@ -201,9 +228,9 @@ __device__ __forceinline__ void MaskedContract(double (&acc)[4][NTC][2], Sinusoi
 			for (int nt = 0; nt < NTC; ++nt) {
 				b[nt] = brow[s * ldb + 8 * nt];
 			}
-			double a[4];
+			double a[MT];
 #pragma unroll
-			for (int mt = 0; mt < 4; ++mt) {
+			for (int mt = 0; mt < MT; ++mt) {
 				bool const m = ((mw[mt] >> (8 * s)) & 0xffu) != 0u;
 				if (WITH_Y) {
 					float const y = s == 0 ? yv[mt].x : (s == 1 ? yv[mt].y : (s == 2 ? yv[mt].z : yv[mt].w));
@@ -215,7 +242,7 @@ __device__ __forceinline__ void MaskedContract(double (&acc)[4][NTC][2], Sinusoi
 #pragma unroll
 			for (int nt = 0; nt < NTC; ++nt) {
 #pragma unroll
-				for (int mt = 0; mt < 4; ++mt) {
+				for (int mt = 0; mt < MT; ++mt) {
 					dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
 				}
 			}
@@ -225,15 +252,16 @@ __device__ __forceinline__ void MaskedContract(double (&acc)[4][NTC][2], Sinusoi
 
 // per-warp partial sums -> shared memory -> dst[r * ld_dst + col0 + c], summed over the warps
 template<int NTC>
-__device__ __forceinline__ void ReducePartials(double const (&acc)[4][NTC][2], Smem const &s,
+__device__ __forceinline__ void ReducePartials(double const (&acc)[MT][NTC][2], Smem const &s,
 		double *dst, int ld_dst, int col0, int warp, int lane, int tid) {
 	constexpr int W = 8 * NTC;
-	double *mine = s.gw + warp * s.gw_stride;
+	double *mine = s.gw + (warp / (4 / MT)) * s.gw_stride; // one [RB][W] buffer per channel group
+	int const mt0 = MT * (warp % (4 / MT));
 #pragma unroll
-	for (int mt = 0; mt < 4; ++mt) {
+	for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
 		for (int nt = 0; nt < NTC; ++nt) {
-			int const r = 8 * mt + (lane >> 2);
+			int const r = 8 * (mt0 + mt) + (lane >> 2);
 			int const k = 8 * nt + 2 * (lane & 3);
 			*reinterpret_cast<double2 *>(mine + r * W + k) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
 		}
@@ -242,7 +270,7 @@ __device__ __forceinline__ void ReducePartials(double const (&acc)[4][NTC][2], S
 	for (int e = tid; e < RB * W; e += kSinThreads) {
 		double tot = 0.0;
 #pragma unroll
-		for (int w = 0; w < NWARP; ++w) {
+		for (int w = 0; w < NGROUP; ++w) {
 			tot += s.gw[w * s.gw_stride + e];
 		}
 		int const r = e / W;
@@ -430,9 +458,9 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 		__syncthreads();
 		// ---- P0: working mask + masked trigonometric sums t = mask x ext (column 0 = valid count) --
 		for (int col0 = 0; col0 < ext_ld; col0 += 32) {
-			double acc[4][4][2];
+			double acc[MT][4][2];
 #pragma unroll
-			for (int mt = 0; mt < 4; ++mt) {
+			for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
 				for (int nt = 0; nt < 4; ++nt) {
 					acc[mt][nt][0] = 0.0;
@@ -459,9 +487,9 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 		}
 		// ---- P1: data moments b = (mask*y) x table ---------------------------------------------------
 		{
-			double acc[4][NT8][2];
+			double acc[MT][NT8][2];
 #pragma unroll
-			for (int mt = 0; mt < 4; ++mt) {
+			for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
 				for (int nt = 0; nt < NT8; ++nt) {
 					acc[mt][nt][0] = 0.0;
@@ -476,7 +504,7 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 		for (int iter = 1; iter <= p.num_fitting_max; ++iter) {
 			// (a) solve, one warp per row
 			bool any_active = false;
-			for (int r = warp; r < RB; r += NWARP) {
+			for (int r = warp; r < RB && warp < NGROUP; r += NGROUP) {
 				if (s.state[r] != kActive) {
 					continue;
 				}
@@ -497,33 +525,37 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 			// (b) model + residual + statistics: coeff x table, 16 channels per warp step; lane
 			// (r8, c4) ends up with channels c0 + 4 c4 .. + 3 of rows 8 mt + r8
 			{
-				int cnt[4] = { 0, 0, 0, 0 };
-				double sum[4] = { 0.0, 0.0, 0.0, 0.0 };
-				double sq[4] = { 0.0, 0.0, 0.0, 0.0 };
+				int cnt[MT];
+				double sum[MT], sq[MT];
 				int const r8 = lane >> 2;
 				int const c4 = lane & 3;
-				bool act[4];
-				float const *yrow[4];
+				int const mt0 = MT * (warp % (4 / MT));
+				bool act[MT];
+				float const *yrow[MT];
 #pragma unroll
-				for (int mt = 0; mt < 4; ++mt) {
-					act[mt] = (s.state[8 * mt + r8] == kActive);
-					size_t const row = act[mt] ? row0 + 8 * mt + r8 : row0;
+				for (int mt = 0; mt < MT; ++mt) {
+					cnt[mt] = 0;
+					sum[mt] = 0.0;
+					sq[mt] = 0.0;
+					act[mt] = (s.state[8 * (mt0 + mt) + r8] == kActive);
+					size_t const row = act[mt] ? row0 + 8 * (mt0 + mt) + r8 : row0;
 					yrow[mt] = p.data + row * p.data_stride;
 				}
 				// B fragment: lane (n = r8, k = c4); column n of half h is channel 4 (n / 2) + (n & 1) + 2 h
 				int const bch = 4 * (r8 >> 1) + (r8 & 1);
-				for (int c0 = warp * 16; c0 < n; c0 += 16 * NWARP) {
+				for (int c0 = (warp / (4 / MT)) * 16; c0 < n; c0 += 16 * NGROUP) {
 					int const ch = c0 + 4 * c4;
-					float4 yv[4];
-					unsigned mw[4];
+					float4 yv[MT];
+					unsigned mw[MT];
 #pragma unroll
-					for (int mt = 0; mt < 4; ++mt) {
+					for (int mt = 0; mt < MT; ++mt) {
 						yv[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + ch);
-						mw[mt] = *reinterpret_cast<unsigned const *>(wmask + static_cast<size_t>(8 * mt + r8) * n + ch);
+						mw[mt] = *reinterpret_cast<unsigned const *>(wmask
+								+ static_cast<size_t>(8 * (mt0 + mt) + r8) * n + ch);
 					}
-					double c[4][2][2];
+					double c[MT][2][2];
 #pragma unroll
-					for (int mt = 0; mt < 4; ++mt) {
+					for (int mt = 0; mt < MT; ++mt) {
 						c[mt][0][0] = c[mt][0][1] = c[mt][1][0] = c[mt][1][1] = 0.0;
 					}
 					double const *tb = p.table + static_cast<size_t>(c0 + bch) * Kp + c4;
@@ -532,16 +564,16 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 						double const b0 = tb[ks];
 						double const b1 = tb[2 * Kp + ks];
 #pragma unroll
-						for (int mt = 0; mt < 4; ++mt) {
-							double const a = s.coef[(8 * mt + r8) * LDC + ks + c4];
+						for (int mt = 0; mt < MT; ++mt) {
+							double const a = s.coef[(8 * (mt0 + mt) + r8) * LDC + ks + c4];
 							dmma(c[mt][0][0], c[mt][0][1], a, b0);
 							dmma(c[mt][1][0], c[mt][1][1], a, b1);
 						}
 					}
 #pragma unroll
-					for (int mt = 0; mt < 4; ++mt) {
+					for (int mt = 0; mt < MT; ++mt) {
 						if (act[mt]) {
-							int const r = 8 * mt + r8;
+							int const r = 8 * (mt0 + mt) + r8;
 							float4 md, rd;
 							md.x = static_cast<float>(c[mt][0][0]);
 							md.y = static_cast<float>(c[mt][0][1]);
@@ -568,7 +600,7 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 					}
 				}
 #pragma unroll
-				for (int mt = 0; mt < 4; ++mt) {
+				for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
 					for (int o = 1; o <= 2; o <<= 1) {
 						cnt[mt] += __shfl_xor_sync(kFull, cnt[mt], o);
@@ -576,7 +608,7 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 						sq[mt] += __shfl_xor_sync(kFull, sq[mt], o);
 					}
 					if (c4 == 0) {
-						double *st = s.stat + (warp * RB + 8 * mt + r8) * 3;
+						double *st = s.stat + ((warp / (4 / MT)) * RB + 8 * (mt0 + mt) + r8) * 3;
 						st[0] = static_cast<double>(cnt[mt]);
 						st[1] = sum[mt];
 						st[2] = sq[mt];
@@ -586,7 +618,7 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 			__syncthreads();
 			if (tid < RB && s.state[tid] == kActive) {
 				double cd = 0.0, sum = 0.0, sq = 0.0;
-				for (int w = 0; w < NWARP; ++w) {
+				for (int w = 0; w < NGROUP; ++w) {
 					double const *st = s.stat + (w * RB + tid) * 3;
 					cd += st[0];
 					sum += st[1];
@@ -615,17 +647,31 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 				uint8_t *wm = wmask + static_cast<size_t>(r) * n;
 				float const *rr = wres + static_cast<size_t>(r) * n;
 				float const *yy = p.data + row * p.data_stride;
-				int *list = reinterpret_cast<int *>(s.gw + warp * s.gw_stride);
+				int *list = reinterpret_cast<int *>(s.gw) + warp * 256;
 				double dt[3] = { 0.0, 0.0, 0.0 };
 				double db[2] = { 0.0, 0.0 };
 				int num_clipped = 0;
+				// the loads of the next step are issued before this step is examined
+				uint2 mv_next = make_uint2(0u, 0u);
+				float4 ra_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+				float4 rb_next = ra_next;
+				if (lane * 8 < n) {
+					mv_next = *reinterpret_cast<uint2 const *>(wm + lane * 8);
+					ra_next = *reinterpret_cast<float4 const *>(rr + lane * 8);
+					rb_next = *reinterpret_cast<float4 const *>(rr + lane * 8 + 4);
+				}
 				for (int cb0 = 0; cb0 < n; cb0 += 256) {
 					int const base = cb0 + lane * 8;
 					unsigned bits = 0u;
+					uint2 mv = mv_next;
+					float4 const ra = ra_next;
+					float4 const rb = rb_next;
+					if (base + 256 < n) {
+						mv_next = *reinterpret_cast<uint2 const *>(wm + base + 256);
+						ra_next = *reinterpret_cast<float4 const *>(rr + base + 256);
+						rb_next = *reinterpret_cast<float4 const *>(rr + base + 260);
+					}
 					if (base < n) {
-						uint2 mv = *reinterpret_cast<uint2 const *>(wm + base);
-						float4 const ra = *reinterpret_cast<float4 const *>(rr + base);
-						float4 const rb = *reinterpret_cast<float4 const *>(rr + base + 4);
 						float const rv[8] = { ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w };
 #pragma unroll
 						for (int u = 0; u < 8; ++u) {
@@ -647,6 +693,9 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 							*reinterpret_cast<uint2 *>(wm + base) = mv;
 						}
 					}
+					if (__any_sync(kFull, bits != 0u) == 0) {
+						continue;
+					}
 					int const mine = __popc(bits);
 					int incl = mine;
 #pragma unroll
@@ -655,9 +704,6 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 						incl += (lane >= o) ? v : 0;
 					}
 					int const total = __shfl_sync(kFull, incl, 31);
-					if (total == 0) {
-						continue;
-					}
 					int at = incl - mine;
 					unsigned b = bits;
 					while (b != 0u) {
@@ -743,9 +789,7 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 			}
 			uint8_t const *wm = wmask + static_cast<size_t>(r) * n;
 			uint8_t *fm = p.final_mask + row * p.mask_stride;
-			for (int i = lane * 8; i < n; i += 256) {
-				*reinterpret_cast<uint2 *>(fm + i) = *reinterpret_cast<uint2 const *>(wm + i);
-			}
+			WarpCopy(reinterpret_cast<uint2 *>(fm), reinterpret_cast<uint2 const *>(wm), n / 8, lane);
 			if (st == kFailedAfterClip) {
 				if (lane == 0) {
 					p.status[row] = kStatusNG;
@@ -757,18 +801,12 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 				continue;
 			}
 			if (p.residual != nullptr) {
-				float4 const *src = reinterpret_cast<float4 const *>(wres + static_cast<size_t>(r) * n);
-				float4 *dst = reinterpret_cast<float4 *>(p.residual + row * p.data_stride);
-				for (int i = lane; i < n / 4; i += 32) {
-					dst[i] = src[i];
-				}
+				WarpCopy(reinterpret_cast<float4 *>(p.residual + row * p.data_stride),
+						reinterpret_cast<float4 const *>(wres + static_cast<size_t>(r) * n), n / 4, lane);
 			}
 			if (p.best_fit != nullptr) {
-				float4 const *src = reinterpret_cast<float4 const *>(wbest + static_cast<size_t>(r) * n);
-				float4 *dst = reinterpret_cast<float4 *>(p.best_fit + row * p.data_stride);
-				for (int i = lane; i < n / 4; i += 32) {
-					dst[i] = src[i];
-				}
+				WarpCopy(reinterpret_cast<float4 *>(p.best_fit + row * p.data_stride),
+						reinterpret_cast<float4 const *>(wbest + static_cast<size_t>(r) * n), n / 4, lane);
 			}
 			if (p.coeff != nullptr) {
 				for (int k = lane; k < K; k += 32) {
@@ -806,8 +844,8 @@ int SinusoidExtLd(int next) {
 
 size_t SinusoidSharedBytes(int Kp, int next) {
 	size_t doubles = static_cast<size_t>(RB) * CoefLd(Kp) + static_cast<size_t>(RB) * Kp
-			+ static_cast<size_t>(RB) * SinusoidExtLd(next) + static_cast<size_t>(NWARP) * GwStride(Kp)
-			+ static_cast<size_t>(NWARP) * RB * 3 + RB;
+			+ static_cast<size_t>(RB) * SinusoidExtLd(next) + static_cast<size_t>(NGROUP) * GwStride(Kp)
+			+ static_cast<size_t>(NGROUP) * RB * 3 + RB;
 	return doubles * sizeof(double) + RB * (2 * sizeof(float) + 2 * sizeof(int))
 			+ GramEntries(Kp) * sizeof(unsigned) + 32;
 }

@@ -10,7 +10,7 @@ namespace sakura_b200 {
 
 constexpr int kSinRowsPerTile = 32; // spectra fitted together by one CTA (4 DMMA row tiles)
 constexpr int kSinMaxKp = 48; // fitted bases, padded to a multiple of 8
-constexpr int kSinThreads = 256;
+constexpr int kSinThreads = 512;
 
 struct SinusoidFitParams {
 	size_t num_spectra;
