@@ -12,6 +12,7 @@
 #include "lsqfit_general.cuh"
 #include "lsqfit_poly.cuh"
 #include "lsqfit_sinusoid.cuh"
+#include "lsqfit_spline.cuh"
 #include "statistics.cuh"
 
 #include <cuda_runtime.h>
@@ -514,6 +515,57 @@ sakura_Status LaunchFit(Context *c, FitCall const &f, cudaStream_t stream) {
 			fb_index = fb + 1;
 		}
 	}
+	// ---- cubic spline: row-resident kernel on per-piece local moments; same hand-over of nearly
+	// singular rows to the general kernel
+	if (f.type == kFitCubicSpline && f.num_data <= static_cast<size_t>(kSplineMaxChannels)
+			&& f.npiece <= static_cast<size_t>(kSplineMaxPieces)
+			&& SplineFastSupported(static_cast<int>(f.num_data), static_cast<int>(f.npiece))
+			&& f.data_stride % 4 == 0 && f.mask_stride % 4 == 0
+			&& f.num_spectra <= static_cast<size_t>(INT32_MAX)
+			&& (reinterpret_cast<uintptr_t>(f.data) % 16) == 0
+			&& (reinterpret_cast<uintptr_t>(f.mask) % 4) == 0
+			&& (reinterpret_cast<uintptr_t>(f.final_mask) % 4) == 0
+			&& (reinterpret_cast<uintptr_t>(f.residual) % 16) == 0) {
+		SplineFitParams sp;
+		memset(&sp, 0, sizeof(sp));
+		sp.num_spectra = f.num_spectra;
+		sp.n = static_cast<int>(f.num_data);
+		sp.npiece = static_cast<int>(f.npiece);
+		sp.data = f.data;
+		sp.data_stride = f.data_stride;
+		sp.mask = f.mask;
+		sp.mask_stride = f.mask_stride;
+		sp.clip_threshold_sigma = f.clip;
+		sp.num_fitting_max = f.nfit;
+		sp.coeff = f.coeff;
+		sp.coeff_stride = f.coeff_stride;
+		sp.best_fit = f.best_fit;
+		sp.residual = f.residual;
+		sp.final_mask = f.final_mask;
+		sp.rms = f.rms;
+		sp.status = f.status;
+		sp.lsqfit_status = f.lsq;
+		sp.flags = f.flags;
+		sp.boundary = f.boundary;
+		CUDA_TRY(c->d_fallback.Reserve((f.num_spectra + 1) * sizeof(int32_t)));
+		int32_t *fb = c->d_fallback.As<int32_t>();
+		CUDA_TRY(cudaMemsetAsync(fb, 0, sizeof(int32_t), stream));
+		sp.fallback_count = fb;
+		sp.fallback_rows = fb + 1;
+		size_t sgrid = static_cast<size_t>(SplineResidentCtas(sp.n, sp.npiece, info.num_sms));
+		if (sgrid > f.num_spectra) {
+			sgrid = f.num_spectra;
+		}
+		cudaError_t e = LaunchSplineFit(sp, static_cast<int>(sgrid), stream);
+		g_launch_count += 1;
+		g_last_kernel = "spline_moments";
+		if (e != cudaSuccess) {
+			SetError("LaunchSplineFit", e);
+			return sakura_Status_kUnknownError;
+		}
+		fb_count = fb;
+		fb_index = fb + 1;
+	}
 	// ---- general path
 	size_t grid = static_cast<size_t>(info.num_sms) * 4;
 	if (fb_index != nullptr) {
@@ -563,7 +615,11 @@ sakura_Status LaunchFit(Context *c, FitCall const &f, cudaStream_t stream) {
 	}
 	cudaError_t e = LaunchGeneralFit(p, static_cast<int>(grid), stream);
 	g_launch_count += 1;
-	g_last_kernel = (fb_index != nullptr) ? "sinusoid_dmma" : "general";
+	if (fb_index == nullptr) {
+		g_last_kernel = "general";
+	} else if (f.type == kFitSinusoid) {
+		g_last_kernel = "sinusoid_dmma";
+	}
 	if (e != cudaSuccess) {
 		SetError("LaunchGeneralFit", e);
 		return sakura_Status_kUnknownError;

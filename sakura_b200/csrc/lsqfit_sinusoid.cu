@@ -24,6 +24,7 @@
 // other kernels; results are staged per tile and published only for rows that succeed.
 #include "lsqfit_sinusoid.cuh"
 #include "device_common.cuh"
+#include "ldlt_device.cuh"
 
 #include <float.h>
 
@@ -47,21 +48,6 @@ constexpr unsigned kGramNeg1 = 1u << 16;
 constexpr unsigned kGramNeg2 = 1u << 17;
 constexpr unsigned kGramPadDiag = 1u << 18;
 constexpr unsigned kGramPad = 1u << 19;
-
-__device__ __forceinline__ void dmma(double &c0, double &c1, double a, double b) {
-	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-			: "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-__device__ __forceinline__ double fast_rcp_pos(double x) {
-	double r;
-	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-	double e = fma(-x, r, 1.0);
-	r = fma(r, e, r);
-	e = fma(-x, r, 1.0);
-	r = fma(r, e, r);
-	return r;
-}
 
 __device__ __forceinline__ double select_f64(bool keep, double v) {
 	// v or +0.0 without a branch and without touching v's NaN payloads when dropped
@@ -88,14 +74,11 @@ __device__ __forceinline__ void WarpCopy(V *__restrict__ dst, V const *__restric
 	}
 }
 
-__host__ __device__ constexpr int SolveLd(int Kp) {
-	return Kp + 2;
-}
 __host__ __device__ constexpr int CoefLd(int Kp) {
 	return Kp + 4; // 2*ld mod 32 == 8 or 24: DMMA A-fragment loads without bank conflicts
 }
 __host__ __device__ inline int GwStride(int Kp) {
-	int const a = (Kp + 1) * SolveLd(Kp); // bordered matrix of the solve
+	int const a = (Kp + 1) * LdltLd(Kp); // bordered matrix of the solve
 	int const b = RB * (Kp > 32 ? Kp : 32); // per-warp partial sums of the contractions
 	return a > b ? a : b;
 }
@@ -286,10 +269,7 @@ template<int NT8>
 __device__ bool WarpSolveRow(unsigned const *gtab, double const *trig, double const *bvec, double *A,
 		double *xout, int K, int lane) {
 	constexpr int Kp = 8 * NT8;
-	constexpr int LD = SolveLd(Kp);
-	int const r8 = lane >> 2;
-	int const c4 = lane & 3;
-	int const l8 = lane & 7;
+	constexpr int LD = LdltLd(Kp);
 	for (int e = lane; e < Kp * (Kp + 1) / 2; e += 32) {
 		unsigned const g = gtab[e];
 		double a1 = trig[g & 0xffu];
@@ -306,113 +286,7 @@ __device__ bool WarpSolveRow(unsigned const *gtab, double const *trig, double co
 		A[Kp * LD + j] = bvec[j];
 	}
 	__syncwarp();
-	double maxd = 0.0;
-	double const tol = DBL_EPSILON * K;
-	bool ok = true;
-#pragma unroll 1
-	for (int kb = 0; kb < NT8; ++kb) {
-		int const c0 = 8 * kb;
-		// diagonal block: lane l8 owns row l8, columns in registers, pivots by shuffle
-		double row[8], dinv[8], dneg[8];
-#pragma unroll
-		for (int j = 0; j < 8; ++j) {
-			row[j] = A[(c0 + l8) * LD + c0 + j];
-		}
-#pragma unroll
-		for (int k = 0; k < 8; ++k) {
-			double const dk = __shfl_sync(kFull, row[k], k);
-			maxd = fmax(maxd, fabs(dk));
-			ok = ok && (dk > maxd * tol);
-			double const rk = fast_rcp_pos(dk);
-			dinv[k] = rk;
-			dneg[k] = -dk;
-			double const lk = row[k] * rk;
-#pragma unroll
-			for (int j = k + 1; j < 8; ++j) {
-				double const ajk = __shfl_sync(kFull, row[k], j);
-				row[j] = fma(-lk, ajk, row[j]);
-			}
-			row[k] = (l8 > k) ? lk : row[k];
-		}
-		if (lane < 8) {
-#pragma unroll
-			for (int j = 0; j < 7; ++j) {
-				if (j < lane) {
-					A[(c0 + lane) * LD + c0 + j] = row[j];
-				}
-			}
-		}
-		__syncwarp();
-		// panel below the block, border row included: w = a - sum_t w_t L_jt, L_ij = w_j / d_j
-		for (int i = c0 + 8 + lane; i <= Kp; i += 32) {
-			double w[8];
-#pragma unroll
-			for (int j = 0; j < 8; ++j) {
-				w[j] = A[i * LD + c0 + j];
-			}
-#pragma unroll
-			for (int j = 1; j < 8; ++j) {
-#pragma unroll
-				for (int t = 0; t < j; ++t) {
-					w[j] = fma(-w[t], A[(c0 + j) * LD + c0 + t], w[j]);
-				}
-			}
-#pragma unroll
-			for (int j = 0; j < 8; ++j) {
-				A[i * LD + c0 + j] = w[j] * dinv[j];
-			}
-		}
-		__syncwarp();
-		// trailing blocks (I, J), kb < J <= I: C -= (L_I D) L_J^T
-		double const nd0 = c4 == 0 ? dneg[0] : (c4 == 1 ? dneg[1] : (c4 == 2 ? dneg[2] : dneg[3]));
-		double const nd1 = c4 == 0 ? dneg[4] : (c4 == 1 ? dneg[5] : (c4 == 2 ? dneg[6] : dneg[7]));
-		for (int I = kb + 1; I < NT8; ++I) {
-			double const *ai = A + (8 * I + r8) * LD + c0 + c4;
-			double const a0 = ai[0] * nd0;
-			double const a1 = ai[4] * nd1;
-			for (int J = kb + 1; J <= I; ++J) {
-				double const *bj = A + (8 * J + r8) * LD + c0 + c4;
-				double *cp = A + (8 * I + r8) * LD + 8 * J + 2 * c4;
-				double x0 = cp[0];
-				double x1 = cp[1];
-				dmma(x0, x1, a0, bj[0]);
-				dmma(x0, x1, a1, bj[4]);
-				cp[0] = x0;
-				cp[1] = x1;
-			}
-		}
-		// border row
-		for (int j = c0 + 8 + lane; j < Kp; j += 32) {
-			double acc = A[Kp * LD + j];
-#pragma unroll
-			for (int t = 0; t < 8; ++t) {
-				acc = fma(A[Kp * LD + c0 + t] * dneg[t], A[j * LD + c0 + t], acc);
-			}
-			A[Kp * LD + j] = acc;
-		}
-		__syncwarp();
-	}
-	// L^T x = z; lane holds x[lane] and x[lane + 32]
-	double xa = (lane < Kp) ? A[Kp * LD + lane] : 0.0;
-	double xb = (Kp > 32 && lane + 32 < Kp) ? A[Kp * LD + lane + 32] : 0.0;
-	for (int k = Kp - 1; k >= 1; --k) {
-		double const xk = (k >= 32) ? __shfl_sync(kFull, xb, k - 32) : __shfl_sync(kFull, xa, k);
-		double const *Lk = A + k * LD;
-		if (lane < k) {
-			xa = fma(-Lk[lane], xk, xa);
-		}
-		if (Kp > 32 && lane + 32 < k) {
-			xb = fma(-Lk[lane + 32], xk, xb);
-		}
-	}
-	if (lane < Kp) {
-		xout[lane] = xa;
-	}
-	if (Kp > 32 && lane + 32 < Kp) {
-		xout[lane + 32] = xb;
-	}
-	__syncwarp();
-	return ok;
+	return WarpLdltSolve<NT8>(A, K, xout, lane);
 }
 
 template<int NT8>

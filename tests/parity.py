@@ -109,3 +109,28 @@ def compare_fit(g, o, data, clip, poly_rescale_n=None, coeff_rtol=1e-5, coeff_at
             ok = (diff <= coeff_atol) | (diff <= coeff_rtol * np.abs(oc)) | (diff <= coeff_rtol * norm)
             assert np.all(ok), float(diff.max())
     return reported
+
+
+def spline_truth_residual(data_row, final_mask_row, boundary_row, npiece):
+    """Residual of the cubic-spline fit solved by float64 SVD least squares on the channels of
+    final_mask, with the basis of baseline.cc:911-980 built from the given boundaries. The normal
+    equations the reference (and the GPU path) solve have cond ~ 2e11 at 20 pieces; this solver
+    works on the design matrix itself (cond ~ 5e5) and is the arbiter when the two disagree."""
+    n = data_row.shape[0]
+    i = np.arange(n, dtype=np.float64)
+    max_x = float(n - 1)
+    x = i / max_x
+    cols = [np.ones(n), x, x * x]
+    x3 = x * x * x
+    bnd = [float(b) for b in boundary_row]
+    cube = [None] + [((i - bnd[j]) / max_x) ** 3 for j in range(1, npiece + 1)]
+    if npiece > 1:
+        x3 = x3 - np.maximum(cube[1], 0.0)
+    cols.append(x3)
+    for j in range(2, npiece + 1):
+        cols.append(np.maximum(cube[j - 1] - np.maximum(cube[j], 0.0), 0.0))
+    phi = np.stack(cols, axis=1)
+    sel = final_mask_row.astype(bool)
+    c, *_ = np.linalg.lstsq(phi[sel], data_row[sel].astype(np.float64), rcond=None)
+    model = (phi @ c).astype(np.float32)
+    return (data_row.astype(np.float32) - model).astype(np.float64)

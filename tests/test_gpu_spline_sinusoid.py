@@ -1,4 +1,4 @@
-"""GPU parity of the cubic-spline and sinusoid fits against the oracle (general kernel)."""
+"""GPU parity of the cubic-spline and sinusoid fits against the oracle (fast kernels; near-singular rows go through the general kernel)."""
 import ctypes as C
 import os
 
@@ -7,7 +7,7 @@ import pytest
 
 from sakura_b200 import synth
 from sakura_b200.capi import STATUS_NG, STATUS_OK, aligned_copy, aligned_empty
-from parity import compare_fit
+from parity import compare_fit, spline_truth_residual
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -28,12 +28,30 @@ def check_spline(g, o, data, clip):
     # reference itself differ by up to 1.8e-3 relative there, so parity is
     # gated on status / boundary / mask / rms / best_fit / residual and coefficients are bounded
     # against that spread.
-    reported = compare_fit(g, o, data, clip, check_coeff=False, resid_atol=2e-5)
+    # The reference's own residual is only good to ~2e-5 here (measured against an SVD solve of
+    # the design matrix, tools/spline_truth.py: CPU reference 1.7e-5, GPU 2.9e-6), so the
+    # comparison with the reference uses that bound and the GPU result is additionally held to
+    # float rounding of the well-conditioned solution.
+    reported = compare_fit(g, o, data, clip, check_coeff=False, resid_atol=5e-5)
     good = o["status"] == STATUS_OK
     assert np.array_equal(g["boundary"][good], o["boundary"][good])
     gc, oc = g["coeff"][good], o["coeff"][good]
     scale = np.abs(oc).max(axis=(1, 2), keepdims=True)
     assert np.all(np.abs(gc - oc) <= 5e-3 * scale)
+    data2 = np.atleast_2d(data)
+    npiece = g["boundary"].shape[-1] - 1
+    g_res, g_fm = np.atleast_2d(g["residual"]), np.atleast_2d(g["final_mask"])
+    o_fm, o_bnd = np.atleast_2d(o["final_mask"]), np.atleast_2d(o["boundary"])
+    for r in np.flatnonzero(np.atleast_1d(good))[:24]:
+        fm = o_fm[r].astype(bool)
+        if fm.sum() < 8 * (npiece + 3) or not np.array_equal(fm, g_fm[r].astype(bool)):
+            continue
+        if not np.all(np.isfinite(data2[r][fm])):
+            continue
+        truth = spline_truth_residual(data2[r], fm, o_bnd[r], npiece)
+        tol = 1e-6 + 2.4e-7 * np.abs(data2[r][fm]).max()
+        err = np.abs(g_res[r].astype(np.float64) - truth)[fm].max()
+        assert err <= tol, (int(r), float(err), float(tol))
     return reported
 
 
@@ -41,7 +59,7 @@ def test_config_c3_shape_8192ch_20pieces(lib, oracle):
     data, mask = synth.make_spectra(96, 8192, seed=61, ripple=True)
     synth.add_edge_case_rows(data, mask, 23)
     g, o = spline_both(lib, oracle, 20, data, mask, 3.0, 3)
-    assert lib.last_kernel_name() == "general"
+    assert lib.last_kernel_name() == "spline_moments"
     assert check_spline(g, o, data, 3.0) == []
 
 
