@@ -128,11 +128,17 @@ __device__ void Boundaries(int n, int npiece, int num_valid, Smem const &s, int 
 		s.bound[0] = 0;
 		s.bound[npiece] = n;
 	}
-	long long const N = num_valid;
+	// rank targets once per row (64-bit divisions), then every thread only compares
+	int *tgt = reinterpret_cast<int *>(s.loc);
+	if (tid >= 1 && tid < npiece) {
+		long long const N = num_valid;
+		tgt[tid] = static_cast<int>((N * tid + npiece - 1) / npiece);
+	}
+	__syncthreads();
 	for (int idx = 1; idx < npiece; ++idx) {
-		long long const target = (N * idx + npiece - 1) / npiece;
+		int const target = tgt[idx];
 		if (target >= start && target < start + cnt) {
-			int rem = static_cast<int>(target - start);
+			int rem = target - start;
 			for (int i = lo; i < hi; i += 4) {
 				unsigned const w = *reinterpret_cast<unsigned const *>(s.wm + i);
 				int const c = __popc(w);
