@@ -405,12 +405,17 @@ def run_ours(args) -> None:
         peak, peak_src = measured_peak_gbs()
         bps = bytes_per_spectrum(n, K)
         achieved = rows * bps / (ms_step * 1e-3) / 1e9
+        # DRAM bytes of one launch: the ncu capture (profiles/) measured bytes per spectrum on a
+        # 131072-row launch of the same kernel and shape; scaled to this launch's row count
         traffic = None
+        traffic_src = None
         tpath = os.path.join(HERE, "profiles", "traffic_per_launch.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and n == 4096 and K == 6:
             try:
                 with open(tpath) as fh:
-                    traffic = json.load(fh)
+                    t = json.load(fh)
+                traffic = float(t["dram_bytes_per_spectrum"]) * rows
+                traffic_src = t.get("source")
             except Exception:
                 traffic = None
         line = {
@@ -423,7 +428,8 @@ def run_ours(args) -> None:
             "e2e": e2e,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src,
                          "kernel": kernel_name, "bytes_per_spectrum": bps,
                          "spectra_per_launch": rows},
             "cpu_baseline": cpu,
