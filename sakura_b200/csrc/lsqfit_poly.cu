@@ -448,7 +448,9 @@ __device__ __forceinline__ bool UpdateAndSolve(Shared<K, NT> &sh, PolyConst cons
 	return ok;
 }
 
-template<int K, int NT>
+// FULL: n == 4 * NT * kSlotGroups (4096 channels at 128 threads, 8192 at 256), every thread owns
+// all 32 channel slots and the per-group bounds checks disappear.
+template<int K, int NT, bool FULL>
 __global__ void __launch_bounds__(NT, (NT == 128 ? (K >= 7 ? 4 : kMinBlocks128) :
 		(K >= 7 ? 2 : kMinBlocks256)))
 PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
@@ -494,7 +496,7 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 #pragma unroll
 		for (int j = 0; j < kSlotGroups; ++j) {
 			int const g = tid + NT * j;
-			if (g < ng) {
+			if (FULL || g < ng) {
 				float4 const y = __ldg(gdata + g);
 				uint32_t m = __ldg(gmask + g);
 				reinterpret_cast<float4 *>(sdata)[g] = y;
@@ -605,7 +607,7 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 #pragma unroll
 			for (int j = 0; j < kSlotGroups; ++j) {
 				int const g = tid + NT * j;
-				if (g < ng) {
+				if (FULL || g < ng) {
 					float4 const y = reinterpret_cast<float4 const *>(sdata)[g];
 					float const ye[4] = { y.x, y.y, y.z, y.w };
 					float re[4];
@@ -620,7 +622,11 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 						float const mf = static_cast<float>(acc);
 						float const r = __fsub_rn(ye[e], mf);
 						re[e] = r;
-						masked_accumulate(sum, sq, static_cast<double>(r), vbits & (1u << (4 * j + e)));
+						// flagged channels contribute +0.0: one integer select on the float, then
+						// unconditional FP64 accumulation (a predicated DADD/DFMA costs four selects)
+						double const rd = static_cast<double>(select_or_zero(r, vbits & (1u << (4 * j + e))));
+						sum += rd;
+						sq = fma(rd, rd, sq);
 					}
 					reinterpret_cast<float4 *>(sres)[g] = make_float4(re[0], re[1], re[2], re[3]);
 				}
@@ -652,22 +658,46 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 			}
 			// pass B: clip. The last channel is never examined (baseline.cc:1081-1096).
 			uint32_t clipped = 0u;
+			// (r-lo)*(hi-r) < 0 in float (baseline.cc:1088) is the same predicate as
+			// (r < lo) || (r > hi) unless the product can underflow to zero; that is excluded for
+			// the whole row when neither threshold is tiny and the window is not degenerate:
+			// then |r-lo| >= 2^-104 for r != lo and the other factor exceeds hi-lo >= 2^-40.
+			bool const by_compare = fabsf(th.lower) >= 0x1p-80f && fabsf(th.upper) >= 0x1p-80f
+					&& fabsf(th.lower) <= FLT_MAX && fabsf(th.upper) <= FLT_MAX
+					&& __fsub_rn(th.upper, th.lower) >= 0x1p-40f;
+			if (by_compare) {
 #pragma unroll
-			for (int j = 0; j < kSlotGroups; ++j) {
-				int const g = tid + NT * j;
-				if (g < ng) {
-					float4 const r4 = reinterpret_cast<float4 const *>(sres)[g];
-					float const re[4] = { r4.x, r4.y, r4.z, r4.w };
+				for (int j = 0; j < kSlotGroups; ++j) {
+					int const g = tid + NT * j;
+					if (FULL || g < ng) {
+						float4 const r4 = reinterpret_cast<float4 const *>(sres)[g];
+						float const re[4] = { r4.x, r4.y, r4.z, r4.w };
 #pragma unroll
-					for (int e = 0; e < 4; ++e) {
-						if (is_clipped(re[e], th.lower, th.upper)) {
-							clipped |= (1u << (4 * j + e));
+						for (int e = 0; e < 4; ++e) {
+							bool const c = (re[e] < th.lower) || (re[e] > th.upper);
+							clipped |= c ? (1u << (4 * j + e)) : 0u;
 						}
 					}
-					if (g == ng - 1) {
-						clipped &= ~(8u << (4 * j)); // channel n-1
+				}
+			} else {
+#pragma unroll
+				for (int j = 0; j < kSlotGroups; ++j) {
+					int const g = tid + NT * j;
+					if (FULL || g < ng) {
+						float4 const r4 = reinterpret_cast<float4 const *>(sres)[g];
+						float const re[4] = { r4.x, r4.y, r4.z, r4.w };
+#pragma unroll
+						for (int e = 0; e < 4; ++e) {
+							if (is_clipped(re[e], th.lower, th.upper)) {
+								clipped |= (1u << (4 * j + e));
+							}
+						}
 					}
 				}
+			}
+			// channel n-1 is never examined
+			if (((n - 4) >> 2) % NT == tid) {
+				clipped &= ~(8u << (4 * (((n - 4) >> 2) / NT)));
 			}
 			clipped &= vbits;
 			vbits &= ~clipped;
@@ -701,11 +731,13 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 		// ---- final mask (bits -> bytes) ------------------------------------------------------------
 		uint32_t *gfmask = reinterpret_cast<uint32_t *>(p.final_mask + row * p.mask_stride);
 		{
-			uint32_t vb = vbits;
-			for (int g = tid; g < ng; g += NT) {
-				uint32_t const b = vb & 0xfu;
-				gfmask[g] = (b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21);
-				vb >>= 4;
+#pragma unroll
+			for (int j = 0; j < kSlotGroups; ++j) {
+				int const g = tid + NT * j;
+				if (FULL || g < ng) {
+					uint32_t const b = (vbits >> (4 * j)) & 0xfu;
+					gfmask[g] = (b & 1u) | ((b & 2u) << 7) | ((b & 4u) << 14) | ((b & 8u) << 21);
+				}
 			}
 		}
 		if (failed) {
@@ -724,8 +756,12 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 		// is only written after a clip pass that clipped something, and then another fit follows.
 		if (p.residual != nullptr && p.best_fit == nullptr) {
 			float4 *outr = reinterpret_cast<float4 *>(p.residual + row * p.data_stride);
-			for (int g = tid; g < ng; g += NT) {
-				outr[g] = reinterpret_cast<float4 const *>(sres)[g];
+#pragma unroll
+			for (int j = 0; j < kSlotGroups; ++j) {
+				int const g = tid + NT * j;
+				if (FULL || g < ng) {
+					outr[g] = reinterpret_cast<float4 const *>(sres)[g];
+				}
 			}
 		} else if (p.best_fit != nullptr) {
 			float4 *outr = p.residual ? reinterpret_cast<float4 *>(p.residual + row * p.data_stride) :
@@ -735,7 +771,7 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 #pragma unroll
 			for (int j = 0; j < kSlotGroups; ++j) {
 				int const g = tid + NT * j;
-				if (g < ng) {
+				if (FULL || g < ng) {
 					float4 const y = reinterpret_cast<float4 const *>(sdata)[g];
 					float const ye[4] = { y.x, y.y, y.z, y.w };
 					float me[4], re[4];
@@ -822,19 +858,20 @@ PolyConst const &GetPolyConst(int n) {
 	return cache.emplace(n, pc).first->second;
 }
 
-template<int K, int NT>
-cudaError_t LaunchKN(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
+template<int K, int NT, bool FULL>
+cudaError_t LaunchKNF(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
 	size_t const smem = PolySharedBytes<K, NT>(p.n);
 	static int per_sm_cache_n = -1;
 	static int per_sm_cache = 0;
-	cudaError_t err = cudaFuncSetAttribute(PolyFitKernel<K, NT>,
+	cudaError_t err = cudaFuncSetAttribute(PolyFitKernel<K, NT, FULL>,
 			cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
 	if (err != cudaSuccess) {
 		return err;
 	}
 	int per_sm = per_sm_cache;
 	if (per_sm_cache_n != p.n) {
-		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, PolyFitKernel<K, NT>, NT, smem);
+		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, PolyFitKernel<K, NT, FULL>, NT,
+				smem);
 		if (err != cudaSuccess) {
 			return err;
 		}
@@ -848,8 +885,17 @@ cudaError_t LaunchKN(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
 	if (grid > p.num_spectra) {
 		grid = p.num_spectra;
 	}
-	PolyFitKernel<K, NT><<<static_cast<unsigned>(grid), NT, smem, stream>>>(p, GetPolyConst(p.n));
+	PolyFitKernel<K, NT, FULL><<<static_cast<unsigned>(grid), NT, smem, stream>>>(p,
+			GetPolyConst(p.n));
 	return cudaGetLastError();
+}
+
+template<int K, int NT>
+cudaError_t LaunchKN(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
+	if (p.n == 4 * NT * kSlotGroups) {
+		return LaunchKNF<K, NT, true>(p, num_sms, stream);
+	}
+	return LaunchKNF<K, NT, false>(p, num_sms, stream);
 }
 
 template<int K>
