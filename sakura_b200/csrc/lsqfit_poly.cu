@@ -62,20 +62,10 @@ struct Shared {
 
 constexpr int kSlotGroups = 8; // float4 groups per thread: 32 channel slots, one mask bit each
 
-/** value if `keep` is non-zero, else +0.0f -- as an integer select on the bit pattern, so that
- *  the compiler cannot move it behind a float->double conversion (where it would cost two). */
+/** value if `keep` is non-zero, else +0.0f (a select on the bit pattern: a NaN/Inf under the mask
+ *  must not leak, so this cannot be a multiplication by 0/1). */
 __device__ __forceinline__ float select_or_zero(float value, uint32_t keep) {
 	return __int_as_float(keep != 0u ? __float_as_int(value) : 0);
-}
-
-/** sum += rd, sq += rd*rd when `keep` is non-zero, as predicated FP64 instructions (no selects). */
-__device__ __forceinline__ void masked_accumulate(double &sum, double &sq, double rd, uint32_t keep) {
-	asm("{\n\t"
-			".reg .pred p;\n\t"
-			"setp.ne.u32 p, %3, 0;\n\t"
-			"@p add.rn.f64 %0, %0, %2;\n\t"
-			"@p fma.rn.f64 %1, %2, %2, %1;\n\t"
-			"}" : "+d"(sum), "+d"(sq) : "d"(rd), "r"(keep));
 }
 
 /** Coefficients of p(zb + u) in powers of u from those of p(z) in powers of z

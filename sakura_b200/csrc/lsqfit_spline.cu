@@ -42,7 +42,6 @@ __host__ __device__ inline int PaddedBases(int npiece) {
 }
 
 struct Smem {
-	double *X; // [npiece + 1] boundary positions b / (n - 1)
 	double *M; // [npiece][Kp][4] local cubic of every basis in every piece
 	double *W; // [npiece][Kp][4] M_q Hank(h_q)
 	double *H; // [npiece][8] local power sums (7 used)
@@ -61,7 +60,7 @@ struct Smem {
 
 __host__ __device__ inline size_t SmemDoubles(int npiece) {
 	int const Kp = PaddedBases(npiece);
-	return static_cast<size_t>(npiece + 1 + 1) / 2 * 2 + 2 * static_cast<size_t>(npiece) * Kp * 4
+	return 2 * static_cast<size_t>(npiece) * Kp * 4
 			+ static_cast<size_t>(npiece) * (8 + 4 + 4 + 4) + LdltDoubles(Kp) + Kp + 3 * NW;
 }
 
@@ -69,8 +68,6 @@ __device__ __forceinline__ Smem Carve(unsigned char *base, int n, int npiece) {
 	int const Kp = PaddedBases(npiece);
 	Smem s;
 	double *d = reinterpret_cast<double *>(base);
-	s.X = d;
-	d += (npiece + 1 + 1) / 2 * 2;
 	s.M = d;
 	d += npiece * Kp * 4;
 	s.W = d;
@@ -95,6 +92,40 @@ __device__ __forceinline__ Smem Carve(unsigned char *base, int n, int npiece) {
 	s.iscr = s.bound + (npiece + 1 + 3) / 4 * 4;
 	s.wm = reinterpret_cast<uint8_t *>(s.iscr + NW + 4);
 	return s;
+}
+
+// One warp walks the channels [b0, b1) of a piece: the 4-aligned interior four channels per lane
+// (128-bit shared-memory accesses, vec(i) with i % 4 == 0), the <= 3 + 3 channels at the two ends
+// one per lane (one(i)). The order in which channels are visited does not matter to the callers.
+template<class Vec, class One>
+__device__ __forceinline__ void ForPiece(int b0, int b1, int lane, Vec vec, One one) {
+	int const a0 = min((b0 + 3) & ~3, b1);
+	int const a1 = max(b1 & ~3, a0);
+	if (lane < a0 - b0) {
+		one(b0 + lane);
+	} else if (lane >= 16 && lane - 16 < b1 - a1) {
+		one(a1 + lane - 16);
+	}
+	for (int i = a0 + 4 * lane; i < a1; i += 128) {
+		vec(i);
+	}
+}
+
+// local power sums h[m] += u^m (m <= 6) and data moments t[a] += y u^a (a <= 3) of one channel
+__device__ __forceinline__ void AddMoments(double (&h)[7], double (&t)[4], double u, double y) {
+	double const u2 = u * u;
+	double const u3 = u2 * u;
+	h[0] += 1.0;
+	h[1] += u;
+	h[2] += u2;
+	h[3] += u3;
+	h[4] = fma(u2, u2, h[4]);
+	h[5] = fma(u2, u3, h[5]);
+	h[6] = fma(u3, u3, h[6]);
+	t[0] += y;
+	t[1] = fma(y, u, t[1]);
+	t[2] = fma(y, u2, t[2]);
+	t[3] = fma(y, u3, t[3]);
 }
 
 // baseline.cc:808-844: boundary[idx] (1 <= idx < npiece) is the unmasked channel whose rank among
@@ -294,25 +325,21 @@ SplineFitKernel(SplineFitParams const p) {
 			int const b1 = s.bound[q + 1];
 			double h[7] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
 			double t[4] = { 0.0, 0.0, 0.0, 0.0 };
-			for (int i = b0 + lane; i < b1; i += 32) {
-				if (s.wm[i]) {
-					double const u = int_to_double(i - b0) * inv;
-					double const y = static_cast<double>(s.y[i]);
-					double const u2 = u * u;
-					double const u3 = u2 * u;
-					h[0] += 1.0;
-					h[1] += u;
-					h[2] += u2;
-					h[3] += u3;
-					h[4] = fma(u2, u2, h[4]);
-					h[5] = fma(u2, u3, h[5]);
-					h[6] = fma(u3, u3, h[6]);
-					t[0] += y;
-					t[1] = fma(y, u, t[1]);
-					t[2] = fma(y, u2, t[2]);
-					t[3] = fma(y, u3, t[3]);
+			auto one = [&](int i, float yf, bool valid) {
+				if (valid) {
+					AddMoments(h, t, int_to_double(i - b0) * inv, static_cast<double>(yf));
 				}
-			}
+			};
+			ForPiece(b0, b1, lane, [&](int i) {
+				float4 const y = *reinterpret_cast<float4 const *>(s.y + i);
+				unsigned const m = *reinterpret_cast<unsigned const *>(s.wm + i);
+				one(i, y.x, (m & 0xffu) != 0u);
+				one(i + 1, y.y, (m & 0xff00u) != 0u);
+				one(i + 2, y.z, (m & 0xff0000u) != 0u);
+				one(i + 3, y.w, (m & 0xff000000u) != 0u);
+			}, [&](int i) {
+				one(i, s.y[i], s.wm[i] != 0);
+			});
 #pragma unroll
 			for (int m = 0; m < 7; ++m) {
 				h[m] = warp_sum(h[m]);
@@ -424,18 +451,29 @@ SplineFitKernel(SplineFitParams const p) {
 				int const b0 = s.bound[q];
 				int const b1 = s.bound[q + 1];
 				double const l0 = s.loc[4 * q], l1 = s.loc[4 * q + 1], l2 = s.loc[4 * q + 2], l3 = s.loc[4 * q + 3];
-				for (int i = b0 + lane; i < b1; i += 32) {
+				auto one = [&](int i, float yf, bool valid) {
 					double const u = int_to_double(i - b0) * inv;
 					double const m = fma(fma(fma(l3, u, l2), u, l1), u, l0);
-					float const rr = __fsub_rn(s.y[i], static_cast<float>(m));
-					s.r[i] = rr;
-					if (s.wm[i]) {
-						double const rd = static_cast<double>(rr);
-						++c;
-						sum += rd;
-						sq = fma(rd, rd, sq);
-					}
-				}
+					float const rr = __fsub_rn(yf, static_cast<float>(m));
+					// flagged channels contribute +0.0 (a select: NaN/Inf under the mask must not leak)
+					double const rd = static_cast<double>(__int_as_float(valid ? __float_as_int(rr) : 0));
+					c += valid ? 1 : 0;
+					sum += rd;
+					sq = fma(rd, rd, sq);
+					return rr;
+				};
+				ForPiece(b0, b1, lane, [&](int i) {
+					float4 const y = *reinterpret_cast<float4 const *>(s.y + i);
+					unsigned const m = *reinterpret_cast<unsigned const *>(s.wm + i);
+					float4 rr;
+					rr.x = one(i, y.x, (m & 0xffu) != 0u);
+					rr.y = one(i + 1, y.y, (m & 0xff00u) != 0u);
+					rr.z = one(i + 2, y.z, (m & 0xff0000u) != 0u);
+					rr.w = one(i + 3, y.w, (m & 0xff000000u) != 0u);
+					*reinterpret_cast<float4 *>(s.r + i) = rr;
+				}, [&](int i) {
+					s.r[i] = one(i, s.y[i], s.wm[i] != 0);
+				});
 			}
 			block_sum3(c, sum, sq, s.part);
 			ClipThresholds const th = make_thresholds(c, sum, sq, p.clip_threshold_sigma);
@@ -451,28 +489,29 @@ SplineFitKernel(SplineFitParams const p) {
 				double h[7] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
 				double t[4] = { 0.0, 0.0, 0.0, 0.0 };
 				bool mine = false;
-				for (int i = b0 + lane; i < last; i += 32) {
-					if (s.wm[i] && is_clipped(s.r[i], th.lower, th.upper)) {
-						s.wm[i] = 0;
-						++nclip;
-						mine = true;
-						double const u = int_to_double(i - b0) * inv;
-						double const y = static_cast<double>(s.y[i]);
-						double const u2 = u * u;
-						double const u3 = u2 * u;
-						h[0] += 1.0;
-						h[1] += u;
-						h[2] += u2;
-						h[3] += u3;
-						h[4] = fma(u2, u2, h[4]);
-						h[5] = fma(u2, u3, h[5]);
-						h[6] = fma(u3, u3, h[6]);
-						t[0] += y;
-						t[1] = fma(y, u, t[1]);
-						t[2] = fma(y, u2, t[2]);
-						t[3] = fma(y, u3, t[3]);
+				auto hit = [&](int i) { // channel i is clipped: unflag it, remember its moments
+					s.wm[i] = 0;
+					++nclip;
+					mine = true;
+					AddMoments(h, t, int_to_double(i - b0) * inv, static_cast<double>(s.y[i]));
+				};
+				ForPiece(b0, last, lane, [&](int i) {
+					float4 const r = *reinterpret_cast<float4 const *>(s.r + i);
+					unsigned const m = *reinterpret_cast<unsigned const *>(s.wm + i);
+					unsigned bits = 0u;
+					bits |= ((m & 0xffu) != 0u && is_clipped(r.x, th.lower, th.upper)) ? 1u : 0u;
+					bits |= ((m & 0xff00u) != 0u && is_clipped(r.y, th.lower, th.upper)) ? 2u : 0u;
+					bits |= ((m & 0xff0000u) != 0u && is_clipped(r.z, th.lower, th.upper)) ? 4u : 0u;
+					bits |= ((m & 0xff000000u) != 0u && is_clipped(r.w, th.lower, th.upper)) ? 8u : 0u;
+					while (bits != 0u) { // rare
+						hit(i + __ffs(bits) - 1);
+						bits &= bits - 1u;
 					}
-				}
+				}, [&](int i) {
+					if (s.wm[i] && is_clipped(s.r[i], th.lower, th.upper)) {
+						hit(i);
+					}
+				});
 				if (__any_sync(kFull, mine)) {
 #pragma unroll
 					for (int m = 0; m < 7; ++m) {
