@@ -68,11 +68,11 @@ struct PairPipe {
 	bool producer;
 };
 
-__device__ __forceinline__ void PipeInit(uint64_t *bars /*[4]*/) {
+__device__ __forceinline__ void PipeInit(uint64_t *bars /*[4]*/, unsigned consumer_warps) {
 	mbar_init(bars + 0, 1);
 	mbar_init(bars + 1, 1);
-	mbar_init(bars + 2, 2);
-	mbar_init(bars + 3, 2);
+	mbar_init(bars + 2, consumer_warps);
+	mbar_init(bars + 3, consumer_warps);
 }
 
 /** Starts the copy for stage use `use` (the stage must have been released `use / 2` times). */

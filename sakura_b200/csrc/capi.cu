@@ -315,18 +315,22 @@ sakura_Status CreateContext(int type, uint16_t param, size_t num_data, Context *
 		FillSinusoidTable(num_data, param, c->h_basis);
 		if (num_data > 1 && param >= 1 && 4 * static_cast<size_t>(param) + 1 <= 96) {
 			// same expression as the reference's table (baseline.cc:356-362), up to 2*nwave
+			// chunk-major layout [chunks][num_data][kSinExtChunkLd], 32 columns per chunk, zero padded
 			int const cols = 4 * param + 1;
-			size_t const ld = static_cast<size_t>(SinusoidExtLd(cols)); // zero padded columns
+			size_t const chunks = static_cast<size_t>(SinusoidExtLd(cols)) / 32;
+			size_t const chunk_doubles = static_cast<size_t>(num_data) * kSinExtChunkLd;
 			c->ext_cols = cols;
-			c->h_ext = new std::vector<double>(static_cast<size_t>(num_data) * ld, 0.0);
+			c->h_ext = new std::vector<double>(chunks * chunk_doubles, 0.0);
 			double const norm = 2.0 * M_PI / static_cast<double>(num_data - 1);
+			auto at = [&](size_t i, int col) -> double & {
+				return (*c->h_ext)[(col / 32) * chunk_doubles + i * kSinExtChunkLd + (col % 32)];
+			};
 			for (size_t i = 0; i < num_data; ++i) {
-				double *row = c->h_ext->data() + i * ld;
-				row[0] = 1.0;
+				at(i, 0) = 1.0;
 				for (int m = 1; m <= 2 * param; ++m) {
 					double const x = static_cast<double>(i) * static_cast<double>(m) * norm;
-					row[2 * m - 1] = sin(x);
-					row[2 * m] = cos(x);
+					at(i, 2 * m - 1) = sin(x);
+					at(i, 2 * m) = cos(x);
 				}
 			}
 		}
@@ -464,7 +468,7 @@ sakura_Status LaunchFit(Context *c, FitCall const &f, cudaStream_t stream) {
 			if (sgrid > tiles) {
 				sgrid = tiles;
 			}
-			CUDA_TRY(c->d_table.Reserve(n * sp.Kp * sizeof(double)));
+			CUDA_TRY(c->d_table.Reserve(SinusoidTableDoubles(sp.n, sp.Kp) * sizeof(double)));
 			CUDA_TRY(c->d_useidx.Reserve(kMaxBases * sizeof(int16_t)));
 			CUDA_TRY(c->d_fallback.Reserve((f.num_spectra + 1) * sizeof(int32_t)));
 			CUDA_TRY(c->ws_mask.Reserve(sgrid * kSinRowsPerTile * n));
@@ -483,8 +487,11 @@ sakura_Status LaunchFit(Context *c, FitCall const &f, cudaStream_t stream) {
 			}
 			int32_t *fb = c->d_fallback.As<int32_t>();
 			CUDA_TRY(cudaMemsetAsync(fb, 0, sizeof(int32_t), stream));
-			sp.table = c->d_table.As<double>();
-			sp.ext = c->d_ext.As<double>();
+			sp.ld_p = sp.Kp + 1;
+			sp.ld_a = SinusoidLdA(sp.Kp);
+			sp.table_p = c->d_table.As<double>();
+			sp.table_a = sp.table_p + n * sp.ld_p;
+			sp.ext_p = c->d_ext.As<double>();
 			sp.ext_ld = SinusoidExtLd(c->ext_cols);
 			sp.data = f.data;
 			sp.data_stride = f.data_stride;

@@ -25,6 +25,7 @@
 #include "lsqfit_sinusoid.cuh"
 #include "device_common.cuh"
 #include "ldlt_device.cuh"
+#include "async_copy.cuh"
 
 #include <float.h>
 
@@ -77,10 +78,19 @@ __device__ __forceinline__ void WarpCopy(V *__restrict__ dst, V const *__restric
 __host__ __device__ constexpr int CoefLd(int Kp) {
 	return Kp + 4; // 2*ld mod 32 == 8 or 24: DMMA A-fragment loads without bank conflicts
 }
+__host__ __device__ constexpr int LdA(int Kp) {
+	return (Kp + 9) / 16 * 16 + 6; // smallest ld >= Kp with ld % 16 == 6, see the model pass
+}
+__host__ __device__ constexpr int TileDoubles(int Kp) {
+	// largest staged tile: 16 channels of table_a, table_p or one extended-table chunk
+	return 16 * (LdA(Kp) > kSinExtChunkLd ? LdA(Kp) : kSinExtChunkLd);
+}
 __host__ __device__ inline int GwStride(int Kp) {
 	int const a = (Kp + 1) * LdltLd(Kp); // bordered matrix of the solve
-	int const b = RB * (Kp > 32 ? Kp : 32); // per-warp partial sums of the contractions
-	return a > b ? a : b;
+	int const b = RB * (Kp > 32 ? Kp : 32); // per-group partial sums of the contractions
+	int const c = 2 * TileDoubles(Kp); // two stages of table tiles per warp pair
+	int const ab = a > b ? a : b;
+	return ab > c ? ab : c;
 }
 __host__ __device__ inline int GramEntries(int Kp) {
 	return Kp * (Kp + 1) / 2;
@@ -98,6 +108,7 @@ struct Smem {
 	int *state; // [RB]
 	int *cnt; // [RB] valid channels (statistics count of the latest fit)
 	unsigned *gtab; // [Kp*(Kp+1)/2]
+	uint64_t *bars; // [NGROUP][4] mbarriers of the table-tile rings
 	int gw_stride;
 };
 
@@ -117,6 +128,8 @@ __device__ __forceinline__ Smem Carve(unsigned char *base, int Kp, int ext_ld) {
 	d += NGROUP * RB * 3;
 	s.rmsd = d;
 	d += RB;
+	s.bars = reinterpret_cast<uint64_t *>(d);
+	d += NGROUP * 4;
 	s.lo = reinterpret_cast<float *>(d);
 	s.hi = s.lo + RB;
 	s.state = reinterpret_cast<int *>(s.hi + RB);
@@ -166,13 +179,17 @@ __device__ unsigned GramPack(SinusoidFitParams const &p, int i, int j, int zero)
 // where A = mask (WITH_Y: mask * y). A warp pair shares the channel groups and splits the four
 // 8-row groups of the tile (mt0 = 0 or 2). 16 channels per step; lane (r8, c4) feeds channels
 // c0 + 4 c4 + s.
+// The B tiles (16 channels x ldb doubles, contiguous in global memory) arrive through the pair's
+// two-stage bulk-copy ring; the A operands (this lane's mask word and float4 of y per row group)
+// are loaded one step ahead into registers.
 template<int NTC, bool WITH_Y, bool NORMALIZE>
 __device__ __forceinline__ void MaskedContract(double (&acc)[MT][NTC][2], SinusoidFitParams const &p,
-		size_t row0, uint8_t *wmask, double const *B, int ldb, int warp, int lane) {
+		size_t row0, uint8_t *wmask, double const *B, int ldb, PairPipe &pp, int warp, int lane) {
 	int const r8 = lane >> 2;
 	int const c4 = lane & 3;
 	int const n = p.n;
 	int const mt0 = MT * (warp % (4 / MT));
+	unsigned const tile_bytes = 16u * static_cast<unsigned>(ldb) * sizeof(double);
 	float const *yrow[MT];
 	uint8_t const *mrow[MT];
 	bool live[MT];
@@ -185,15 +202,40 @@ __device__ __forceinline__ void MaskedContract(double (&acc)[MT][NTC][2], Sinuso
 		mrow[mt] = NORMALIZE ? p.mask + row * p.mask_stride
 				: wmask + static_cast<size_t>(8 * (mt0 + mt) + r8) * n;
 	}
-	for (int c0 = (warp / (4 / MT)) * 16; c0 < n; c0 += 16 * NGROUP) {
+	unsigned use = pp.it;
+	int const first = (warp / (4 / MT)) * 16;
+	unsigned mw_next[MT];
+	float4 yv_next[MT];
+	if (first < n) {
+		PipeIssue(pp, use, B + static_cast<size_t>(first) * ldb, tile_bytes, lane);
+#pragma unroll
+		for (int mt = 0; mt < MT; ++mt) {
+			mw_next[mt] = *reinterpret_cast<unsigned const *>(mrow[mt] + first + 4 * c4);
+			if (WITH_Y) {
+				yv_next[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + first + 4 * c4);
+			}
+		}
+	}
+	for (int c0 = first; c0 < n; c0 += 16 * NGROUP, ++use) {
 		int const ch = c0 + 4 * c4;
 		unsigned mw[MT];
 		float4 yv[MT];
 #pragma unroll
 		for (int mt = 0; mt < MT; ++mt) {
-			mw[mt] = *reinterpret_cast<unsigned const *>(mrow[mt] + ch);
+			mw[mt] = mw_next[mt];
 			if (WITH_Y) {
-				yv[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + ch);
+				yv[mt] = yv_next[mt];
+			}
+		}
+		int const cn = c0 + 16 * NGROUP;
+		if (cn < n) {
+			PipeIssue(pp, use + 1u, B + static_cast<size_t>(cn) * ldb, tile_bytes, lane);
+#pragma unroll
+			for (int mt = 0; mt < MT; ++mt) {
+				mw_next[mt] = *reinterpret_cast<unsigned const *>(mrow[mt] + cn + 4 * c4);
+				if (WITH_Y) {
+					yv_next[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + cn + 4 * c4);
+				}
 			}
 		}
 		if (NORMALIZE) {
@@ -203,7 +245,7 @@ __device__ __forceinline__ void MaskedContract(double (&acc)[MT][NTC][2], Sinuso
 				*reinterpret_cast<unsigned *>(wmask + static_cast<size_t>(8 * (mt0 + mt) + r8) * n + ch) = mw[mt];
 			}
 		}
-		double const *brow = B + static_cast<size_t>(ch) * ldb + r8;
+		double const *brow = PipeWait(pp, use) + 4 * c4 * ldb + r8;
 #pragma unroll
 		for (int s = 0; s < 4; ++s) {
 			double b[NTC];
@@ -230,7 +272,9 @@ __device__ __forceinline__ void MaskedContract(double (&acc)[MT][NTC][2], Sinuso
 				}
 			}
 		}
+		PipeRelease(pp, use, lane);
 	}
+	pp.it = use;
 }
 
 // per-warp partial sums -> shared memory -> dst[r * ld_dst + col0 + c], summed over the warps
@@ -240,6 +284,7 @@ __device__ __forceinline__ void ReducePartials(double const (&acc)[MT][NTC][2], 
 	constexpr int W = 8 * NTC;
 	double *mine = s.gw + (warp / (4 / MT)) * s.gw_stride; // one [RB][W] buffer per channel group
 	int const mt0 = MT * (warp % (4 / MT));
+	__syncthreads(); // the buffers alias the table-tile stages other warps may still be reading
 #pragma unroll
 	for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -326,6 +371,20 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 		}
 		s.gtab[e] = GramPack(p, i, e - i * (i + 1) / 2, p.next);
 	}
+	// table-tile ring of this warp's pair (group); its stages live in the group's workspace
+	int const group = warp / (4 / MT);
+	if (tid < NGROUP) {
+		PipeInit(s.bars + 4 * tid, 4 / MT);
+	}
+	mbar_fence_init();
+	PairPipe pp;
+	pp.full = s.bars + 4 * group;
+	pp.empty = pp.full + 2;
+	pp.stage = s.gw + group * s.gw_stride;
+	pp.stage_doubles = TileDoubles(Kp);
+	pp.it = 0u;
+	pp.producer = (warp % (4 / MT)) == 0;
+	size_t const ext_chunk = static_cast<size_t>(n) * kSinExtChunkLd;
 
 	for (size_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 		size_t const row0 = tile * RB;
@@ -342,9 +401,10 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 				}
 			}
 			if (col0 == 0) {
-				MaskedContract<4, false, true>(acc, p, row0, wmask, p.ext, ext_ld, warp, lane);
+				MaskedContract<4, false, true>(acc, p, row0, wmask, p.ext_p, kSinExtChunkLd, pp, warp, lane);
 			} else {
-				MaskedContract<4, false, false>(acc, p, row0, wmask, p.ext + col0, ext_ld, warp, lane);
+				MaskedContract<4, false, false>(acc, p, row0, wmask, p.ext_p + (col0 / 32) * ext_chunk,
+						kSinExtChunkLd, pp, warp, lane);
 			}
 			ReducePartials<4>(acc, s, s.trig, ext_ld, col0, warp, lane, tid);
 		}
@@ -370,7 +430,7 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 					acc[mt][nt][1] = 0.0;
 				}
 			}
-			MaskedContract<NT8, true, false>(acc, p, row0, wmask, p.table, Kp, warp, lane);
+			MaskedContract<NT8, true, false>(acc, p, row0, wmask, p.table_p, Kp + 1, pp, warp, lane);
 			ReducePartials<NT8>(acc, s, s.bvec, Kp, 0, warp, lane, tid);
 		}
 
@@ -415,28 +475,55 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 					size_t const row = act[mt] ? row0 + 8 * (mt0 + mt) + r8 : row0;
 					yrow[mt] = p.data + row * p.data_stride;
 				}
-				// B fragment: lane (n = r8, k = c4); column n of half h is channel 4 (n / 2) + (n & 1) + 2 h
-				int const bch = 4 * (r8 >> 1) + (r8 & 1);
-				for (int c0 = (warp / (4 / MT)) * 16; c0 < n; c0 += 16 * NGROUP) {
+				// B fragment: lane (n = r8, k = c4) of the table tile staged in shared memory (16 channels
+				// x ld_a). Column n of half h is channel 4 (n / 2) + 2 (n & 1) + h, so that this lane's C
+				// fragments {c[0][0], c[1][0], c[0][1], c[1][1]} are the 4 consecutive channels 4 c4 .. + 3,
+				// and with ld_a % 16 == 6 the rows {0, 2, 4, 6} + h of a half warp fall into disjoint banks.
+				constexpr int LDA = LdA(Kp);
+				int const brow = 4 * (r8 >> 1) + 2 * (r8 & 1);
+				unsigned const tile_bytes = 16u * LDA * sizeof(double);
+				int const first = group * 16;
+				unsigned use = pp.it;
+				float4 yv_next[MT];
+				unsigned mw_next[MT];
+				if (first < n) {
+					PipeIssue(pp, use, p.table_a + static_cast<size_t>(first) * LDA, tile_bytes, lane);
+#pragma unroll
+					for (int mt = 0; mt < MT; ++mt) {
+						yv_next[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + first + 4 * c4);
+						mw_next[mt] = *reinterpret_cast<unsigned const *>(wmask
+								+ static_cast<size_t>(8 * (mt0 + mt) + r8) * n + first + 4 * c4);
+					}
+				}
+				for (int c0 = first; c0 < n; c0 += 16 * NGROUP, ++use) {
 					int const ch = c0 + 4 * c4;
 					float4 yv[MT];
 					unsigned mw[MT];
 #pragma unroll
 					for (int mt = 0; mt < MT; ++mt) {
-						yv[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + ch);
-						mw[mt] = *reinterpret_cast<unsigned const *>(wmask
-								+ static_cast<size_t>(8 * (mt0 + mt) + r8) * n + ch);
+						yv[mt] = yv_next[mt];
+						mw[mt] = mw_next[mt];
+					}
+					int const cn = c0 + 16 * NGROUP;
+					if (cn < n) {
+						PipeIssue(pp, use + 1u, p.table_a + static_cast<size_t>(cn) * LDA, tile_bytes, lane);
+#pragma unroll
+						for (int mt = 0; mt < MT; ++mt) {
+							yv_next[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + cn + 4 * c4);
+							mw_next[mt] = *reinterpret_cast<unsigned const *>(wmask
+									+ static_cast<size_t>(8 * (mt0 + mt) + r8) * n + cn + 4 * c4);
+						}
 					}
 					double c[MT][2][2];
 #pragma unroll
 					for (int mt = 0; mt < MT; ++mt) {
 						c[mt][0][0] = c[mt][0][1] = c[mt][1][0] = c[mt][1][1] = 0.0;
 					}
-					double const *tb = p.table + static_cast<size_t>(c0 + bch) * Kp + c4;
+					double const *tb = PipeWait(pp, use) + brow * LDA + c4;
 #pragma unroll
 					for (int ks = 0; ks < Kp; ks += 4) {
 						double const b0 = tb[ks];
-						double const b1 = tb[2 * Kp + ks];
+						double const b1 = tb[LDA + ks];
 #pragma unroll
 						for (int mt = 0; mt < MT; ++mt) {
 							double const a = s.coef[(8 * (mt0 + mt) + r8) * LDC + ks + c4];
@@ -444,14 +531,15 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 							dmma(c[mt][1][0], c[mt][1][1], a, b1);
 						}
 					}
+					PipeRelease(pp, use, lane);
 #pragma unroll
 					for (int mt = 0; mt < MT; ++mt) {
 						if (act[mt]) {
 							int const r = 8 * (mt0 + mt) + r8;
 							float4 md, rd;
 							md.x = static_cast<float>(c[mt][0][0]);
-							md.y = static_cast<float>(c[mt][0][1]);
-							md.z = static_cast<float>(c[mt][1][0]);
+							md.y = static_cast<float>(c[mt][1][0]);
+							md.z = static_cast<float>(c[mt][0][1]);
 							md.w = static_cast<float>(c[mt][1][1]);
 							rd.x = __fsub_rn(yv[mt].x, md.x);
 							rd.y = __fsub_rn(yv[mt].y, md.y);
@@ -473,6 +561,7 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 						}
 					}
 				}
+				pp.it = use;
 #pragma unroll
 				for (int mt = 0; mt < MT; ++mt) {
 #pragma unroll
@@ -598,12 +687,12 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 						}
 #pragma unroll
 						for (int q = 0; q < 4; ++q) {
-							double const *er = p.ext + static_cast<size_t>(ch[q]) * ext_ld;
-							double const *tr = p.table + static_cast<size_t>(ch[q]) * Kp;
+							double const *er = p.ext_p + static_cast<size_t>(ch[q]) * kSinExtChunkLd + lane;
+							double const *tr = p.table_p + static_cast<size_t>(ch[q]) * (Kp + 1);
 							y[q] = yy[ch[q]];
-							e0[q] = er[lane];
-							e1[q] = (lane + 32 < ext_ld) ? er[lane + 32] : 0.0;
-							e2[q] = (lane + 64 < ext_ld) ? er[lane + 64] : 0.0;
+							e0[q] = er[0];
+							e1[q] = (32 < ext_ld) ? er[ext_chunk] : 0.0;
+							e2[q] = (64 < ext_ld) ? er[2 * ext_chunk] : 0.0;
 							t0[q] = (lane < Kp) ? tr[lane] : 0.0;
 							t1[q] = (Kp > 32 && lane + 32 < Kp) ? tr[lane + 32] : 0.0;
 						}
@@ -699,14 +788,25 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 	}
 }
 
+// table_p[i][k] (row stride Kp + 1) and table_a[i][k] (row stride LdA(Kp)), zero in the padding
 __global__ void GatherTableKernel(double const *ctx_table, int nb_ctx, int n, int K, int Kp,
-		int16_t const *use_idx, double *table) {
-	size_t const total = static_cast<size_t>(n) * Kp;
+		int16_t const *use_idx, double *tables) {
+	int const ldp = Kp + 1;
+	int const lda = LdA(Kp);
+	size_t const np = static_cast<size_t>(n) * ldp;
+	size_t const total = np + static_cast<size_t>(n) * lda;
 	for (size_t e = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; e < total;
 			e += static_cast<size_t>(gridDim.x) * blockDim.x) {
-		size_t const i = e / Kp;
-		int const k = static_cast<int>(e - i * Kp);
-		table[e] = (k < K) ? ctx_table[i * nb_ctx + use_idx[k]] : 0.0;
+		size_t i;
+		int k;
+		if (e < np) {
+			i = e / ldp;
+			k = static_cast<int>(e - i * ldp);
+		} else {
+			i = (e - np) / lda;
+			k = static_cast<int>((e - np) - i * lda);
+		}
+		tables[e] = (k < K) ? ctx_table[i * nb_ctx + use_idx[k]] : 0.0;
 	}
 }
 
@@ -716,17 +816,25 @@ int SinusoidExtLd(int next) {
 	return (next + 31) / 32 * 32;
 }
 
+int SinusoidLdA(int Kp) {
+	return LdA(Kp);
+}
+
+size_t SinusoidTableDoubles(int n, int Kp) {
+	return static_cast<size_t>(n) * (Kp + 1) + static_cast<size_t>(n) * LdA(Kp);
+}
+
 size_t SinusoidSharedBytes(int Kp, int next) {
 	size_t doubles = static_cast<size_t>(RB) * CoefLd(Kp) + static_cast<size_t>(RB) * Kp
 			+ static_cast<size_t>(RB) * SinusoidExtLd(next) + static_cast<size_t>(NGROUP) * GwStride(Kp)
-			+ static_cast<size_t>(NGROUP) * RB * 3 + RB;
+			+ static_cast<size_t>(NGROUP) * RB * 3 + RB + static_cast<size_t>(NGROUP) * 4;
 	return doubles * sizeof(double) + RB * (2 * sizeof(float) + 2 * sizeof(int))
 			+ GramEntries(Kp) * sizeof(unsigned) + 32;
 }
 
 cudaError_t LaunchGatherTable(double const *ctx_table, int nb_ctx, int n, int K, int Kp,
-		int16_t const *use_idx_dev, double *table, cudaStream_t stream) {
-	GatherTableKernel<<<256, 256, 0, stream>>>(ctx_table, nb_ctx, n, K, Kp, use_idx_dev, table);
+		int16_t const *use_idx_dev, double *tables, cudaStream_t stream) {
+	GatherTableKernel<<<256, 256, 0, stream>>>(ctx_table, nb_ctx, n, K, Kp, use_idx_dev, tables);
 	return cudaGetLastError();
 }
 
@@ -743,7 +851,8 @@ static cudaError_t LaunchNT(SinusoidFitParams const &p, int grid, cudaStream_t s
 }
 
 cudaError_t LaunchSinusoidFit(SinusoidFitParams const &p, int grid, cudaStream_t stream) {
-	if (p.ext_ld != SinusoidExtLd(p.next) || p.ext_ld > 96) {
+	if (p.ext_ld != SinusoidExtLd(p.next) || p.ext_ld > 96 || p.ld_p != p.Kp + 1
+			|| p.ld_a != LdA(p.Kp) || p.n % 16 != 0) {
 		return cudaErrorInvalidValue;
 	}
 	switch (p.Kp / 8) {

@@ -18,9 +18,18 @@ struct SinusoidFitParams {
 	int K; // fitted bases
 	int Kp; // K rounded up to a multiple of 8
 	int next; // columns of the extended trigonometric table: 2*mmax + 1
-	double const *table; // [n][Kp] selected basis columns (zero padded), built per call
-	int ext_ld; // row stride of ext: SinusoidExtLd(next), the padding columns are zero
-	double const *ext; // [n][ext_ld]: 1, then (sin, cos)(m theta_i) for m = 1..mmax
+	// Selected basis columns (zero padded to Kp), built per call, in two row strides so that tiles
+	// of 16 channels are contiguous (one bulk copy) and their shared-memory images are read
+	// without bank conflicts: ld_p = Kp + 1 for the channel-contracting passes (trig sums, data
+	// moments), ld_a = SinusoidLdA(Kp) for the model pass.
+	double const *table_p; // [n][ld_p]
+	double const *table_a; // [n][ld_a]
+	int ld_p;
+	int ld_a;
+	int ext_ld; // columns of the trig sums kept per spectrum: SinusoidExtLd(next) = 32 * chunks
+	// [ext_ld / 32][n][kSinExtChunkLd]: 1, then (sin, cos)(m theta_i) for m = 1..mmax, 32 columns
+	// per chunk (+1 padding column), the columns beyond `next` are zero
+	double const *ext_p;
 	// basis k is: kind[k] = 0 constant, 1 sin, 2 cos; wave[k] its wave number
 	int8_t kind[kSinMaxKp];
 	int16_t wave[kSinMaxKp];
@@ -45,12 +54,17 @@ struct SinusoidFitParams {
 	int32_t *fallback_count;
 };
 
+constexpr int kSinExtChunkLd = 33; // row stride of one 32-column chunk of the extended table
+
 size_t SinusoidSharedBytes(int Kp, int next);
 int SinusoidExtLd(int next);
+int SinusoidLdA(int Kp);
+/** doubles of the two per-call tables together (table_p first, table_a at n * (Kp + 1)). */
+size_t SinusoidTableDoubles(int n, int Kp);
 
-/** Gathers the selected columns of the context table into the compact [n][Kp] table. */
+/** Gathers the selected columns of the context table into table_p and table_a. */
 cudaError_t LaunchGatherTable(double const *ctx_table, int nb_ctx, int n, int K, int Kp,
-		int16_t const *use_idx_host, double *table, cudaStream_t stream);
+		int16_t const *use_idx_dev, double *tables, cudaStream_t stream);
 
 cudaError_t LaunchSinusoidFit(SinusoidFitParams const &p, int grid, cudaStream_t stream);
 
