@@ -470,6 +470,18 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 	for (size_t row = blockIdx.x; row < p.num_spectra; row += gridDim.x) {
 		float4 const *gdata = reinterpret_cast<float4 const *>(p.data + row * p.data_stride);
 		uint32_t const *gmask = reinterpret_cast<uint32_t const *>(p.mask + row * p.mask_stride);
+		// pull this CTA's next row into L2 while this one is being fitted (one bulk prefetch each
+		// for data and mask), so that the next prologue's loads hit L2 instead of HBM
+		if (tid == 0 && row + gridDim.x < p.num_spectra) {
+			size_t const nrow = row + gridDim.x;
+			asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+					:: "l"(p.data + nrow * p.data_stride), "r"(static_cast<unsigned>(n) * 4u) : "memory");
+			uint8_t const *nmask = p.mask + nrow * p.mask_stride;
+			if (n % 16 == 0 && (reinterpret_cast<uintptr_t>(nmask) & 15u) == 0u) {
+				asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+						:: "l"(nmask), "r"(static_cast<unsigned>(n)) : "memory");
+			}
+		}
 		__syncthreads(); // the previous row's shared state is dead
 
 		// ---- prologue: load the row, valid bits, data moments in z = channel index ----------
