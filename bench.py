@@ -81,6 +81,14 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def measured_peaks() -> dict:
+    try:
+        with open(os.path.join(HERE, "MEASURED_PEAKS.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
+
+
 def measured_peak_gbs():
     path = os.path.join(HERE, "MEASURED_PEAKS.json")
     try:
@@ -147,7 +155,7 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------- synthetic data
-def generate_on_device(torch, rows: int, n: int, seed: int, device):
+def generate_on_device(torch, rows: int, n: int, seed: int, device, ripple: bool = False):
     """Synthetic spectra of SURVEY 8(d) generated on the GPU (quintic continuum, Gaussian
     emission lines, single-channel spikes, N(0,1) noise; edges + 2 % random flags + one flagged
     block).  Returns (data float32 [rows, n], mask bool [rows, n])."""
@@ -164,6 +172,11 @@ def generate_on_device(torch, rows: int, n: int, seed: int, device):
         y = torch.zeros(r, n, dtype=torch.float64, device=device)
         for k in range(5, -1, -1):
             y = y * x + co[:, k:k + 1]
+        if ripple:  # standing wave of configs C3/C4 (as sakura_b200/synth.py)
+            amp = 0.5 + 1.5 * torch.rand(r, 1, dtype=torch.float64, device=device, generator=g)
+            kk = torch.randint(1, 21, (r, 1), device=device, generator=g).double()
+            ph = 2.0 * np.pi * torch.rand(r, 1, dtype=torch.float64, device=device, generator=g)
+            y = y + amp * torch.sin(2.0 * np.pi * kk * x[None, :] + ph)
         y = y.float()
         y += torch.randn(r, n, dtype=torch.float32, device=device, generator=g)
         nl = torch.randint(0, 4, (r, 1), device=device, generator=g)
@@ -249,6 +262,76 @@ def workload_config(args, rows_per_step=None) -> dict:
         "l2": "inputs (20 GiB per step) far exceed the 126 MB L2; no explicit flush needed",
         "parallelism": "rows sharded per GPU, no collective",
     }
+
+
+def side_configs(lib, torch, device, rows: int = 16384, n: int = 8192, reps: int = 3) -> dict:
+    """BASELINE configs[2] and [3] at reduced row count (same channels, bases, iterations):
+    device-resident spectra/s of the cubic-spline (20 pieces) and sinusoid (nwave 0..20) fits.
+    Not bench lines of their own; reported under "also" so the round's numbers for the
+    tensor-core kernel are in the same JSON."""
+    out = {}
+    data, mask = generate_on_device(torch, rows, n, seed=20240611 + 7, device=device, ripple=True)
+    res = torch.empty(rows, n, dtype=torch.float32, device=device)
+    fm = torch.empty(rows, n, dtype=torch.bool, device=device)
+    rms = torch.empty(rows, dtype=torch.float32, device=device)
+    st = torch.empty(rows, dtype=torch.int32, device=device)
+    ls = torch.empty(rows, dtype=torch.int32, device=device)
+    stream = torch.cuda.current_stream(device)
+
+    def timeit(fn):
+        for _ in range(2):
+            assert fn() == 0, lib.last_error()
+        torch.cuda.synchronize(device)
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize(device)
+        return e0.elapsed_time(e1) / reps
+
+    peak_hbm = measured_peak_gbs()[0]
+    # C3: cubic spline, 20 pieces, 3 fits
+    npiece = 20
+    s, ctx = lib.create_cubicspline_context(npiece, n)
+    co = torch.empty(rows, npiece, 4, dtype=torch.float64, device=device)
+    bd = torch.empty(rows, npiece + 1, dtype=torch.int64, device=device)
+    ms = timeit(lambda: lib.lib.sakura_LSQFitCubicSplineFloatBatchDevice(
+        ctx, npiece, rows, n, data.data_ptr(), n, mask.data_ptr(), n, 3.0, 3, co.data_ptr(), None,
+        res.data_ptr(), fm.data_ptr(), rms.data_ptr(), bd.data_ptr(), st.data_ptr(), ls.data_ptr(),
+        stream.cuda_stream))
+    bps = n * 10 + 8 * 4 * npiece + 8 * (npiece + 1) + 8
+    out["config_c3_cubic_spline"] = {
+        "workload": f"{rows} x {n} ch, 20 pieces, 3 fits, residual out", "value": rows / (ms * 1e-3),
+        "unit": UNIT, "ms": ms, "kernel": lib.last_kernel_name(), "rows_ok": int((st == 0).sum().item()),
+        "roofline": {"bound": "hbm", "bytes_per_spectrum": bps,
+                     "achieved": rows * bps / (ms * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                     "frac": rows * bps / (ms * 1e-3) / 1e9 / peak_hbm}}
+    lib.destroy_context(ctx)
+    # C4: sinusoid, wave numbers 0..20 (41 bases), 3 fits
+    s, ctx = lib.create_sinusoid_context(20, n)
+    nw = np.arange(21, dtype=np.uint64)
+    co = torch.empty(rows, 41, dtype=torch.float64, device=device)
+    ms = timeit(lambda: lib.lib.sakura_LSQFitSinusoidFloatBatchDevice(
+        ctx, 21, nw.ctypes.data, rows, n, data.data_ptr(), n, mask.data_ptr(), n, 3.0, 3, 41,
+        co.data_ptr(), None, res.data_ptr(), fm.data_ptr(), rms.data_ptr(), st.data_ptr(),
+        ls.data_ptr(), stream.cuda_stream))
+    # FP64 tensor-core work of the kernel: trig sums n x 96, data moments n x 48, model n x 48 per fit
+    flop = 2.0 * n * (96 + 48 + 3 * 48)
+    sm_mhz = measured_peaks().get("sm_max_mhz", 1965.0)
+    peak_tf = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12
+    out["config_c4_sinusoid"] = {
+        "workload": f"{rows} x {n} ch, nwave 0..20 (41 bases), 3 fits, residual out",
+        "value": rows / (ms * 1e-3), "unit": UNIT, "ms": ms, "kernel": lib.last_kernel_name(),
+        "rows_ok": int((st == 0).sum().item()),
+        "roofline": {"bound": "tensor", "flop_per_spectrum": flop,
+                     "achieved": rows * flop / (ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
+                     "frac": rows * flop / (ms * 1e-3) / 1e12 / peak_tf,
+                     "peak_source": "FP64 DMMA/DFMA issue rate measured on this GPU (64 FMA/clk/SM, "
+                                    "tools/microbench.cu; ncu dmma sub-pipe) x 148 SMs x max SM clock"}}
+    lib.destroy_context(ctx)
+    return out
 
 
 # ----------------------------------------------------------------------------- our arm
@@ -339,6 +422,11 @@ def run_ours(args) -> None:
             "value": world * rows / (ms3 * 1e-3), "unit": UNIT, "ms_per_step": ms3,
             "hbm_frac": rows * bytes_per_spectrum(n, K) / (ms3 * 1e-3) / 1e9 / measured_peak_gbs()[0],
             "per_iteration_streaming": streaming_equivalent(n, 3, rows, ms3)}
+    if not args.no_also and world == 1:
+        try:
+            also.update(side_configs(lib, torch, device))
+        except Exception as exc:  # the headline line must not depend on the side configs
+            also["side_configs_error"] = repr(exc)
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region --------------
     e2e = None
