@@ -674,7 +674,13 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 	size_t const dstride = RoundUp(n, 32);
 	bool const fast = (f.type == kFitPolynomial) && PolyFastSupported(n, f.K, dstride, dstride,
 			nullptr, nullptr, nullptr, nullptr, nullptr);
-	size_t chunk_rows = (static_cast<size_t>(96) << 20) / (dstride * sizeof(float));
+	// chunk size of the pipeline in MiB of data (tuning knob; default from measurements on B200)
+	static size_t const chunk_mib = []() -> size_t {
+		char const *e = getenv("SAKURA_B200_CHUNK_MIB");
+		long const v = (e != nullptr) ? atol(e) : 0;
+		return (v >= 1 && v <= 4096) ? static_cast<size_t>(v) : 96;
+	}();
+	size_t chunk_rows = (chunk_mib << 20) / (dstride * sizeof(float));
 	if (chunk_rows < 1) {
 		chunk_rows = 1;
 	}
