@@ -254,6 +254,42 @@ sakura_Status sakura_LSQFitSinusoidFloatBatchDevice(
 		float d_rms[], int32_t d_status[], int32_t d_lsqfit_status[], void *cuda_stream)
 				SAKURA_B200_NOEXCEPT;
 
+/* ---- position-switch calibration ---------------------------
+ * result = scaling_factor * (data - reference) / reference in float: subtract, multiply, true
+ * divide (normalization.cc:128-139). */
+
+/** Replaces sakura_CalibrateDataWithArrayScalingFloat, sakura.h:1137 (normalization.cc:206). */
+sakura_Status sakura_CalibrateDataWithArrayScalingFloat(size_t num_data,
+		float const scaling_factor[/*num_data*/], float const data[/*num_data*/],
+		float const reference[/*num_data*/], float result[/*num_data*/]) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_CalibrateDataWithConstScalingFloat, sakura.h:1178 (normalization.cc:245). */
+sakura_Status sakura_CalibrateDataWithConstScalingFloat(float scaling_factor, size_t num_data,
+		float const data[/*num_data*/], float const reference[/*num_data*/],
+		float result[/*num_data*/]) SAKURA_B200_NOEXCEPT;
+/** NEW. Rows of device arrays; strides in elements, a stride of 0 shares one reference /
+ *  scaling array between all rows; d_scaling_factor NULL selects const_scaling_factor.
+ *  d_result may alias d_data or d_reference. Asynchronous on `cuda_stream`. */
+sakura_Status sakura_CalibrateDataFloatBatchDevice(size_t num_spectra, size_t num_data,
+		float const d_scaling_factor[], size_t scaling_stride, float const_scaling_factor,
+		float const d_data[], size_t data_stride, float const d_reference[],
+		size_t reference_stride, float d_result[], size_t result_stride, void *cuda_stream)
+				SAKURA_B200_NOEXCEPT;
+/** NEW. sakura_LSQFitPolynomialFloatBatchDevice on the calibrated spectra
+ *  scaling * (d_data - d_reference) / d_reference, which are never written to memory: the fit
+ *  kernel calibrates each row while loading it. With flag_nan_or_inf the mask the fit uses is
+ *  d_mask AND "calibrated value is finite" (sakura_SetFalseIfNanOrInfFloat, sakura.h:636, merged in).
+ *  residual / best_fit refer to the calibrated spectrum. Results are identical to calling the
+ *  calibration, the NaN/Inf filter and the fit one after the other. */
+sakura_Status sakura_CalibrateAndLSQFitPolynomialFloatBatchDevice(
+		struct sakura_LSQFitContextFloat const *context, uint16_t order, size_t num_spectra,
+		size_t num_data, float const d_scaling_factor[], size_t scaling_stride,
+		float const_scaling_factor, float const d_data[], size_t data_stride,
+		float const d_reference[], size_t reference_stride, bool flag_nan_or_inf,
+		bool const d_mask[], size_t mask_stride, float clip_threshold_sigma,
+		uint16_t num_fitting_max, size_t num_coeff, double d_coeff[], float d_best_fit[],
+		float d_residual[], bool d_final_mask[], float d_rms[], int32_t d_status[],
+		int32_t d_lsqfit_status[], void *cuda_stream) SAKURA_B200_NOEXCEPT;
+
 /* ---- NEW: library introspection (measurement support) --------------------- */
 
 /** Number of CUDA kernels this library has launched in this process so far. */

@@ -311,4 +311,29 @@ int ref_statistics_batch(int accurate, size_t num_spectra, size_t num_data, floa
 	return 0;
 }
 
+/**
+ * sakura_CalibrateDataWith{Array,Const}ScalingFloat (normalization.cc:206-282) row by row. A row
+ * stride of 0 shares one reference / scaling array; scaling == NULL selects const_scaling.
+ * Rows must be aligned (sakura_GetAlignment()); the reference rejects unaligned arrays.
+ */
+int ref_calibrate_batch(size_t num_spectra, size_t num_data, float const *scaling,
+		size_t scaling_stride, float const_scaling, float const *data, size_t data_stride,
+		float const *reference, size_t reference_stride, float *result, size_t result_stride,
+		int32_t *status) {
+	for (size_t r = 0; r < num_spectra; ++r) {
+		sakura_Status st;
+		if (scaling != nullptr) {
+			st = sakura_CalibrateDataWithArrayScalingFloat(num_data, scaling + r * scaling_stride,
+					data + r * data_stride, reference + r * reference_stride,
+					result + r * result_stride);
+		} else {
+			st = sakura_CalibrateDataWithConstScalingFloat(const_scaling, num_data,
+					data + r * data_stride, reference + r * reference_stride,
+					result + r * result_stride);
+		}
+		status[r] = static_cast<int32_t>(st);
+	}
+	return 0;
+}
+
 } // extern "C"

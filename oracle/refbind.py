@@ -78,6 +78,8 @@ class Oracle:
         L.ref_lsqfit_sinusoid_batch.argtypes = [u16, sz, vp, sz, sz, vp, sz, vp, sz, f32, u16, sz, vp,
                                                 vp, vp, vp, vp, vp, vp, i32]
         L.ref_statistics_batch.argtypes = [i32, sz, sz, vp, sz, vp, sz, vp, vp, i32]
+        L.ref_calibrate_batch.argtypes = [sz, sz, vp, sz, f32, vp, sz, vp, sz, vp, sz, vp]
+        L.ref_calibrate_batch.restype = i32
         for name in ("ref_lsqfit_polynomial_batch", "ref_lsqfit_cubicspline_batch",
                      "ref_lsqfit_sinusoid_batch", "ref_statistics_batch"):
             getattr(L, name).restype = i32
@@ -167,6 +169,27 @@ class Oracle:
         if rc != 0:
             raise RuntimeError("oracle: context creation failed")
         return res
+
+    def calibrate_batch(self, scaling, data, reference, in_place: bool = False):
+        """sakura_CalibrateDataWith{Array,Const}ScalingFloat row by row. `scaling` is a float
+        (const scaling) or an array shaped like data, or one row shared by all rows; `reference`
+        likewise. Returns (result [R, n] float32, status [R] int32); with in_place the result
+        overwrites (an aligned copy of) data, as the reference allows."""
+        data = np.atleast_2d(np.asarray(data, dtype=np.float32))
+        R, n = data.shape
+        data = aligned_copy(data)
+        ref = aligned_copy(np.atleast_2d(np.asarray(reference, dtype=np.float32)))
+        ref_stride = 0 if ref.shape[0] == 1 and R > 1 else n
+        if np.isscalar(scaling):
+            sc, sc_ptr, sc_stride, const = None, None, 0, float(scaling)
+        else:
+            sc = aligned_copy(np.atleast_2d(np.asarray(scaling, dtype=np.float32)))
+            sc_ptr, sc_stride, const = _ptr(sc), (0 if sc.shape[0] == 1 and R > 1 else n), 0.0
+        result = data if in_place else aligned_empty((R, n), np.float32)
+        status = aligned_empty((R,), np.int32)
+        self.lib.ref_calibrate_batch(R, n, sc_ptr, sc_stride, const, _ptr(data), n, _ptr(ref),
+                                     ref_stride, _ptr(result), n, _ptr(status))
+        return result, status
 
     def statistics_batch(self, data, mask, accurate: bool = True, nthreads: int = 0):
         data, mask = self._rows(data, mask)

@@ -1137,6 +1137,41 @@ int ref_statistics_batch(int accurate, size_t num_spectra, size_t num_data, floa
 	return 0;
 }
 
+/* Position-switch calibration, normalization.cc:128-139 (in place, AVX: mul(factor, sub(result,
+ * reference)) then div) and :147-176 (out of place, scalar expression factor * (target -
+ * reference) / reference): float subtract, multiply, divide in that order in both. Argument
+ * rules of :224-243 / :253-271: num_data == 0 is kOK before anything else, then NULL pointers and
+ * unaligned arrays (32 bytes) are kInvalidArgument. */
+int ref_calibrate_batch(size_t num_spectra, size_t num_data, float const *scaling,
+		size_t scaling_stride, float const_scaling, float const *data, size_t data_stride,
+		float const *reference, size_t reference_stride, float *result, size_t result_stride,
+		int32_t *status) {
+	for (size_t r = 0; r < num_spectra; ++r) {
+		float const *s = scaling ? scaling + r * scaling_stride : NULL;
+		float const *t = data ? data + r * data_stride : NULL;
+		float const *ref = reference ? reference + r * reference_stride : NULL;
+		float *out = result ? result + r * result_stride : NULL;
+		if (num_data == 0) {
+			status[r] = kStatusOK;
+			continue;
+		}
+		if (t == NULL || ref == NULL || out == NULL || ((uintptr_t) t % 32) != 0
+				|| ((uintptr_t) ref % 32) != 0 || ((uintptr_t) out % 32) != 0
+				|| (s != NULL && ((uintptr_t) s % 32) != 0)) {
+			status[r] = kStatusInvalidArgument;
+			continue;
+		}
+		for (size_t i = 0; i < num_data; ++i) {
+			float const factor = s ? s[i] : const_scaling;
+			float const diff = t[i] - ref[i];
+			float const prod = factor * diff;
+			out[i] = prod / ref[i];
+		}
+		status[r] = kStatusOK;
+	}
+	return 0;
+}
+
 /* standalone building blocks for the known-answer tests (numeric_operation.cc:867-968) */
 int oracle_get_lsq_coefficients(size_t num_data, float const *data, unsigned char const *mask,
 		size_t num_model_bases, double const *basis, size_t num_lsq_bases, size_t const *use_idx,

@@ -143,6 +143,17 @@ class SakuraLib:
             L.sakura_LSQFitSinusoidFloatBatch.argtypes + [vp]
         L.sakura_ComputeStatisticsFloatBatch.argtypes = [sz, sz, vp, sz, vp, sz, vp]
         L.sakura_ComputeStatisticsFloatBatchDevice.argtypes = [sz, sz, vp, sz, vp, sz, vp, vp]
+        L.sakura_CalibrateDataWithArrayScalingFloat.argtypes = [sz, vp, vp, vp, vp]
+        L.sakura_CalibrateDataWithConstScalingFloat.argtypes = [f32, sz, vp, vp, vp]
+        L.sakura_CalibrateDataFloatBatchDevice.argtypes = [sz, sz, vp, sz, f32, vp, sz, vp, sz, vp, sz, vp]
+        L.sakura_CalibrateAndLSQFitPolynomialFloatBatchDevice.argtypes = \
+            [vp, u16, sz, sz, vp, sz, f32, vp, sz, vp, sz, C.c_bool, vp, sz, f32, u16, sz,
+             vp, vp, vp, vp, vp, i32p, i32p, vp]
+        for name in ("sakura_CalibrateDataWithArrayScalingFloat",
+                     "sakura_CalibrateDataWithConstScalingFloat",
+                     "sakura_CalibrateDataFloatBatchDevice",
+                     "sakura_CalibrateAndLSQFitPolynomialFloatBatchDevice"):
+            getattr(L, name).restype = C.c_int
         for name in ("sakura_LSQFitPolynomialFloatBatch", "sakura_LSQFitPolynomialFloatBatchDevice",
                      "sakura_LSQFitCubicSplineFloatBatch", "sakura_LSQFitCubicSplineFloatBatchDevice",
                      "sakura_LSQFitSinusoidFloatBatch", "sakura_LSQFitSinusoidFloatBatchDevice",
@@ -284,6 +295,23 @@ class SakuraLib:
             _ptr(res["residual"]), _ptr(res["final_mask"]), _ptr(res["rms"]), _ptr(res["status"]),
             _ptr(res["lsqfit_status"]))
         return res
+
+    # ------------------------------------------------------------------ calibration
+    def calibrate(self, scaling, data, reference, in_place: bool = False):
+        """One array through sakura_CalibrateDataWith{Array,Const}ScalingFloat (host pointers);
+        `scaling` is a float or an array like data. Returns (status, result)."""
+        data = aligned_copy(np.asarray(data, dtype=np.float32).ravel())
+        ref = aligned_copy(np.asarray(reference, dtype=np.float32).ravel())
+        n = data.size
+        result = data if in_place else aligned_empty(max(n, 1), np.float32)[:n]
+        if np.isscalar(scaling):
+            st = self.lib.sakura_CalibrateDataWithConstScalingFloat(float(scaling), n, _ptr(data),
+                                                                    _ptr(ref), _ptr(result))
+        else:
+            sc = aligned_copy(np.asarray(scaling, dtype=np.float32).ravel())
+            st = self.lib.sakura_CalibrateDataWithArrayScalingFloat(n, _ptr(sc), _ptr(data),
+                                                                    _ptr(ref), _ptr(result))
+        return st, result
 
     # ------------------------------------------------------------------ statistics
     def compute_statistics_batch(self, data, mask) -> np.ndarray:

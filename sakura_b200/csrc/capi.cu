@@ -13,6 +13,7 @@
 #include "lsqfit_poly.cuh"
 #include "lsqfit_sinusoid.cuh"
 #include "lsqfit_spline.cuh"
+#include "calibration.cuh"
 #include "statistics.cuh"
 
 #include <cuda_runtime.h>
@@ -196,6 +197,7 @@ struct sakura_LSQFitContextFloat {
 	int ext_cols;
 	DeviceBuffer d_ext, d_table, d_useidx, d_fallback, ws_mask, ws_sin_residual,
 			ws_sin_best_fit;
+	DeviceBuffer ws_cal, ws_calmask; // calibrated copy of a batch for the paths that cannot fuse it
 	// staging for the host-pointer entry points
 	DeviceBuffer s_data, s_mask, s_coeff, s_best_fit, s_residual, s_final_mask, s_rms,
 			s_status, s_lsq, s_flags, s_boundary;
@@ -247,6 +249,8 @@ void ReleaseDeviceState(Context *c) {
 		c->ws_mask.Release();
 		c->ws_sin_residual.Release();
 		c->ws_sin_best_fit.Release();
+		c->ws_cal.Release();
+		c->ws_calmask.Release();
 		c->s_data.Release();
 		c->s_mask.Release();
 		c->s_coeff.Release();
@@ -388,9 +392,10 @@ struct FitCall {
 	int32_t *lsq;
 	int32_t *flags;
 	unsigned long long *boundary;
+	CalibrationSpec cal; // optional calibration fused in front of the fit (reference == NULL: none)
 };
 
-sakura_Status LaunchFit(Context *c, FitCall const &f, cudaStream_t stream) {
+sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 	DeviceInfo info;
 	sakura_Status st = CurrentDevice(&info);
 	if (st != sakura_Status_kOK) {
@@ -400,8 +405,49 @@ sakura_Status LaunchFit(Context *c, FitCall const &f, cudaStream_t stream) {
 	if (st != sakura_Status_kOK) {
 		return st;
 	}
-	if (f.num_spectra == 0) {
+	if (f_in.num_spectra == 0) {
 		return sakura_Status_kOK;
+	}
+	FitCall f = f_in;
+	if (f.cal.reference != nullptr) {
+		// The polynomial kernel calibrates while it loads a row. Every other path gets the
+		// calibrated spectra (and the NaN/Inf-merged mask) from a pre-pass into context scratch.
+		bool const fused = f.type == kFitPolynomial
+				&& PolyFastSupported(f.num_data, f.K, f.data_stride, f.mask_stride, f.data, f.mask,
+						f.best_fit, f.residual, f.final_mask)
+				&& (reinterpret_cast<uintptr_t>(f.cal.reference) % 16) == 0
+				&& f.cal.reference_stride % 4 == 0
+				&& (reinterpret_cast<uintptr_t>(f.cal.scaling) % 16) == 0
+				&& f.cal.scaling_stride % 4 == 0;
+		if (!fused) {
+			CalibrateParams cp;
+			memset(&cp, 0, sizeof(cp));
+			cp.num_spectra = f.num_spectra;
+			cp.num_data = f.num_data;
+			cp.data = f.data;
+			cp.data_stride = f.data_stride;
+			cp.spec = f.cal;
+			CUDA_TRY(c->ws_cal.Reserve(f.num_spectra * f.data_stride * sizeof(float)));
+			cp.result = c->ws_cal.As<float>();
+			cp.result_stride = f.data_stride;
+			if (f.cal.flag_nonfinite) {
+				CUDA_TRY(c->ws_calmask.Reserve(f.num_spectra * f.mask_stride));
+				cp.mask = f.mask;
+				cp.mask_stride = f.mask_stride;
+				cp.mask_out = c->ws_calmask.As<uint8_t>();
+			}
+			cudaError_t const e = LaunchCalibrate(cp, info.num_sms, stream);
+			g_launch_count += 1;
+			if (e != cudaSuccess) {
+				SetError("LaunchCalibrate", e);
+				return sakura_Status_kUnknownError;
+			}
+			f.data = cp.result;
+			if (cp.mask_out != nullptr) {
+				f.mask = cp.mask_out;
+			}
+			memset(&f.cal, 0, sizeof(f.cal));
+		}
 	}
 	// ---- polynomial hot path: register-resident kernel
 	if (f.type == kFitPolynomial && PolyFastSupported(f.num_data, f.K, f.data_stride, f.mask_stride,
@@ -425,6 +471,7 @@ sakura_Status LaunchFit(Context *c, FitCall const &f, cudaStream_t stream) {
 		p.status = f.status;
 		p.lsqfit_status = f.lsq;
 		p.flags = f.flags;
+		p.cal = f.cal;
 		int launches = 0;
 		cudaError_t e = LaunchPolyFit(p, info.num_sms, stream, &launches);
 		g_launch_count += launches;
@@ -1245,12 +1292,13 @@ sakura_Status sakura_LSQFitPolynomialFloatBatch(struct sakura_LSQFitContextFloat
 	return RunHostBatch(c, f, h);
 }
 
-sakura_Status sakura_LSQFitPolynomialFloatBatchDevice(
-		struct sakura_LSQFitContextFloat const *context, uint16_t order, size_t num_spectra,
-		size_t num_data, float const d_data[], size_t data_stride, bool const d_mask[],
-		size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max, size_t num_coeff,
-		double d_coeff[], float d_best_fit[], float d_residual[], bool d_final_mask[], float d_rms[],
-		int32_t d_status[], int32_t d_lsqfit_status[], void *cuda_stream) noexcept {
+namespace {
+sakura_Status PolynomialBatchDevice(struct sakura_LSQFitContextFloat const *context, uint16_t order,
+		size_t num_spectra, size_t num_data, float const d_data[], size_t data_stride,
+		bool const d_mask[], size_t mask_stride, float clip_threshold_sigma,
+		uint16_t num_fitting_max, size_t num_coeff, double d_coeff[], float d_best_fit[],
+		float d_residual[], bool d_final_mask[], float d_rms[], int32_t d_status[],
+		int32_t d_lsqfit_status[], void *cuda_stream, CalibrationSpec const *cal) {
 	CHECK_ARGS(d_status != nullptr && d_lsqfit_status != nullptr);
 	auto rows_ok = [&](void const *p, size_t stride_bytes) {
 		return DeviceRowsAligned(p, stride_bytes, num_spectra);
@@ -1286,7 +1334,172 @@ sakura_Status sakura_LSQFitPolynomialFloatBatchDevice(
 	f.status = d_status;
 	f.lsq = d_lsqfit_status;
 	f.flags = nullptr;
+	if (cal != nullptr) {
+		f.cal = *cal;
+	}
 	return LaunchFit(c, f, static_cast<cudaStream_t>(cuda_stream));
+}
+} // namespace
+
+sakura_Status sakura_LSQFitPolynomialFloatBatchDevice(
+		struct sakura_LSQFitContextFloat const *context, uint16_t order, size_t num_spectra,
+		size_t num_data, float const d_data[], size_t data_stride, bool const d_mask[],
+		size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max, size_t num_coeff,
+		double d_coeff[], float d_best_fit[], float d_residual[], bool d_final_mask[], float d_rms[],
+		int32_t d_status[], int32_t d_lsqfit_status[], void *cuda_stream) noexcept {
+	return PolynomialBatchDevice(context, order, num_spectra, num_data, d_data, data_stride, d_mask,
+			mask_stride, clip_threshold_sigma, num_fitting_max, num_coeff, d_coeff, d_best_fit,
+			d_residual, d_final_mask, d_rms, d_status, d_lsqfit_status, cuda_stream, nullptr);
+}
+
+// ---------------------------------------------------------------- calibration
+namespace {
+// shared argument rules of the calibration entry points: a row stride of 0 shares one array
+sakura_Status CheckCalibration(size_t num_spectra, size_t num_data, float const *scaling,
+		size_t scaling_stride, float const *data, size_t data_stride, float const *reference,
+		size_t reference_stride) {
+	CHECK_ARGS(data != nullptr && reference != nullptr);
+	CHECK_ARGS(data_stride >= num_data || num_spectra <= 1);
+	CHECK_ARGS(reference_stride == 0 || reference_stride >= num_data || num_spectra <= 1);
+	CHECK_ARGS(scaling == nullptr || scaling_stride == 0 || scaling_stride >= num_data
+			|| num_spectra <= 1);
+	return sakura_Status_kOK;
+}
+
+sakura_Status CalibrateHost(float const *scaling, float const_scaling, size_t num_data,
+		float const *data, float const *reference, float *result) {
+	if (num_data == 0) { // normalization.cc:229-232: nothing to do, before any other check
+		return sakura_Status_kOK;
+	}
+	CHECK_ARGS(data != nullptr && reference != nullptr && result != nullptr); // :234-238
+	CHECK_ARGS(sakura_IsAligned(data) && sakura_IsAligned(reference) && sakura_IsAligned(result));
+	DeviceInfo info;
+	sakura_Status st = CurrentDevice(&info);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	size_t const bytes = num_data * sizeof(float);
+	static thread_local DeviceBuffer d_t, d_r, d_s, d_o;
+	CUDA_TRY(d_t.Reserve(bytes));
+	CUDA_TRY(d_r.Reserve(bytes));
+	CUDA_TRY(d_o.Reserve(bytes));
+	cudaStream_t const stream = 0;
+	CUDA_TRY(cudaMemcpyAsync(d_t.ptr, data, bytes, cudaMemcpyHostToDevice, stream));
+	CUDA_TRY(cudaMemcpyAsync(d_r.ptr, reference, bytes, cudaMemcpyHostToDevice, stream));
+	CalibrateParams p;
+	memset(&p, 0, sizeof(p));
+	if (scaling != nullptr) {
+		CUDA_TRY(d_s.Reserve(bytes));
+		CUDA_TRY(cudaMemcpyAsync(d_s.ptr, scaling, bytes, cudaMemcpyHostToDevice, stream));
+		p.spec.scaling = d_s.As<float>();
+	}
+	p.num_spectra = 1;
+	p.num_data = num_data;
+	p.data = d_t.As<float>();
+	p.data_stride = num_data;
+	p.spec.reference = d_r.As<float>();
+	p.spec.reference_stride = num_data;
+	p.spec.scaling_stride = num_data;
+	p.spec.const_scaling = const_scaling;
+	p.result = d_o.As<float>();
+	p.result_stride = num_data;
+	cudaError_t const e = LaunchCalibrate(p, info.num_sms, stream);
+	g_launch_count += 1;
+	g_last_kernel = "calibrate";
+	if (e != cudaSuccess) {
+		SetError("LaunchCalibrate", e);
+		return sakura_Status_kUnknownError;
+	}
+	// result may alias data or reference (in-place is allowed, sakura.h:1112-1114): both were
+	// copied to the device before anything is written back
+	CUDA_TRY(cudaMemcpyAsync(result, d_o.ptr, bytes, cudaMemcpyDeviceToHost, stream));
+	CUDA_TRY(cudaStreamSynchronize(stream));
+	return sakura_Status_kOK;
+}
+} // namespace
+
+sakura_Status sakura_CalibrateDataWithArrayScalingFloat(size_t num_data,
+		float const scaling_factor[], float const data[], float const reference[],
+		float result[]) noexcept {
+	if (num_data == 0) {
+		return sakura_Status_kOK;
+	}
+	CHECK_ARGS(scaling_factor != nullptr && sakura_IsAligned(scaling_factor)); // :186-198
+	return CalibrateHost(scaling_factor, 0.0f, num_data, data, reference, result);
+}
+
+sakura_Status sakura_CalibrateDataWithConstScalingFloat(float scaling_factor, size_t num_data,
+		float const data[], float const reference[], float result[]) noexcept {
+	return CalibrateHost(nullptr, scaling_factor, num_data, data, reference, result);
+}
+
+sakura_Status sakura_CalibrateDataFloatBatchDevice(size_t num_spectra, size_t num_data,
+		float const d_scaling_factor[], size_t scaling_stride, float const_scaling_factor,
+		float const d_data[], size_t data_stride, float const d_reference[],
+		size_t reference_stride, float d_result[], size_t result_stride,
+		void *cuda_stream) noexcept {
+	if (num_spectra == 0 || num_data == 0) {
+		return sakura_Status_kOK;
+	}
+	CHECK_ARGS(d_result != nullptr && (result_stride >= num_data || num_spectra <= 1));
+	sakura_Status st = CheckCalibration(num_spectra, num_data, d_scaling_factor, scaling_stride,
+			d_data, data_stride, d_reference, reference_stride);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	DeviceInfo info;
+	st = CurrentDevice(&info);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	CalibrateParams p;
+	memset(&p, 0, sizeof(p));
+	p.num_spectra = num_spectra;
+	p.num_data = num_data;
+	p.data = d_data;
+	p.data_stride = data_stride;
+	p.spec.reference = d_reference;
+	p.spec.reference_stride = reference_stride;
+	p.spec.scaling = d_scaling_factor;
+	p.spec.scaling_stride = scaling_stride;
+	p.spec.const_scaling = const_scaling_factor;
+	p.result = d_result;
+	p.result_stride = result_stride;
+	cudaError_t const e = LaunchCalibrate(p, info.num_sms, static_cast<cudaStream_t>(cuda_stream));
+	g_launch_count += 1;
+	g_last_kernel = "calibrate";
+	if (e != cudaSuccess) {
+		SetError("LaunchCalibrate", e);
+		return sakura_Status_kUnknownError;
+	}
+	return sakura_Status_kOK;
+}
+
+sakura_Status sakura_CalibrateAndLSQFitPolynomialFloatBatchDevice(
+		struct sakura_LSQFitContextFloat const *context, uint16_t order, size_t num_spectra,
+		size_t num_data, float const d_scaling_factor[], size_t scaling_stride,
+		float const_scaling_factor, float const d_data[], size_t data_stride,
+		float const d_reference[], size_t reference_stride, bool flag_nan_or_inf,
+		bool const d_mask[], size_t mask_stride, float clip_threshold_sigma,
+		uint16_t num_fitting_max, size_t num_coeff, double d_coeff[], float d_best_fit[],
+		float d_residual[], bool d_final_mask[], float d_rms[], int32_t d_status[],
+		int32_t d_lsqfit_status[], void *cuda_stream) noexcept {
+	sakura_Status const st = CheckCalibration(num_spectra, num_data, d_scaling_factor,
+			scaling_stride, d_data, data_stride, d_reference, reference_stride);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	CalibrationSpec cal;
+	memset(&cal, 0, sizeof(cal));
+	cal.reference = d_reference;
+	cal.reference_stride = reference_stride;
+	cal.scaling = d_scaling_factor;
+	cal.scaling_stride = scaling_stride;
+	cal.const_scaling = const_scaling_factor;
+	cal.flag_nonfinite = flag_nan_or_inf ? 1 : 0;
+	return PolynomialBatchDevice(context, order, num_spectra, num_data, d_data, data_stride, d_mask,
+			mask_stride, clip_threshold_sigma, num_fitting_max, num_coeff, d_coeff, d_best_fit,
+			d_residual, d_final_mask, d_rms, d_status, d_lsqfit_status, cuda_stream, &cal);
 }
 
 sakura_Status sakura_LSQFitPolynomialFloat(struct sakura_LSQFitContextFloat const *context,

@@ -499,10 +499,31 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 		for (int j = 0; j < kSlotGroups; ++j) {
 			int const g = tid + NT * j;
 			if (FULL || g < ng) {
-				float4 const y = __ldg(gdata + g);
+				float4 y = __ldg(gdata + g);
 				uint32_t m = __ldg(gmask + g);
-				reinterpret_cast<float4 *>(sdata)[g] = y;
 				m = __vcmpne4(m, 0u) & 0x01010101u; // any non-zero byte is "true"
+				if (p.cal.reference != nullptr) { // block-uniform: calibration fused into the load
+					float4 const r = __ldg(reinterpret_cast<float4 const *>(p.cal.reference
+							+ row * p.cal.reference_stride) + g);
+					float4 s = make_float4(p.cal.const_scaling, p.cal.const_scaling,
+							p.cal.const_scaling, p.cal.const_scaling);
+					if (p.cal.scaling != nullptr) {
+						s = __ldg(reinterpret_cast<float4 const *>(p.cal.scaling
+								+ row * p.cal.scaling_stride) + g);
+					}
+					y.x = CalibrateOne(s.x, y.x, r.x);
+					y.y = CalibrateOne(s.y, y.y, r.y);
+					y.z = CalibrateOne(s.z, y.z, r.z);
+					y.w = CalibrateOne(s.w, y.w, r.w);
+					if (p.cal.flag_nonfinite) { // sakura_SetFalseIfNanOrInfFloat merged into the mask
+						auto finite = [](float v) {
+							return (__float_as_uint(v) & 0x7f800000u) != 0x7f800000u;
+						};
+						m &= (finite(y.x) ? 0x1u : 0u) | (finite(y.y) ? 0x100u : 0u)
+								| (finite(y.z) ? 0x10000u : 0u) | (finite(y.w) ? 0x1000000u : 0u);
+					}
+				}
+				reinterpret_cast<float4 *>(sdata)[g] = y;
 				uint32_t const nib = (m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xfu;
 				vbits |= nib << (4 * j);
 				float const ye[4] = { y.x, y.y, y.z, y.w };

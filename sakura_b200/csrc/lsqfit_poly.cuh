@@ -6,6 +6,8 @@
 #include <stdint.h>
 #include <cuda_runtime.h>
 
+#include "calibration.cuh"
+
 namespace sakura_b200 {
 
 struct PolyFitParams {
@@ -26,6 +28,9 @@ struct PolyFitParams {
 	int32_t *status;
 	int32_t *lsqfit_status;
 	int32_t *flags; // may be NULL; bit0 results published, bit1 final_mask written
+	// optional position-switch calibration (and NaN/Inf flagging) applied while the row is loaded:
+	// the fit then sees scaling * (data - reference) / reference (SURVEY 8(f) N1 fused in front)
+	CalibrationSpec cal;
 };
 
 /** True when the shape/alignment can be served by the register-resident kernel. */

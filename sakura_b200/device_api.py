@@ -155,6 +155,65 @@ class DeviceFits:
             self._flat(res["lsqfit_status"], ("<i4",), "lsqfit_status", R), self._stream(stream))
         return res
 
+    def _calibration_args(self, scaling, reference, R, n):
+        ref = DeviceArray(reference, ("<f4",), "reference")
+        if ref.shape[1] != n or ref.shape[0] not in (1, R):
+            raise ValueError("reference: expected [rows, channels] or one shared row")
+        ref_stride = 0 if (ref.shape[0] == 1 and R > 1) else ref.row_stride
+        if np.isscalar(scaling):
+            return None, 0, float(scaling), C.c_void_p(ref.ptr), ref_stride, ref, None
+        sc = DeviceArray(scaling, ("<f4",), "scaling")
+        if sc.shape[1] != n or sc.shape[0] not in (1, R):
+            raise ValueError("scaling: expected a float, [rows, channels] or one shared row")
+        sc_stride = 0 if (sc.shape[0] == 1 and R > 1) else sc.row_stride
+        return C.c_void_p(sc.ptr), sc_stride, 0.0, C.c_void_p(ref.ptr), ref_stride, ref, sc
+
+    def calibrate(self, scaling, data, reference, out=None, stream=None):
+        """result = scaling * (data - reference) / reference on device arrays
+        (sakura_CalibrateDataFloatBatchDevice); `scaling` is a float or an array, `reference` and
+        an array `scaling` may be one row shared by all rows."""
+        d = DeviceArray(data, ("<f4",), "data")
+        R, n = d.shape
+        sc, scs, const, ref, refs, _k1, _k2 = self._calibration_args(scaling, reference, R, n)
+        if out is None:
+            out = _torch().empty((R, n), dtype=_torch().float32, device=self._device_of(data))
+        o = DeviceArray(out, ("<f4",), "out")
+        if o.shape != d.shape:
+            raise ValueError("out: shape differs from data")
+        st = self.lib.lib.sakura_CalibrateDataFloatBatchDevice(
+            R, n, sc, scs, const, C.c_void_p(d.ptr), d.row_stride, ref, refs, C.c_void_p(o.ptr),
+            o.row_stride, self._stream(stream))
+        if st != STATUS_OK:
+            raise RuntimeError(f"sakura_CalibrateDataFloatBatchDevice -> {st}: {self.lib.last_error()}")
+        return out
+
+    def calibrate_and_polynomial(self, ctx, order: int, scaling, data, reference, mask,
+                                 clip_threshold_sigma: float, num_fitting_max: int,
+                                 flag_nan_or_inf: bool = False, num_coeff: Optional[int] = None,
+                                 want_coeff: bool = True, want_best_fit: bool = False,
+                                 want_residual: bool = True, out: Optional[dict] = None,
+                                 stream=None) -> dict:
+        """sakura_CalibrateAndLSQFitPolynomialFloatBatchDevice: the fit of the calibrated spectra,
+        calibrated (and NaN/Inf-flagged) inside the fit kernel's load."""
+        d = DeviceArray(data, ("<f4",), "data")
+        m = DeviceArray(mask, ("|b1", "|u1"), "mask")
+        if d.shape != m.shape:
+            raise ValueError("data and mask shapes differ")
+        R, n = d.shape
+        K = order + 1 if num_coeff is None else num_coeff
+        sc, scs, const, ref, refs, _k1, _k2 = self._calibration_args(scaling, reference, R, n)
+        res = self._outputs(out, self._device_of(data), R, n, (K,), want_coeff, want_best_fit,
+                            want_residual)
+        bf, rs, fm = self._row_outputs(res, R, n, d.row_stride, m.row_stride)
+        co = self._flat(res["coeff"], ("<f8",), "coeff", R * K) if res["coeff"] is not None else None
+        res["call_status"] = self.lib.lib.sakura_CalibrateAndLSQFitPolynomialFloatBatchDevice(
+            ctx, order, R, n, sc, scs, const, C.c_void_p(d.ptr), d.row_stride, ref, refs,
+            bool(flag_nan_or_inf), C.c_void_p(m.ptr), m.row_stride, clip_threshold_sigma,
+            num_fitting_max, K, co, bf, rs, fm, self._flat(res["rms"], ("<f4",), "rms", R),
+            self._flat(res["status"], ("<i4",), "status", R),
+            self._flat(res["lsqfit_status"], ("<i4",), "lsqfit_status", R), self._stream(stream))
+        return res
+
     def cubicspline(self, ctx, num_pieces: int, data, mask, clip_threshold_sigma: float,
                     num_fitting_max: int, want_coeff: bool = True, want_best_fit: bool = False,
                     want_residual: bool = True, out: Optional[dict] = None, stream=None) -> dict:
