@@ -412,7 +412,7 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 	if (f.cal.reference != nullptr) {
 		// The polynomial kernel calibrates while it loads a row. Every other path gets the
 		// calibrated spectra (and the NaN/Inf-merged mask) from a pre-pass into context scratch.
-		bool const fused = f.type == kFitPolynomial
+		bool const fused = f.type == kFitPolynomial && PolyFusedCalibrationSupported(f.num_data)
 				&& PolyFastSupported(f.num_data, f.K, f.data_stride, f.mask_stride, f.data, f.mask,
 						f.best_fit, f.residual, f.final_mask)
 				&& (reinterpret_cast<uintptr_t>(f.cal.reference) % 16) == 0

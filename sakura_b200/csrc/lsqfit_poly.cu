@@ -440,7 +440,9 @@ __device__ __forceinline__ bool UpdateAndSolve(Shared<K, NT> &sh, PolyConst cons
 
 // FULL: n == 4 * NT * kSlotGroups (4096 channels at 128 threads, 8192 at 256), every thread owns
 // all 32 channel slots and the per-group bounds checks disappear.
-template<int K, int NT, bool FULL>
+// CAL: position-switch calibration (and NaN/Inf flagging) applied while the row is loaded; only
+// instantiated together with FULL, other shapes calibrate in a pre-pass (capi.cu).
+template<int K, int NT, bool FULL, bool CAL>
 __global__ void __launch_bounds__(NT, (NT == 128 ? (K >= 7 ? 4 : kMinBlocks128) :
 		(K >= 7 ? 2 : kMinBlocks256)))
 PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
@@ -502,7 +504,7 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 				float4 y = __ldg(gdata + g);
 				uint32_t m = __ldg(gmask + g);
 				m = __vcmpne4(m, 0u) & 0x01010101u; // any non-zero byte is "true"
-				if (p.cal.reference != nullptr) { // block-uniform: calibration fused into the load
+				if (CAL) { // calibration fused into the load
 					float4 const r = __ldg(reinterpret_cast<float4 const *>(p.cal.reference
 							+ row * p.cal.reference_stride) + g);
 					float4 s = make_float4(p.cal.const_scaling, p.cal.const_scaling,
@@ -881,19 +883,19 @@ PolyConst const &GetPolyConst(int n) {
 	return cache.emplace(n, pc).first->second;
 }
 
-template<int K, int NT, bool FULL>
-cudaError_t LaunchKNF(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
+template<int K, int NT, bool FULL, bool CAL>
+cudaError_t LaunchKNFC(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
 	size_t const smem = PolySharedBytes<K, NT>(p.n);
 	static int per_sm_cache_n = -1;
 	static int per_sm_cache = 0;
-	cudaError_t err = cudaFuncSetAttribute(PolyFitKernel<K, NT, FULL>,
+	cudaError_t err = cudaFuncSetAttribute(PolyFitKernel<K, NT, FULL, CAL>,
 			cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
 	if (err != cudaSuccess) {
 		return err;
 	}
 	int per_sm = per_sm_cache;
 	if (per_sm_cache_n != p.n) {
-		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, PolyFitKernel<K, NT, FULL>, NT,
+		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, PolyFitKernel<K, NT, FULL, CAL>, NT,
 				smem);
 		if (err != cudaSuccess) {
 			return err;
@@ -908,7 +910,7 @@ cudaError_t LaunchKNF(PolyFitParams const &p, int num_sms, cudaStream_t stream) 
 	if (grid > p.num_spectra) {
 		grid = p.num_spectra;
 	}
-	PolyFitKernel<K, NT, FULL><<<static_cast<unsigned>(grid), NT, smem, stream>>>(p,
+	PolyFitKernel<K, NT, FULL, CAL><<<static_cast<unsigned>(grid), NT, smem, stream>>>(p,
 			GetPolyConst(p.n));
 	return cudaGetLastError();
 }
@@ -916,9 +918,15 @@ cudaError_t LaunchKNF(PolyFitParams const &p, int num_sms, cudaStream_t stream) 
 template<int K, int NT>
 cudaError_t LaunchKN(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
 	if (p.n == 4 * NT * kSlotGroups) {
-		return LaunchKNF<K, NT, true>(p, num_sms, stream);
+		if (p.cal.reference != nullptr) {
+			return LaunchKNFC<K, NT, true, true>(p, num_sms, stream);
+		}
+		return LaunchKNFC<K, NT, true, false>(p, num_sms, stream);
 	}
-	return LaunchKNF<K, NT, false>(p, num_sms, stream);
+	if (p.cal.reference != nullptr) {
+		return cudaErrorInvalidValue; // see PolyFusedCalibrationSupported
+	}
+	return LaunchKNFC<K, NT, false, false>(p, num_sms, stream);
 }
 
 template<int K>
@@ -945,6 +953,10 @@ bool PolyFastSupported(size_t n, size_t K, size_t data_stride, size_t mask_strid
 	auto a16 = [](void const *q) {return q == nullptr || (reinterpret_cast<uintptr_t>(q) % 16) == 0;};
 	auto a4 = [](void const *q) {return (reinterpret_cast<uintptr_t>(q) % 4) == 0;};
 	return a16(data) && a16(best_fit) && a16(residual) && a4(mask) && a4(final_mask);
+}
+
+bool PolyFusedCalibrationSupported(size_t n) {
+	return n == 4u * 128u * kSlotGroups || n == 4u * 256u * kSlotGroups;
 }
 
 cudaError_t LaunchPolyFit(PolyFitParams const &p, int num_sms, cudaStream_t stream, int *launches) {

@@ -37,6 +37,10 @@ struct PolyFitParams {
 bool PolyFastSupported(size_t n, size_t K, size_t data_stride, size_t mask_stride, void const *data,
 		void const *mask, void const *best_fit, void const *residual, void const *final_mask);
 
+/** True when the kernel variant that calibrates while loading exists for this channel count
+ *  (4096 and 8192: every thread owns all of its 32 channel slots). */
+bool PolyFusedCalibrationSupported(size_t n);
+
 cudaError_t LaunchPolyFit(PolyFitParams const &p, int num_sms, cudaStream_t stream, int *launches);
 
 } // namespace sakura_b200
