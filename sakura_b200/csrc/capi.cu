@@ -412,7 +412,8 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 	if (f.cal.reference != nullptr) {
 		// The polynomial kernel calibrates while it loads a row. Every other path gets the
 		// calibrated spectra (and the NaN/Inf-merged mask) from a pre-pass into context scratch.
-		bool const fused = f.type == kFitPolynomial && PolyFusedCalibrationSupported(f.num_data)
+		bool const fused = (f.type == kFitPolynomial || (f.type == kFitChebyshev && f.K <= 6))
+				&& PolyFusedCalibrationSupported(f.num_data)
 				&& PolyFastSupported(f.num_data, f.K, f.data_stride, f.mask_stride, f.data, f.mask,
 						f.best_fit, f.residual, f.final_mask)
 				&& (reinterpret_cast<uintptr_t>(f.cal.reference) % 16) == 0
@@ -450,8 +451,13 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 		}
 	}
 	// ---- polynomial hot path: register-resident kernel
-	if (f.type == kFitPolynomial && PolyFastSupported(f.num_data, f.K, f.data_stride, f.mask_stride,
-			f.data, f.mask, f.best_fit, f.residual, f.final_mask)) {
+	// Chebyshev contexts share the polynomial kernel up to order 5: the model space is the same and
+	// only the reported coefficients change basis. Beyond that the monomial normal equations the
+	// kernel solves (cond > 1e9) would lose accuracy the reference's well-conditioned Chebyshev
+	// solve keeps (measured: coefficients 6e-10 relative at order 5, 1e-7 at 6, 5e-6 at 7).
+	if ((f.type == kFitPolynomial || (f.type == kFitChebyshev && f.K <= 6))
+			&& PolyFastSupported(f.num_data, f.K, f.data_stride, f.mask_stride, f.data, f.mask,
+					f.best_fit, f.residual, f.final_mask)) {
 		PolyFitParams p;
 		memset(&p, 0, sizeof(p));
 		p.num_spectra = f.num_spectra;
@@ -472,6 +478,7 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 		p.lsqfit_status = f.lsq;
 		p.flags = f.flags;
 		p.cal = f.cal;
+		p.chebyshev = (f.type == kFitChebyshev) ? 1 : 0;
 		int launches = 0;
 		cudaError_t e = LaunchPolyFit(p, info.num_sms, stream, &launches);
 		g_launch_count += launches;
@@ -719,7 +726,8 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 	size_t const n = f.num_data;
 	size_t const R = f.num_spectra;
 	size_t const dstride = RoundUp(n, 32);
-	bool const fast = (f.type == kFitPolynomial) && PolyFastSupported(n, f.K, dstride, dstride,
+	bool const fast = (f.type == kFitPolynomial || (f.type == kFitChebyshev && f.K <= 6))
+			&& PolyFastSupported(n, f.K, dstride, dstride,
 			nullptr, nullptr, nullptr, nullptr, nullptr);
 	// chunk size of the pipeline in MiB of data (tuning knob; default from measurements on B200)
 	static size_t const chunk_mib = []() -> size_t {

@@ -44,6 +44,9 @@ struct PolyConst {
 	double hpow[kMaxMoments]; // h^k
 	double s_all[kMaxMoments]; // sum_{i=0}^{n-1} (i h)^k, correctly rounded
 	double factor[kMaxPolyK]; // (n-1)^k by repeated multiplication (baseline.cc:1313-1318)
+	// Chebyshev coefficients from power-basis ones: a_j = sum_{k>=j} cheb[j][k] c_k, where
+	// sum_k c_k x^k = sum_j a_j T_j(2x - 1), x = i/(n-1) (baseline.cc:299-323 basis)
+	double cheb[kMaxPolyK][kMaxPolyK];
 };
 
 template<int K, int NT>
@@ -819,7 +822,17 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 			}
 		}
 		if (p.coeff != nullptr && tid < K) {
-			p.coeff[row * K + tid] = sh.cx[tid] / pc.factor[tid];
+			if (p.chebyshev) {
+				// the fit was done in the (identical) polynomial space; report it in the
+				// Chebyshev basis the context was created with
+				double a = 0.0;
+				for (int k = K - 1; k >= tid; --k) {
+					a = fma(pc.cheb[tid][k], sh.cx[k], a);
+				}
+				p.coeff[row * K + tid] = a;
+			} else {
+				p.coeff[row * K + tid] = sh.cx[tid] / pc.factor[tid];
+			}
 		}
 		if (tid == 0) {
 			p.rms[row] = static_cast<float>(rms_d);
@@ -874,6 +887,42 @@ PolyConst const &GetPolyConst(int n) {
 	}
 	for (int k = 0; k < kMaxMoments; ++k) {
 		pc.s_all[k] = static_cast<double>(acc[k]);
+	}
+	{
+		// P[j][k]: coefficient of x^k in T_j(2x - 1), by T_{j+1} = 2 (2x - 1) T_j - T_{j-1};
+		// cheb = (P^T)^-1, upper triangular, each column from a back substitution
+		long double P[kMaxPolyK][kMaxPolyK];
+		for (int j = 0; j < kMaxPolyK; ++j) {
+			for (int k = 0; k < kMaxPolyK; ++k) {
+				P[j][k] = 0.0L;
+			}
+		}
+		P[0][0] = 1.0L;
+		P[1][0] = -1.0L;
+		P[1][1] = 2.0L;
+		for (int j = 1; j + 1 < kMaxPolyK; ++j) {
+			for (int k = 0; k <= j + 1; ++k) {
+				long double v = -2.0L * P[j][k] - P[j - 1][k];
+				if (k > 0) {
+					v += 4.0L * P[j][k - 1];
+				}
+				P[j + 1][k] = v;
+			}
+		}
+		for (int col = 0; col < kMaxPolyK; ++col) {
+			// solve sum_{j>=k} P[j][k] a_j = delta(k, col) for a
+			long double a[kMaxPolyK];
+			for (int k = kMaxPolyK - 1; k >= 0; --k) {
+				long double rhs = (k == col) ? 1.0L : 0.0L;
+				for (int j = k + 1; j < kMaxPolyK; ++j) {
+					rhs -= P[j][k] * a[j];
+				}
+				a[k] = rhs / P[k][k];
+			}
+			for (int j = 0; j < kMaxPolyK; ++j) {
+				pc.cheb[j][col] = static_cast<double>(a[j]);
+			}
+		}
 	}
 	double factor = 1.0;
 	for (int k = 0; k < kMaxPolyK; ++k) {

@@ -31,6 +31,7 @@ struct PolyFitParams {
 	// optional position-switch calibration (and NaN/Inf flagging) applied while the row is loaded:
 	// the fit then sees scaling * (data - reference) / reference (SURVEY 8(f) N1 fused in front)
 	CalibrationSpec cal;
+	int chebyshev; // report the coefficients in the Chebyshev basis T_j(2 i/(n-1) - 1)
 };
 
 /** True when the shape/alignment can be served by the register-resident kernel. */

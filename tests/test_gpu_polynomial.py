@@ -91,8 +91,15 @@ def test_chebyshev_and_high_order_general_kernel(lib, oracle):
     data, mask = synth.make_spectra(64, 1024, seed=5)
     g, o, kernel = run_both(lib, oracle, 5, data, mask, 3.0, 3, lsqfit_type=LSQFIT_TYPE_CHEBYSHEV,
                             want_best_fit=True)
-    assert kernel == "general"
+    # Chebyshev up to order 5 is fitted by the polynomial kernel (same model space) and only the
+    # coefficients are converted to the Chebyshev basis
+    assert kernel == "poly_fast"
     compare_fit(g, o, data, 3.0)
+    for order in (0, 1, 3, 4, 7):
+        g, o, kernel = run_both(lib, oracle, order, data, mask, 3.0, 4, lsqfit_type=LSQFIT_TYPE_CHEBYSHEV,
+                                want_best_fit=True)
+        assert kernel == ("poly_fast" if order <= 5 else "general")
+        compare_fit(g, o, data, 3.0)
     # well-conditioned high order: Chebyshev 20 (the monomial basis is numerically rank deficient
     # beyond order ~10, where the rank-truncated solution depends on the last bit of G)
     nogap, nogap_mask = synth.make_spectra(64, 1024, seed=6, max_block=0)  # no wide flagged gap
