@@ -314,6 +314,33 @@ sakura_Status CreateContext(int type, uint16_t param, size_t num_data, Context *
 		break;
 	case kFitChebyshev:
 		FillChebyshevTable(num_data, num_bases, c->h_basis);
+		if (num_data > 1 && param >= 1 && 2 * static_cast<size_t>(param) + 1 <= 96) {
+			// T_j T_k = (T_{j+k} + T_{|j-k|}) / 2: the Gram matrix of a Chebyshev fit needs only the
+			// masked sums of T_m, m <= 2*order, exactly like the cosine terms of the sinusoid kernel
+			// (T_m(cos t) = cos(m t)). Extended table: column m = T_m(x_i), same chunked layout.
+			int const cols = 2 * param + 1;
+			size_t const chunks = static_cast<size_t>(SinusoidExtLd(cols)) / 32;
+			size_t const chunk_doubles = static_cast<size_t>(num_data) * kSinExtChunkLd;
+			c->ext_cols = cols;
+			c->h_ext = new std::vector<double>(chunks * chunk_doubles, 0.0);
+			double const max_x = static_cast<double>(num_data - 1);
+			std::vector<long double> t(cols);
+			for (size_t i = 0; i < num_data; ++i) {
+				long double const x = static_cast<long double>(
+						2.0 * static_cast<double>(i) / max_x - 1.0); // the table's own x
+				t[0] = 1.0L;
+				if (cols > 1) {
+					t[1] = x;
+				}
+				for (int m = 2; m < cols; ++m) {
+					t[m] = 2.0L * x * t[m - 1] - t[m - 2];
+				}
+				for (int m = 0; m < cols; ++m) {
+					(*c->h_ext)[(m / 32) * chunk_doubles + i * kSinExtChunkLd + (m % 32)] =
+							static_cast<double>(t[m]);
+				}
+			}
+		}
 		break;
 	default:
 		FillSinusoidTable(num_data, param, c->h_basis);
@@ -493,7 +520,9 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 	// equations are not safely positive definite are handed to the general kernel below
 	int32_t const *fb_index = nullptr;
 	int32_t const *fb_count = nullptr;
-	if (f.type == kFitSinusoid && c->h_ext != nullptr && f.num_data % 32 == 0 && f.num_data >= 64
+	bool const cheb_dmma = f.type == kFitChebyshev;
+	if ((f.type == kFitSinusoid || cheb_dmma) && c->h_ext != nullptr && f.num_data % 32 == 0
+			&& f.num_data >= 64
 			&& f.K >= 1 && f.K <= static_cast<size_t>(kSinMaxKp) && f.data_stride % 4 == 0
 			&& f.mask_stride % 8 == 0 && f.num_spectra <= static_cast<size_t>(INT32_MAX)
 			&& (reinterpret_cast<uintptr_t>(f.data) % 16) == 0
@@ -510,10 +539,16 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 		sp.Kp = static_cast<int>(RoundUp(f.K, 8));
 		sp.next = c->ext_cols;
 		bool columns_ok = true;
+		sp.cos_only = cheb_dmma ? 1 : 0;
 		for (size_t k = 0; k < f.K; ++k) {
 			int const col = f.use_idx[k];
-			sp.kind[k] = static_cast<int8_t>(col == 0 ? 0 : ((col & 1) ? 1 : 2));
-			sp.wave[k] = static_cast<int16_t>((col + 1) / 2);
+			if (cheb_dmma) { // basis T_col: a "cosine" of wave number col
+				sp.kind[k] = static_cast<int8_t>(col == 0 ? 0 : 2);
+				sp.wave[k] = static_cast<int16_t>(col);
+			} else {
+				sp.kind[k] = static_cast<int8_t>(col == 0 ? 0 : ((col & 1) ? 1 : 2));
+				sp.wave[k] = static_cast<int16_t>((col + 1) / 2);
+			}
 			columns_ok = columns_ok && (col >= 0 && static_cast<size_t>(col) < c->num_bases);
 		}
 		if (columns_ok) {
@@ -680,6 +715,8 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 		g_last_kernel = "general";
 	} else if (f.type == kFitSinusoid) {
 		g_last_kernel = "sinusoid_dmma";
+	} else if (f.type == kFitChebyshev) {
+		g_last_kernel = "chebyshev_dmma";
 	}
 	if (e != cudaSuccess) {
 		SetError("LaunchGeneralFit", e);

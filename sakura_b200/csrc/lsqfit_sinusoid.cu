@@ -146,7 +146,8 @@ __device__ unsigned GramPack(SinusoidFitParams const &p, int i, int j, int zero)
 		return pos | kGramPad | (i == j ? kGramPadDiag : 0u);
 	}
 	int const ki = p.kind[i], wi = p.wave[i], kj = p.kind[j], wj = p.wave[j];
-	auto C = [](int m) {return static_cast<unsigned>(m == 0 ? 0 : 2 * m);};
+	bool const cos_only = p.cos_only != 0;
+	auto C = [cos_only](int m) {return static_cast<unsigned>(cos_only ? m : (m == 0 ? 0 : 2 * m));};
 	auto S = [zero](int m) {return static_cast<unsigned>(m == 0 ? zero : 2 * (m < 0 ? -m : m) - 1);};
 	unsigned i1, i2, neg = 0u;
 	if (ki == 0 && kj == 0) {

@@ -18,6 +18,7 @@ struct SinusoidFitParams {
 	int K; // fitted bases
 	int Kp; // K rounded up to a multiple of 8
 	int next; // columns of the extended trigonometric table: 2*mmax + 1
+	int cos_only; // extended table holds only C_m (column m): Chebyshev bases T_m = cos(m t)
 	// Selected basis columns (zero padded to Kp), built per call, in two row strides so that tiles
 	// of 16 channels are contiguous (one bulk copy) and their shared-memory images are read
 	// without bank conflicts: ld_p = Kp + 1 for the channel-contracting passes (trig sums, data

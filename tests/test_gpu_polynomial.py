@@ -98,14 +98,16 @@ def test_chebyshev_and_high_order_general_kernel(lib, oracle):
     for order in (0, 1, 3, 4, 7):
         g, o, kernel = run_both(lib, oracle, order, data, mask, 3.0, 4, lsqfit_type=LSQFIT_TYPE_CHEBYSHEV,
                                 want_best_fit=True)
-        assert kernel == ("poly_fast" if order <= 5 else "general")
+        # orders 6..47: Gram matrix from masked sums of T_m (T_j T_k = (T_{j+k} + T_{|j-k|}) / 2) in
+        # the tensor-core kernel of the sinusoid fit
+        assert kernel == ("poly_fast" if order <= 5 else "chebyshev_dmma")
         compare_fit(g, o, data, 3.0)
     # well-conditioned high order: Chebyshev 20 (the monomial basis is numerically rank deficient
     # beyond order ~10, where the rank-truncated solution depends on the last bit of G)
     nogap, nogap_mask = synth.make_spectra(64, 1024, seed=6, max_block=0)  # no wide flagged gap
     g, o, kernel = run_both(lib, oracle, 20, nogap, nogap_mask, 3.0, 3, lsqfit_type=LSQFIT_TYPE_CHEBYSHEV,
                             want_best_fit=True)
-    assert kernel == "general"
+    assert kernel == "chebyshev_dmma"
     compare_fit(g, o, nogap, 3.0, resid_atol=1e-4, coeff_rtol=1e-3)
     g, o, kernel = run_both(lib, oracle, 8, nogap, nogap_mask, 3.0, 3, want_best_fit=True)
     assert kernel == "general"
@@ -326,3 +328,12 @@ def test_results_are_deterministic(lib):
     lib.destroy_context(ctx)
     for k in ("coeff", "residual", "final_mask", "rms"):
         assert np.array_equal(a[k], b[k][::-1], equal_nan=True), k
+
+
+def test_chebyshev_high_order_large_shape(lib, oracle):
+    # order 30 at 8192 channels with the usual flagged edges / gaps: the tensor-core path
+    data, mask = synth.make_spectra(40, 8192, seed=77, ripple=True)
+    g, o, kernel = run_both(lib, oracle, 30, data, mask, 3.0, 3, lsqfit_type=LSQFIT_TYPE_CHEBYSHEV,
+                            want_best_fit=True)
+    assert kernel == "chebyshev_dmma"
+    compare_fit(g, o, data, 3.0, resid_atol=1e-4, coeff_rtol=1e-3)
