@@ -296,6 +296,11 @@ sakura_Status sakura_CalibrateAndLSQFitPolynomialFloatBatchDevice(
 uint64_t sakura_b200_GetKernelLaunchCount(void) SAKURA_B200_NOEXCEPT;
 /** Name of the kernel variant the last fit call dispatched to ("poly_fast", "general", ...). */
 char const *sakura_b200_GetLastKernelName(void) SAKURA_B200_NOEXCEPT;
+/** Rows of the last polynomial fit on this context that the screening kernel ("poly_screen") did
+ *  not decide itself and handed to the per-channel kernel; -1 if the last call did not screen.
+ *  Synchronises the device. */
+int64_t sakura_b200_GetLastHandOverCount(struct sakura_LSQFitContextFloat const *context)
+		SAKURA_B200_NOEXCEPT;
 /** Text of the last CUDA error seen by the library ("" if none). */
 char const *sakura_b200_GetLastErrorMessage(void) SAKURA_B200_NOEXCEPT;
 /** "sakura_b200 <version> (sm_100a)". */

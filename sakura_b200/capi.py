@@ -160,6 +160,8 @@ class SakuraLib:
                      "sakura_ComputeStatisticsFloatBatch", "sakura_ComputeStatisticsFloatBatchDevice"):
             getattr(L, name).restype = C.c_int
         L.sakura_b200_GetKernelLaunchCount.restype = C.c_uint64
+        L.sakura_b200_GetLastHandOverCount.argtypes = [vp]
+        L.sakura_b200_GetLastHandOverCount.restype = C.c_int64
         L.sakura_b200_GetLastKernelName.restype = C.c_char_p
         L.sakura_b200_GetLastErrorMessage.restype = C.c_char_p
         L.sakura_b200_GetVersionString.restype = C.c_char_p
@@ -196,6 +198,10 @@ class SakuraLib:
 
     def last_kernel_name(self) -> str:
         return self.lib.sakura_b200_GetLastKernelName().decode()
+
+    def last_handover_count(self, ctx) -> int:
+        """Rows the screening kernel handed to the per-channel kernel in the last fit on `ctx`."""
+        return int(self.lib.sakura_b200_GetLastHandOverCount(ctx))
 
     def last_error(self) -> str:
         return self.lib.sakura_b200_GetLastErrorMessage().decode()

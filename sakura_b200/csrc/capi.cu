@@ -141,7 +141,7 @@ struct PipelineSlot {
 	cudaStream_t down = nullptr; // bulk result download, so that it never blocks the next upload
 	cudaEvent_t flags_ready = nullptr; // kernel done and per-row flags on the host
 	cudaEvent_t down_done = nullptr; // result buffers of this slot may be overwritten
-	DeviceBuffer data, mask, coeff, best_fit, residual, final_mask, small;
+	DeviceBuffer data, mask, coeff, best_fit, residual, final_mask, small, handover;
 	std::vector<int32_t> h_flags;
 	size_t row0 = 0;
 	size_t rows = 0; // non-zero while a chunk is in flight in this slot
@@ -153,6 +153,7 @@ struct PipelineSlot {
 		residual.Release();
 		final_mask.Release();
 		small.Release();
+		handover.Release();
 		if (stream != nullptr) {
 			cudaStreamDestroy(stream);
 			stream = nullptr;
@@ -202,6 +203,7 @@ struct sakura_LSQFitContextFloat {
 	DeviceBuffer s_data, s_mask, s_coeff, s_best_fit, s_residual, s_final_mask, s_rms,
 			s_status, s_lsq, s_flags, s_boundary;
 	std::vector<int32_t> *h_flags;
+	int32_t const *last_handover; // device counter of the rows the last fit handed to a slower kernel
 	PipelineSlot *slots; // kPipelineSlots entries, created on first pipelined call
 };
 
@@ -298,6 +300,7 @@ sakura_Status CreateContext(int type, uint16_t param, size_t num_data, Context *
 	c->num_lsq_bases_max = lsq_max;
 	c->device = -1;
 	c->h_flags = nullptr;
+	c->last_handover = nullptr;
 	c->slots = nullptr;
 	c->h_ext = nullptr;
 	c->ext_cols = 0;
@@ -420,6 +423,9 @@ struct FitCall {
 	int32_t *flags;
 	unsigned long long *boundary;
 	CalibrationSpec cal; // optional calibration fused in front of the fit (reference == NULL: none)
+	// hand-over list of the screening kernel (num_spectra + 1 int32); NULL: the context's own buffer.
+	// Chunks of the host pipeline run concurrently on one context and bring their slot's buffer.
+	int32_t *handover;
 };
 
 sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
@@ -506,10 +512,17 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 		p.flags = f.flags;
 		p.cal = f.cal;
 		p.chebyshev = (f.type == kFitChebyshev) ? 1 : 0;
+		if (f.handover != nullptr) {
+			p.fallback_rows = f.handover;
+		} else if (f.num_spectra <= static_cast<size_t>(INT32_MAX)) {
+			CUDA_TRY(c->d_fallback.Reserve((f.num_spectra + 1) * sizeof(int32_t)));
+			p.fallback_rows = c->d_fallback.As<int32_t>();
+		}
 		int launches = 0;
 		cudaError_t e = LaunchPolyFit(p, info.num_sms, stream, &launches);
 		g_launch_count += launches;
-		g_last_kernel = "poly_fast";
+		g_last_kernel = launches > 1 ? "poly_screen" : "poly_fast";
+		c->last_handover = launches > 1 ? p.fallback_rows : nullptr;
 		if (e != cudaSuccess) {
 			SetError("LaunchPolyFit", e);
 			return sakura_Status_kUnknownError;
@@ -814,6 +827,7 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 		if (h.residual != nullptr) {
 			CUDA_TRY(sl.residual.Reserve(chunk_rows * dstride * sizeof(float)));
 		}
+		CUDA_TRY(sl.handover.Reserve((chunk_rows + 1) * sizeof(int32_t)));
 		sl.h_flags.resize(chunk_rows);
 		sl.rows = 0;
 	}
@@ -919,6 +933,7 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 		fc.lsq = d_lsq;
 		fc.flags = d_flags;
 		fc.boundary = nullptr;
+		fc.handover = sl.handover.As<int32_t>();
 		st = LaunchFit(c, fc, sl.stream);
 		if (st != sakura_Status_kOK) {
 			return st;
@@ -1223,6 +1238,18 @@ uint64_t sakura_b200_GetKernelLaunchCount(void) noexcept {
 
 char const *sakura_b200_GetLastKernelName(void) noexcept {
 	return g_last_kernel;
+}
+
+int64_t sakura_b200_GetLastHandOverCount(struct sakura_LSQFitContextFloat const *context) noexcept {
+	if (!ValidContext(context) || context->last_handover == nullptr) {
+		return -1;
+	}
+	int32_t v = 0;
+	if (cudaDeviceSynchronize() != cudaSuccess
+			|| cudaMemcpy(&v, context->last_handover, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess) {
+		return -1;
+	}
+	return v;
 }
 
 char const *sakura_b200_GetLastErrorMessage(void) noexcept {

@@ -27,8 +27,11 @@
 // of an FP64 computation; masks, rms and float residuals are checked against the oracle.
 #include "lsqfit_poly.cuh"
 #include "device_common.cuh"
+#include "poly_device.cuh"
 
 #include <float.h>
+#include <math.h>
+#include <stdlib.h>
 #include <map>
 #include <mutex>
 
@@ -36,18 +39,6 @@ namespace sakura_b200 {
 
 namespace {
 
-constexpr int kMaxPolyK = 8;
-constexpr int kMaxMoments = 2 * kMaxPolyK - 1;
-
-struct PolyConst {
-	double h; // 1/(n-1)
-	double hpow[kMaxMoments]; // h^k
-	double s_all[kMaxMoments]; // sum_{i=0}^{n-1} (i h)^k, correctly rounded
-	double factor[kMaxPolyK]; // (n-1)^k by repeated multiplication (baseline.cc:1313-1318)
-	// Chebyshev coefficients from power-basis ones: a_j = sum_{k>=j} cheb[j][k] c_k, where
-	// sum_k c_k x^k = sum_j a_j T_j(2x - 1), x = i/(n-1) (baseline.cc:299-323 basis)
-	double cheb[kMaxPolyK][kMaxPolyK];
-};
 
 template<int K, int NT>
 struct Shared {
@@ -65,33 +56,6 @@ struct Shared {
 
 constexpr int kSlotGroups = 8; // float4 groups per thread: 32 channel slots, one mask bit each
 
-/** value if `keep` is non-zero, else +0.0f (a select on the bit pattern: a NaN/Inf under the mask
- *  must not leak, so this cannot be a multiplication by 0/1). */
-__device__ __forceinline__ float select_or_zero(float value, uint32_t keep) {
-	return __int_as_float(keep != 0u ? __float_as_int(value) : 0);
-}
-
-/** Coefficients of p(zb + u) in powers of u from those of p(z) in powers of z
- *  (repeated synthetic division: K(K-1)/2 FMAs). */
-template<int K>
-__device__ __forceinline__ void TaylorShift(double const *c, double zb, double *d) {
-#pragma unroll
-	for (int k = 0; k < K; ++k) {
-		d[k] = c[k];
-	}
-#pragma unroll
-	for (int i = 0; i < K - 1; ++i) {
-#pragma unroll
-		for (int j = K - 2; j >= i; --j) {
-			d[j] = fma(zb, d[j + 1], d[j]);
-		}
-	}
-}
-
-__device__ __forceinline__ double u32_to_double(uint32_t v) {
-	// exact, without the (slow) conversion pipe
-	return __hiloint2double(0x43300000, static_cast<int>(v)) - 4503599627370496.0;
-}
 
 // ---- moments over the channels whose bit is set in `bits` (this thread's channel slots) ----
 // Accumulates sum x^k (k < 2K-1) and, if WITH_T, sum y x^k (k < K), x = z*h, then reduces the
@@ -166,68 +130,6 @@ __device__ __forceinline__ void WarpBitMoments(uint32_t bits, double zbase, doub
 	__syncwarp();
 }
 
-// Reciprocal of a positive, normal double: hardware estimate + two Newton steps (5 instructions
-// instead of the ~25 of an IEEE division; measured DDIV throughput on B200 is 2.6 /clk/SM).
-// Accurate to ~1 ulp, which is all the elimination below needs.
-__device__ __forceinline__ double fast_rcp(double x) {
-	double r;
-	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-	double e = fma(-x, r, 1.0);
-	r = fma(r, e, r);
-	e = fma(-x, r, 1.0);
-	r = fma(r, e, r);
-	return r;
-}
-
-// ---- solve G c = T, G[j][k] = S[j+k], entirely in registers (every lane the same work) -------
-// LDL^T / Gaussian elimination in natural order on the upper triangle. G is a Gram matrix:
-// symmetric positive definite unless the row is degenerate. Returns false when a pivot is not
-// safely positive; the caller then uses the full-pivot rank-revealing solver.
-template<int K>
-__device__ __forceinline__ bool SolveLDLT(double const *S, double const *T, double *c_out) {
-	double a[K][K];
-	double c[K];
-	double rcp[K];
-#pragma unroll
-	for (int i = 0; i < K; ++i) {
-#pragma unroll
-		for (int j = i; j < K; ++j) {
-			a[i][j] = S[i + j];
-		}
-		c[i] = T[i];
-	}
-	double maxpivot = 0.0;
-	bool ok = true;
-#pragma unroll
-	for (int k = 0; k < K; ++k) {
-		double const pivot = a[k][k];
-		maxpivot = fmax(maxpivot, fabs(pivot));
-		ok = ok && (pivot > maxpivot * (DBL_EPSILON * K));
-		rcp[k] = fast_rcp(pivot);
-#pragma unroll
-		for (int i = k + 1; i < K; ++i) {
-			double const l = a[k][i] * rcp[k];
-#pragma unroll
-			for (int j = i; j < K; ++j) {
-				a[i][j] = fma(-l, a[k][j], a[i][j]);
-			}
-			c[i] = fma(-l, c[k], c[i]);
-		}
-	}
-#pragma unroll
-	for (int j = K - 1; j >= 0; --j) {
-		c[j] *= rcp[j];
-#pragma unroll
-		for (int i = 0; i < j; ++i) {
-			c[i] = fma(-a[i][j], c[j], c[i]);
-		}
-	}
-#pragma unroll
-	for (int i = 0; i < K; ++i) {
-		c_out[i] = c[i];
-	}
-	return ok;
-}
 
 // Full-pivot LU within one warp on a K x K matrix in shared memory; same algorithm as
 // lsq_device.cuh::SolveFullPivLU (Eigen FullPivLU semantics), used for degenerate rows.
@@ -472,13 +374,17 @@ PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 	int const nslots = (tid < ng) ? 4 * ((ng - 1 - tid) / NT + 1) : 0;
 	uint32_t const slot_mask = (nslots >= 32) ? 0xffffffffu : ((1u << nslots) - 1u);
 
-	for (size_t row = blockIdx.x; row < p.num_spectra; row += gridDim.x) {
+	// row list (rows handed over by the screening kernel, lsqfit_poly_screen.cu) or all rows
+	size_t const num_rows = (p.row_count != nullptr) ? static_cast<size_t>(*p.row_count) : p.num_spectra;
+	for (size_t it = blockIdx.x; it < num_rows; it += gridDim.x) {
+		size_t const row = (p.row_index != nullptr) ? static_cast<size_t>(p.row_index[it]) : it;
 		float4 const *gdata = reinterpret_cast<float4 const *>(p.data + row * p.data_stride);
 		uint32_t const *gmask = reinterpret_cast<uint32_t const *>(p.mask + row * p.mask_stride);
 		// pull this CTA's next row into L2 while this one is being fitted (one bulk prefetch each
 		// for data and mask), so that the next prologue's loads hit L2 instead of HBM
-		if (tid == 0 && row + gridDim.x < p.num_spectra) {
-			size_t const nrow = row + gridDim.x;
+		if (tid == 0 && it + gridDim.x < num_rows) {
+			size_t const nrow = (p.row_index != nullptr) ?
+					static_cast<size_t>(p.row_index[it + gridDim.x]) : it + gridDim.x;
 			asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
 					:: "l"(p.data + nrow * p.data_stride), "r"(static_cast<unsigned>(n) * 4u) : "memory");
 			uint8_t const *nmask = p.mask + nrow * p.mask_stride;
@@ -850,6 +756,8 @@ size_t PolySharedBytes(int n) {
 	return SharedOffset<K, NT>(n) + sizeof(Shared<K, NT>) + 16;
 }
 
+} // namespace
+
 PolyConst const &GetPolyConst(int n) {
 	static std::mutex mu;
 	static std::map<int, PolyConst> cache;
@@ -924,6 +832,28 @@ PolyConst const &GetPolyConst(int n) {
 			}
 		}
 	}
+	for (int j = 0; j < kMaxPolyK; ++j) {
+		for (int k = 0; k < kMaxPolyK; ++k) {
+			// binom[j][k] = (-1)^j sum_{i<=k} (-1)^i C(k,i) (i+1)^j (Newton series of u^j at -1, -2, ...)
+			long long acc = 0;
+			long long c = 1; // C(k, i)
+			for (int i = 0; i <= k; ++i) {
+				long long pw = 1;
+				for (int e = 0; e < j; ++e) {
+					pw *= (i + 1);
+				}
+				acc += ((i & 1) ? -1 : 1) * c * pw;
+				c = c * (k - i) / (i + 1);
+			}
+			pc.binom[j][k] = (k <= j) ? static_cast<double>((j & 1) ? -acc : acc) : 0.0;
+		}
+	}
+	for (int q = 0; q < 32; ++q) {
+		pc.node[q] = static_cast<double>(0.5L + 0.5L * cosl((2 * q + 1) * 3.14159265358979323846264338327950288L / 64.0L));
+	}
+	for (int k = 0; k < kMaxPolyK; ++k) {
+		pc.ez[k] = static_cast<double>(1.000001L / cosl(k * 3.14159265358979323846264338327950288L / 64.0L));
+	}
 	double factor = 1.0;
 	for (int k = 0; k < kMaxPolyK; ++k) {
 		pc.factor[k] = factor;
@@ -931,6 +861,8 @@ PolyConst const &GetPolyConst(int n) {
 	}
 	return cache.emplace(n, pc).first->second;
 }
+
+namespace {
 
 template<int K, int NT, bool FULL, bool CAL>
 cudaError_t LaunchKNFC(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
@@ -1008,8 +940,47 @@ bool PolyFusedCalibrationSupported(size_t n) {
 	return n == 4u * 128u * kSlotGroups || n == 4u * 256u * kSlotGroups;
 }
 
-cudaError_t LaunchPolyFit(PolyFitParams const &p, int num_sms, cudaStream_t stream, int *launches) {
+namespace {
+
+cudaError_t LaunchPolyFitKernel(PolyFitParams const &p, int num_sms, cudaStream_t stream);
+
+bool ScreeningEnabled() {
+	// SAKURA_B200_POLY_SCREEN=0 runs every row through PolyFitKernel (used by the parity tests to
+	// compare the two kernels); read per call so that a test can switch within one process
+	char const *e = getenv("SAKURA_B200_POLY_SCREEN");
+	return e == nullptr || e[0] != '0';
+}
+
+} // namespace
+
+cudaError_t LaunchPolyFit(PolyFitParams const &p_in, int num_sms, cudaStream_t stream, int *launches) {
+	PolyFitParams p = p_in;
+	p.row_index = nullptr;
+	p.row_count = nullptr;
+	if (p.fallback_rows != nullptr && ScreeningEnabled() && PolyScreenSupported(p)) {
+		// screened clip iterations first; the rows that kernel gives up (undecidable channel,
+		// degenerate system) are then fitted by the per-channel kernel from its list
+		p.fallback_count = p.fallback_rows;
+		p.fallback_rows = p.fallback_rows + 1;
+		cudaError_t err = cudaMemsetAsync(p.fallback_count, 0, sizeof(int32_t), stream);
+		if (err != cudaSuccess) {
+			return err;
+		}
+		err = LaunchPolyScreenFit(p, num_sms, stream);
+		*launches += 1;
+		if (err != cudaSuccess) {
+			return err;
+		}
+		p.row_index = p.fallback_rows;
+		p.row_count = p.fallback_count;
+	}
 	*launches += 1;
+	return LaunchPolyFitKernel(p, num_sms, stream);
+}
+
+namespace {
+
+cudaError_t LaunchPolyFitKernel(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
 	switch (p.K) {
 	case 1:
 		return LaunchK<1>(p, num_sms, stream);
@@ -1031,5 +1002,7 @@ cudaError_t LaunchPolyFit(PolyFitParams const &p, int num_sms, cudaStream_t stre
 		return cudaErrorInvalidValue;
 	}
 }
+
+} // namespace
 
 } // namespace sakura_b200

@@ -32,6 +32,14 @@ struct PolyFitParams {
 	// the fit then sees scaling * (data - reference) / reference (SURVEY 8(f) N1 fused in front)
 	CalibrationSpec cal;
 	int chebyshev; // report the coefficients in the Chebyshev basis T_j(2 i/(n-1) - 1)
+	// PolyFitKernel only: fit the rows row_index[0 .. *row_count) instead of all rows (device
+	// pointers; the list is produced by the screening kernel)
+	int32_t const *row_index;
+	int32_t const *row_count;
+	// rows the screening kernel does not decide: LaunchPolyFit takes a buffer of num_spectra + 1
+	// int32 in fallback_rows (NULL: no screening) and splits it into count and list itself
+	int32_t *fallback_rows;
+	int32_t *fallback_count;
 };
 
 /** True when the shape/alignment can be served by the register-resident kernel. */
@@ -43,6 +51,10 @@ bool PolyFastSupported(size_t n, size_t K, size_t data_stride, size_t mask_strid
 bool PolyFusedCalibrationSupported(size_t n);
 
 cudaError_t LaunchPolyFit(PolyFitParams const &p, int num_sms, cudaStream_t stream, int *launches);
+
+/** Screened clip iterations (lsqfit_poly_screen.cu): n = 4096 or 8192 channels, K <= 8. */
+bool PolyScreenSupported(PolyFitParams const &p);
+cudaError_t LaunchPolyScreenFit(PolyFitParams const &p, int num_sms, cudaStream_t stream);
 
 } // namespace sakura_b200
 

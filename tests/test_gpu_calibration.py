@@ -82,7 +82,7 @@ def test_batch_device_matches_oracle(lib, dev, oracle):
     assert np.array_equal(bits(dd.cpu().numpy()), bits(ref))
 
 
-@pytest.mark.parametrize("n,order,kernel", [(4096, 5, "poly_fast"), (1008, 3, "poly_fast"), (8192, 7, "poly_fast"),
+@pytest.mark.parametrize("n,order,kernel", [(4096, 5, "poly_screen"), (1008, 3, "poly_fast"), (8192, 7, "poly_screen"),
                                             (1024, 9, "general")])
 def test_fused_calibration_equals_sequence(lib, dev, oracle, n, order, kernel):
     import torch

@@ -1,0 +1,115 @@
+"""The screening kernel (csrc/lsqfit_poly_screen.cu) against the per-channel kernel
+(csrc/lsqfit_poly.cu) and the oracle: a row the screening kernel finishes must carry exactly the
+clip decisions of the per-channel evaluation; rows it cannot decide are handed over."""
+import os
+
+import numpy as np
+import pytest
+
+from sakura_b200 import synth
+from sakura_b200.capi import STATUS_OK
+from parity import compare_fit
+
+pytestmark = pytest.mark.gpu
+
+
+def fit(lib, order, data, mask, clip, nfit, screen, **want):
+    st, ctx = lib.create_polynomial_context(order, data.shape[-1])
+    assert st == STATUS_OK
+    old = os.environ.get("SAKURA_B200_POLY_SCREEN")
+    os.environ["SAKURA_B200_POLY_SCREEN"] = "1" if screen else "0"
+    try:
+        g = lib.lsqfit_polynomial_batch(ctx, order, data, mask, clip, nfit, **want)
+        kernel = lib.last_kernel_name()
+        handed = lib.last_handover_count(ctx)
+    finally:
+        if old is None:
+            del os.environ["SAKURA_B200_POLY_SCREEN"]
+        else:
+            os.environ["SAKURA_B200_POLY_SCREEN"] = old
+    lib.destroy_context(ctx)
+    return g, kernel, handed
+
+
+def assert_same(a, b, data, loose=False):
+    assert np.array_equal(a["status"], b["status"])
+    assert np.array_equal(a["lsqfit_status"], b["lsqfit_status"])
+    assert np.array_equal(a["final_mask"], b["final_mask"]), int((a["final_mask"] != b["final_mask"]).sum())
+    good = a["status"] == 0
+    ra, rb = a["rms"][good].astype(np.float64), b["rms"][good].astype(np.float64)
+    # same clip decisions -> same fit; the last fit's model is evaluated from a different
+    # expansion point in the two kernels, so a float residual may differ by one ulp of the model
+    assert np.all(np.abs(ra - rb) <= 1e-6 * np.abs(rb) + 1e-30)
+    for key in ("residual", "best_fit"):
+        if a.get(key) is None:
+            continue
+        x, y = a[key][good].astype(np.float64), b[key][good].astype(np.float64)
+        model = np.abs(np.nan_to_num(data[good].astype(np.float64))) + np.abs(np.nan_to_num(y))
+        both_nan = np.isnan(x) & np.isnan(y)
+        # orders 6, 7: cond(G) ~ 1e9..1e10 turns the O(eps) differences of the two kernels' moment
+        # sums into 1e-6-level model differences (tests/test_gpu_polynomial.py widens likewise)
+        assert np.all((np.abs(x - y) <= (2e-4 if loose else 2.4e-7) * model + 1e-30) | both_nan), key
+    ca, cb = a["coeff"][good], b["coeff"][good]
+    scale = np.abs(cb).max(axis=1, keepdims=True) + 1e-300
+    assert np.all(np.abs(ca - cb) <= (1e-3 if loose else 1e-7) * np.abs(cb) + (1e-4 if loose else 1e-12) * scale)
+
+
+@pytest.mark.parametrize("n,order,nfit", [(4096, 5, 5), (4096, 5, 3), (4096, 5, 2), (4096, 5, 1),
+                                           (4096, 0, 4), (4096, 1, 4), (4096, 3, 6), (4096, 7, 3),
+                                           (8192, 5, 5), (8192, 2, 3)])
+def test_screen_equals_per_channel_kernel(lib, oracle, n, order, nfit):
+    rows = 768
+    data, mask = synth.make_spectra(rows, n, seed=100 + order + nfit)
+    synth.add_edge_case_rows(data, mask, order + 1)
+    s, kernel, handed = fit(lib, order, data, mask, 3.0, nfit, True, want_best_fit=True)
+    assert kernel == "poly_screen"
+    p, kernel, _ = fit(lib, order, data, mask, 3.0, nfit, False, want_best_fit=True)
+    assert kernel == "poly_fast"
+    assert_same(s, p, data, loose=order >= 6)
+    # the edge-case rows (constant data, exactly K valid channels, ...) are handed over by design;
+    # ordinary rows almost never are
+    assert 0 <= handed <= 16 + rows // 50, handed
+    if order <= 5:
+        o = oracle.lsqfit_polynomial_batch(order, data, mask, 3.0, nfit, want_best_fit=True)
+        reported = compare_fit(s, o, data, 3.0, poly_rescale_n=n)
+        assert reported == [], reported
+
+
+@pytest.mark.parametrize("scale,offset", [(1.0, 1000.0), (1e-6, 0.0), (1e6, 3e7), (1e-20, 0.0), (1.0, 1e6)])
+def test_screen_scales_and_offsets(lib, scale, offset):
+    """Large offsets widen the float-rounding band (more hand-overs, same results); tiny scales
+    push the thresholds below the underflow guard (every row handed over)."""
+    data, mask = synth.make_spectra(256, 4096, seed=77)
+    data = (data * np.float32(scale) + np.float32(offset)).astype(np.float32)
+    s, kernel, handed = fit(lib, 5, data, mask, 3.0, 5, True)
+    assert kernel == "poly_screen"
+    p, _, _ = fit(lib, 5, data, mask, 3.0, 5, False)
+    assert_same(s, p, data)
+    if scale == 1e-20:
+        assert handed == 256
+
+
+@pytest.mark.parametrize("clip", [0.5, 1.5, 2.5, 6.0])
+def test_screen_clip_levels(lib, clip):
+    """Low thresholds clip a large part of the row per pass (long clipped lists, several rounds
+    per warp); many iterations exercise the stale passes."""
+    data, mask = synth.make_spectra(128, 4096, seed=int(clip * 10))
+    s, _, handed = fit(lib, 4, data, mask, clip, 12, True)
+    p, _, _ = fit(lib, 4, data, mask, clip, 12, False)
+    assert_same(s, p, data)
+
+
+def test_screen_dense_flags_and_runs(lib):
+    """Rows with most channels flagged (direct power sums instead of the complement), long
+    flagged runs, rows that run out of channels while clipping."""
+    rng = np.random.default_rng(5)
+    data, mask = synth.make_spectra(192, 4096, seed=9)
+    mask[:64] &= rng.random((64, 4096)) < 0.3
+    for r in range(64, 128):
+        a = int(rng.integers(0, 3000))
+        mask[r, a:a + int(rng.integers(300, 1000))] = False
+    mask[128:160] &= rng.random((32, 4096)) < 0.004   # ~16 valid channels: clipping exhausts them
+    s, _, handed = fit(lib, 5, data, mask, 3.0, 6, True, want_best_fit=True)
+    p, _, _ = fit(lib, 5, data, mask, 3.0, 6, False, want_best_fit=True)
+    assert_same(s, p, data)
+    assert (s["status"] != 0).sum() == (p["status"] != 0).sum()

@@ -20,4 +20,4 @@ for it in range(3):
     assert rc == 0, rc
 torch.cuda.synchronize()
 ms = ev0.elapsed_time(ev1)
-print("ok", int((st == 0).sum()), "ms", ms, "spectra/s", R / ms * 1e3, lib.last_kernel_name())
+print("ok", int((st == 0).sum()), "ms", ms, "spectra/s", R / ms * 1e3, lib.last_kernel_name(), "handed over", lib.last_handover_count(ctx))
