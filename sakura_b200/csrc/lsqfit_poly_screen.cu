@@ -42,7 +42,7 @@ namespace sakura_b200 {
 
 namespace {
 
-constexpr int kListCap = 32; // clipped-channel entries per warp and round
+constexpr int kListCap = 8; // clipped-channel entries per warp (the light path; >= kHeavyClipped)
 constexpr double kU32 = 5.9604644775390625e-8; // 2^-24: unit roundoff of float
 constexpr double kSlack = 1.0009765625; // 1 + 2^-10
 constexpr double kTiny40 = 9.094947017729282e-13; // 2^-40
@@ -66,10 +66,10 @@ struct ScreenShared {
 	static constexpr int NS = 2 * K - 1;
 	static constexpr int NV = 3 * K; // S (2K-1 power sums), T (K data moments), Q (sum y^2)
 	double wtot[NW][NV]; // per-warp moment totals of the channels flagged / clipped in this pass
-	double st[NV]; // current S, T, Q over the valid channels (owned by warp 0)
+	double st[NV]; // current S, T, Q over the valid channels (owned by the control warp)
 	double stat[NW][2]; // final pass: sum, sum of squares per warp
 	double2 list[NW][kListCap]; // (x, y) of the channels a warp clipped in this pass
-	// ---- control block: written by warp 0, read by everybody after a barrier
+	// ---- control block: written by the control warp, read by everybody after a barrier
 	double cz[K]; // model coefficients in the channel index z
 	double cx[K]; // ... in x = z/(n-1)
 	double cxs[K]; // coefficients of the model the stored r~ refers to
@@ -85,15 +85,15 @@ struct ScreenShared {
 
 template<int K, int NT>
 __host__ __device__ constexpr size_t ScreenResidualBytes() {
-	// r~ rows padded to 36 floats; doubles as the prologue's reduction scratch (NW x NS x 33 doubles)
+	// r~ rows; doubles as the prologue's reduction scratch (NW x NS x 33 doubles)
 	size_t const need = static_cast<size_t>(NT / 32) * (2 * K - 1) * 33 * sizeof(double);
-	size_t const res = static_cast<size_t>(NT) * 36 * 4;
+	size_t const res = static_cast<size_t>(NT) * 32 * 4;
 	return ((res > need ? res : need) + 15) / 16 * 16;
 }
 
 template<int K, int NT>
 __host__ __device__ constexpr size_t ScreenSharedBytes() {
-	return static_cast<size_t>(NT) * 36 * 4 + ScreenResidualBytes<K, NT>() + static_cast<size_t>(NT) * 8
+	return static_cast<size_t>(NT) * 32 * 4 + ScreenResidualBytes<K, NT>() + static_cast<size_t>(NT) * 8
 			+ sizeof(ScreenShared<K, NT>) + 16;
 }
 
@@ -103,6 +103,27 @@ __device__ __forceinline__ double warp_max(double v) {
 		v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
 	}
 	return v;
+}
+
+/** Shared-memory position (in float4 units) of slot q (4 channels) of thread t's 32 consecutive
+ *  channels: rows of 8 float4, the slot XOR-swizzled with the row number so that both the coalesced
+ *  pattern of the load / store passes (consecutive groups) and the per-thread pattern (one row per
+ *  lane) touch 8 different 16-byte columns per quarter warp: conflict-free without padding. */
+__device__ __forceinline__ int slot_index(int t, int q) {
+	return 8 * t + (q ^ (t & 7));
+}
+
+/** ... of a single channel (in floats) */
+__device__ __forceinline__ int channel_index(int t, int u) {
+	return 32 * t + 4 * ((u >> 2) ^ (t & 7)) + (u & 3);
+}
+
+/** value if bit `pos` of `word` is set, else +0.0f: an AND with the sign-extended bit (a NaN/Inf under
+ *  the mask must not leak, so this cannot be a multiplication by 0/1). */
+__device__ __forceinline__ float keep_if_bit(float value, uint32_t word, int pos) {
+	int m;
+	asm("bfe.s32 %0, %1, %2, 1;" : "=r"(m) : "r"(word), "r"(pos));
+	return __int_as_float(__float_as_int(value) & m);
 }
 
 /** word |= bit if lo < r < hi (two compares and one predicated OR; false for NaN). */
@@ -167,15 +188,11 @@ __device__ __forceinline__ void WarpFlaggedPowerSums(uint32_t bits, double zbase
 	__syncwarp();
 }
 
-/** maxima of two values over the warp, the two butterflies interleaved */
-__device__ __forceinline__ void warp_max2(double &a, double &b) {
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) {
-		double const oa = __shfl_xor_sync(0xffffffffu, a, o);
-		double const ob = __shfl_xor_sync(0xffffffffu, b, o);
-		a = fmax(a, oa);
-		b = fmax(b, ob);
-	}
+/** >= the maximum over the warp of a non-negative value: rounded up to float, whose bit patterns
+ *  order like the values (a NaN orders above +Inf and survives), one REDUX instruction. */
+__device__ __forceinline__ double warp_max_upper(double a) {
+	unsigned const bits = __float_as_uint(__double2float_ru(a));
+	return static_cast<double>(__uint_as_float(__reduce_max_sync(0xffffffffu, bits)));
 }
 
 /** >= sqrt(v) for v >= 0 (float square root of the value rounded up; +Inf when out of float range) */
@@ -192,7 +209,7 @@ __device__ __forceinline__ double sqrt_fast(double v) {
 	return v * r;
 }
 
-// Warp 0: apply the per-warp moment totals, solve, derive the control block of the next pass.
+// One warp: apply the per-warp moment totals, solve, derive the control block of the next pass.
 //   first      : the totals are the prologue's (flagged-channel power sums, data moments in z)
 //   count      : number of valid channels the system is built from
 //   want_clip  : false for the last fit (no thresholds needed)
@@ -252,9 +269,8 @@ __device__ __forceinline__ void Control(ScreenShared<K, NT> &sh, PolyConst const
 		mv = fma(mv, xq, cx[k]);
 		dv = fma(dv, xq, have_stored ? cx[k] - sh.cxs[k] : 0.0);
 	}
-	mv = fabs(mv);
-	dv = fabs(dv);
-	warp_max2(mv, dv);
+	mv = warp_max_upper(fabs(mv));
+	dv = warp_max_upper(fabs(dv));
 	double const A = fma(mv, pc.ez[K - 1], kTiny44 * c1);
 	double const D = fma(dv, pc.ez[K - 1], kTiny44 * (c1 + sh.c1s));
 	int mode = kModeGiveUp;
@@ -358,17 +374,17 @@ __device__ __forceinline__ void Control(ScreenShared<K, NT> &sh, PolyConst const
 }
 
 template<int K, int NT, bool CAL>
-__global__ void __launch_bounds__(NT, (NT == 128 ? 5 : 2))
-PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
+__global__ void __launch_bounds__(NT, (NT == 128 ? 6 : 3))
+PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc, int const num_sms) {
 	constexpr int NW = NT / 32;
 	constexpr int NS = 2 * K - 1;
 	constexpr int NV = 3 * K;
 	constexpr int n = 32 * NT;
 	extern __shared__ __align__(16) unsigned char smem_raw[];
-	// layout: data rows [NT][36] | r~ rows [NT][36] (also prologue scratch) | mask nibbles | control
+	// layout: data rows [NT][32] | r~ rows [NT][32] (also prologue scratch) | mask nibbles | control
 	float *sdata = reinterpret_cast<float *>(smem_raw);
-	float *sres = reinterpret_cast<float *>(smem_raw + static_cast<size_t>(NT) * 36 * 4);
-	uint8_t *snib = smem_raw + static_cast<size_t>(NT) * 36 * 4 + ScreenResidualBytes<K, NT>();
+	float *sres = reinterpret_cast<float *>(smem_raw + static_cast<size_t>(NT) * 32 * 4);
+	uint8_t *snib = smem_raw + static_cast<size_t>(NT) * 32 * 4 + ScreenResidualBytes<K, NT>();
 	ScreenShared<K, NT> &sh = *reinterpret_cast<ScreenShared<K, NT> *>(snib + static_cast<size_t>(NT) * 8);
 
 	int const tid = threadIdx.x;
@@ -377,16 +393,21 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
 	double *scratch = reinterpret_cast<double *>(sres) + warp * (NS * 33);
 	double const zbase_il = static_cast<double>(4 * tid); // interleaved ownership (load pass)
 	float const clip = p.clip_threshold_sigma;
-	// consecutive ownership: channels 32 tid + u, u < 32, at floats 36 tid + u
-	float4 *own_data = reinterpret_cast<float4 *>(sdata) + 9 * tid;
-	float4 *own_res = reinterpret_cast<float4 *>(sres) + 9 * tid;
+	// consecutive ownership: channels 32 tid + u, u < 32; slot q (channels 4q..4q+3) at own_*[q ^ t7]
+	float4 *own_data = reinterpret_cast<float4 *>(sdata) + 8 * tid;
+	float4 *own_res = reinterpret_cast<float4 *>(sres) + 8 * tid;
+	int const t7 = tid & 7;
 	uint32_t const examine = (tid == NT - 1) ? 0x7fffffffu : 0xffffffffu; // channel n-1 is never clipped
 
 	// The per-channel loops below are deliberately NOT unrolled over the eight float4 groups of a
 	// thread and use no per-channel immediates: the unrolled form of this kernel (70 KB of SASS)
 	// ran at a 69 % instruction-cache hit rate with the GPC instruction cache at 93 % of its
 	// request peak (profiles/r01/screen_v2_ncu_summary.txt); the loop bodies fit the caches.
-	for (size_t row = blockIdx.x; row < p.num_spectra; row += gridDim.x) {
+	// The warp that runs Control (a long dependent FP64 chain) rotates from row to row and differs
+	// between the CTAs resident on one SM: warp w always issues on scheduler w % 4, and with a fixed
+	// control warp every CTA of the SM would queue its chain on the same scheduler.
+	int cwarp = (blockIdx.x / num_sms) % NW;
+	for (size_t row = blockIdx.x; row < p.num_spectra; row += gridDim.x, cwarp = (cwarp + 1) % NW) {
 		float4 const *gdata = reinterpret_cast<float4 const *>(p.data + row * p.data_stride);
 		uint32_t const *gmask = reinterpret_cast<uint32_t const *>(p.mask + row * p.mask_stride);
 		if (tid == 0 && row + gridDim.x < p.num_spectra) {
@@ -428,7 +449,7 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
 				}
 			}
 			// group g belongs to thread g/8 of the consecutive ownership, slot g%8
-			reinterpret_cast<float4 *>(sdata)[9 * (g >> 3) + (g & 7)] = y;
+			reinterpret_cast<float4 *>(sdata)[slot_index(g >> 3, g & 7)] = y;
 			uint32_t const nib = (m | (m >> 7) | (m >> 14) | (m >> 21)) & 0xfu;
 			snib[g] = static_cast<uint8_t>(nib);
 			vbits_il |= nib << (4 * j);
@@ -481,13 +502,13 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
 			}
 #pragma unroll 1
 			for (int q = 7; q >= 0; --q) {
-				float4 const y = own_data[q];
+				float4 const y = own_data[q ^ t7];
 				float const ye[4] = { y.x, y.y, y.z, y.w };
 				uint32_t const nib = vbits >> (4 * q);
 #pragma unroll
 				for (int e = 3; e >= 0; --e) {
 					// select (on the bits), not multiply: a NaN/Inf under the mask must not leak
-					double const yd = static_cast<double>(select_or_zero(ye[e], nib & (1u << e)));
+					double const yd = static_cast<double>(keep_if_bit(ye[e], nib, e));
 					s[0] += yd;
 #pragma unroll
 					for (int k = 1; k < K; ++k) {
@@ -545,7 +566,7 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
 				failed = true;
 				break;
 			}
-			if (warp == 0) { // moments of all warps are visible (barrier above / at the end of the pass)
+			if (warp == cwarp) { // moments of all warps are visible (barrier above / at the end of the pass)
 				Control<K, NT>(sh, pc, iter == 1, complement, lane, count, clip, iter < p.num_fitting_max,
 						have_stored, iter & 1);
 			}
@@ -593,9 +614,9 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
 				o_hi = __double2float_ru((static_cast<double>(hi_p) + et) * kOutside);
 				o_lo = __double2float_rd((static_cast<double>(lo_m) - et) * kOutside);
 				float ub = 0.0f; // local channel index of the group's first channel (exact in float)
-#pragma unroll 1
+#pragma unroll 2
 				for (int q = 0; q < 8; ++q) {
-					float4 const y = own_data[q];
+					float4 const y = own_data[q ^ t7];
 					float const ye[4] = { y.x, y.y, y.z, y.w };
 					float re[4];
 					uint32_t nib = 0u;
@@ -615,7 +636,7 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
 						re[e] = r;
 						or_if_inside(nib, r, c_lo, c_hi, 1u << e);
 					}
-					own_res[q] = make_float4(re[0], re[1], re[2], re[3]);
+					own_res[q ^ t7] = make_float4(re[0], re[1], re[2], re[3]);
 					inside |= nib << (4 * q);
 					ub = __fadd_rn(ub, 4.0f);
 				}
@@ -628,7 +649,7 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
 				o_lo = __double2float_rd((static_cast<double>(lo_m) - et) * kOutside);
 #pragma unroll 2
 				for (int q = 0; q < 8; ++q) {
-					float4 const r4 = own_res[q];
+					float4 const r4 = own_res[q ^ t7];
 					uint32_t nib = 0u;
 					or_if_inside(nib, r4.x, c_lo, c_hi, 1u);
 					or_if_inside(nib, r4.y, c_lo, c_hi, 2u);
@@ -648,7 +669,7 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
 				uint32_t outside = 0u;
 #pragma unroll 2
 				for (int q = 0; q < 8; ++q) {
-					float4 const r4 = own_res[q];
+					float4 const r4 = own_res[q ^ t7];
 					uint32_t nib = 0u;
 					or_if_outside(nib, r4.x, o_lo, o_hi, 1u);
 					or_if_outside(nib, r4.y, o_lo, o_hi, 2u);
@@ -662,12 +683,12 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
 			while (cand != 0u) {
 				int const s = __ffs(cand) - 1;
 				cand &= cand - 1u;
-				float const rt = sres[36 * tid + s];
+				float const rt = sres[channel_index(tid, s)];
 				if (rt > o_hi || rt < o_lo) {
 					clipped |= 1u << s;
 					continue;
 				}
-				float const y = sdata[36 * tid + s];
+				float const y = sdata[channel_index(tid, s)];
 				double const z = static_cast<double>(32 * tid + s);
 				double acc = sh.cz[K - 1];
 #pragma unroll
@@ -714,7 +735,7 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
 					w &= w - 1u;
 					int const ch = 1024 * warp + 8 * (lane + 32 * (s >> 3)) + (s & 7);
 					double const x = static_cast<double>(ch) * pc.h;
-					double const yd = static_cast<double>(sdata[36 * (ch >> 5) + (ch & 31)]);
+					double const yd = static_cast<double>(sdata[channel_index(ch >> 5, ch & 31)]);
 					double pw = 1.0;
 #pragma unroll
 					for (int k = 0; k < NS; ++k) {
@@ -765,7 +786,7 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
 							int const s = __ffs(b) - 1;
 							b &= b - 1u;
 							double const x = static_cast<double>(32 * tid + s) * pc.h;
-							sh.list[warp][r] = make_double2(x, static_cast<double>(sdata[36 * tid + s]));
+							sh.list[warp][r] = make_double2(x, static_cast<double>(sdata[channel_index(tid, s)]));
 							++r;
 						}
 					}
@@ -860,9 +881,9 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
 			}
 			bool const want_best_fit = p.best_fit != nullptr;
 			double ub = 0.0;
-#pragma unroll 1
+#pragma unroll 2
 			for (int q = 0; q < 8; ++q) {
-				float4 const y = own_data[q];
+				float4 const y = own_data[q ^ t7];
 				float const ye[4] = { y.x, y.y, y.z, y.w };
 				float re[4], me[4];
 				uint32_t const nib = vbits >> (4 * q);
@@ -877,13 +898,13 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
 					me[e] = static_cast<float>(acc);
 					float const r = __fsub_rn(ye[e], me[e]);
 					re[e] = r;
-					double const rd = static_cast<double>(select_or_zero(r, nib & (1u << e)));
+					double const rd = static_cast<double>(keep_if_bit(r, nib, e));
 					sum += rd;
 					sq = fma(rd, rd, sq);
 				}
-				own_res[q] = make_float4(re[0], re[1], re[2], re[3]);
+				own_res[q ^ t7] = make_float4(re[0], re[1], re[2], re[3]);
 				if (want_best_fit) {
-					own_data[q] = make_float4(me[0], me[1], me[2], me[3]);
+					own_data[q ^ t7] = make_float4(me[0], me[1], me[2], me[3]);
 				}
 				ub += 4.0;
 			}
@@ -900,7 +921,7 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
 #pragma unroll
 			for (int j = 0; j < 8; ++j) {
 				int const g = tid + NT * j;
-				outr[g] = reinterpret_cast<float4 const *>(sres)[9 * (g >> 3) + (g & 7)];
+				outr[g] = reinterpret_cast<float4 const *>(sres)[slot_index(g >> 3, g & 7)];
 			}
 		}
 		if (p.best_fit != nullptr) {
@@ -908,7 +929,7 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc) {
 #pragma unroll
 			for (int j = 0; j < 8; ++j) {
 				int const g = tid + NT * j;
-				outb[g] = reinterpret_cast<float4 const *>(sdata)[9 * (g >> 3) + (g & 7)];
+				outb[g] = reinterpret_cast<float4 const *>(sdata)[slot_index(g >> 3, g & 7)];
 			}
 		}
 		if (p.coeff != nullptr && tid < K) {
@@ -966,7 +987,7 @@ cudaError_t LaunchScreenKNC(PolyFitParams const &p, int num_sms, cudaStream_t st
 		grid = p.num_spectra;
 	}
 	PolyScreenFitKernel<K, NT, CAL><<<static_cast<unsigned>(grid), NT, smem, stream>>>(p,
-			GetPolyConst(p.n));
+			GetPolyConst(p.n), num_sms);
 	return cudaGetLastError();
 }
 

@@ -94,7 +94,8 @@ __device__ __forceinline__ bool SolveLDLT(double const *S, double const *T, doub
 #pragma unroll
 	for (int k = 0; k < K; ++k) {
 		double const pivot = a[k][k];
-		maxpivot = fmax(maxpivot, fabs(pivot));
+		double const apivot = fabs(pivot);
+		maxpivot = (apivot > maxpivot) ? apivot : maxpivot; // (a NaN pivot fails the test below)
 		ok = ok && (pivot > maxpivot * (DBL_EPSILON * K));
 		rcp[k] = fast_rcp(pivot);
 #pragma unroll
