@@ -5,7 +5,8 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" is ONE pass of the hot path over the whole synthetic batch resident in HBM:
-one call of sakura_LSQFitPolynomialFloatBatchDevice = one launch of the fit kernel.
+one call of sakura_LSQFitPolynomialFloatBatchDevice = one launch of the screening fit kernel plus
+one launch of the per-channel kernel over the (few) rows the former hands over.
 Workload (BASELINE.json configs[1]): 1,048,576 spectra x 4,096 channels float32 + bool mask,
 polynomial order 5, num_fitting_max = 5 clip iterations at 3 sigma; outputs coeff, residual,
 final_mask, rms, status.  The 3-iteration figure named in the metric string is reported
@@ -407,6 +408,9 @@ def run_ours(args) -> None:
     ms_step, launches = timed(args.nfit, args.steps, max(args.warmup, 3))
     clocks = sampler.stop() if rank == 0 else None
     kernel_name = lib.last_kernel_name()
+    # rows the screening kernel did not decide itself and handed to the per-channel kernel (second
+    # launch of the same step, inside the timed region)
+    handed_over = lib.last_handover_count(ctx)
     ok_rows = int((status == 0).sum().item())
     mean_clipped = float((mask & ~fmask).sum(dim=1).float().mean().item())
     # snapshot of the headline run's results for the parity check against the CPU sample
@@ -423,6 +427,21 @@ def run_ours(args) -> None:
             "hbm_frac": rows * bytes_per_spectrum(n, K) / (ms3 * 1e-3) / 1e9 / measured_peak_gbs()[0],
             "per_iteration_streaming": streaming_equivalent(n, 3, rows, ms3)}
     if not args.no_also and world == 1:
+        # the same workload with every row through the per-channel kernel (screening off), and a
+        # bit-for-bit comparison of its clip decisions with the headline run's
+        step(args.nfit)
+        torch.cuda.synchronize(device)
+        fm_screen = fmask.clone()
+        os.environ["SAKURA_B200_POLY_SCREEN"] = "0"
+        try:
+            ms_pc, _ = timed(args.nfit, max(args.steps // 3, 2), 1)
+            also["per_channel_kernel_only"] = {
+                "value": rows / (ms_pc * 1e-3), "unit": UNIT, "ms_per_step": ms_pc,
+                "kernel": lib.last_kernel_name(),
+                "final_mask_mismatches_vs_headline": int((fm_screen != fmask).sum().item())}
+        finally:
+            del os.environ["SAKURA_B200_POLY_SCREEN"]
+            del fm_screen
         try:
             also.update(side_configs(lib, torch, device))
         except Exception as exc:  # the headline line must not depend on the side configs
@@ -538,7 +557,8 @@ def run_ours(args) -> None:
                          "per_iteration_streaming": streaming_equivalent(n, args.nfit, rows, ms_step)},
             "cpu_baseline": cpu,
             "also": also,
-            "check": {"rows_ok": ok_rows, "rows": rows, "mean_clipped_channels": mean_clipped},
+            "check": {"rows_ok": ok_rows, "rows": rows, "mean_clipped_channels": mean_clipped,
+                      "rows_handed_to_per_channel_kernel": handed_over},
         }
         print(json.dumps(line))
     lib.destroy_context(ctx)

@@ -944,11 +944,17 @@ namespace {
 
 cudaError_t LaunchPolyFitKernel(PolyFitParams const &p, int num_sms, cudaStream_t stream);
 
-bool ScreeningEnabled() {
-	// SAKURA_B200_POLY_SCREEN=0 runs every row through PolyFitKernel (used by the parity tests to
-	// compare the two kernels); read per call so that a test can switch within one process
+bool ScreeningEnabled(int num_fitting_max) {
+	// Screening pays from the fourth fit on (measured on B200, 4096 channels, order 5: 7.1e7 against
+	// 7.8e7 spectra/s at one fit, 3.5e7 / 3.6e7 at three, 2.7e7 / 2.6e7 at five).
+	// SAKURA_B200_POLY_SCREEN=0 runs every row through PolyFitKernel, =1 screens whatever the number
+	// of fits (the parity tests compare the two kernels); read per call so that a test can switch
+	// within one process.
 	char const *e = getenv("SAKURA_B200_POLY_SCREEN");
-	return e == nullptr || e[0] != '0';
+	if (e != nullptr && (e[0] == '0' || e[0] == '1')) {
+		return e[0] == '1';
+	}
+	return num_fitting_max >= 4;
 }
 
 } // namespace
@@ -957,7 +963,7 @@ cudaError_t LaunchPolyFit(PolyFitParams const &p_in, int num_sms, cudaStream_t s
 	PolyFitParams p = p_in;
 	p.row_index = nullptr;
 	p.row_count = nullptr;
-	if (p.fallback_rows != nullptr && ScreeningEnabled() && PolyScreenSupported(p)) {
+	if (p.fallback_rows != nullptr && ScreeningEnabled(p.num_fitting_max) && PolyScreenSupported(p)) {
 		// screened clip iterations first; the rows that kernel gives up (undecidable channel,
 		// degenerate system) are then fitted by the per-channel kernel from its list
 		p.fallback_count = p.fallback_rows;

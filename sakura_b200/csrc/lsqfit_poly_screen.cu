@@ -37,6 +37,7 @@
 #include "poly_device.cuh"
 
 #include <float.h>
+#include <stdlib.h>
 
 namespace sakura_b200 {
 
@@ -596,18 +597,26 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc, int const num_sms
 				}
 				float const dhi = static_cast<float>(d[0]);
 				float const dlo = static_cast<float>(d[0] - static_cast<double>(dhi));
-				float df[K];
-				double V = 0.0;
+				// Over 32 channels the terms of third and higher order of the local expansion are of the
+				// order of 1e-5 of the model's variation: they are not evaluated per channel but added to
+				// this thread's band (V3), which costs a fraction of a candidate per row and pass.
+				constexpr int KS = (K < 3) ? K : 3; // local terms evaluated per channel: 1, u, u^2
+				float df[KS];
+				double V = 0.0, V3 = 0.0;
 				{
 					double upow = 1.0;
 #pragma unroll
 					for (int k = 1; k < K; ++k) {
 						upow *= 31.0;
-						df[k] = static_cast<float>(d[k]);
-						V = fma(fabs(d[k]), upow, V);
+						if (k < KS) {
+							df[k] = static_cast<float>(d[k]);
+							V = fma(fabs(d[k]), upow, V);
+						} else {
+							V3 = fma(fabs(d[k]), upow, V3);
+						}
 					}
 				}
-				vs_t = __double2float_ru(V * (16.0 * kU32 * kSlack));
+				vs_t = __double2float_ru(V * (16.0 * kU32 * kSlack) + V3 * kSlack);
 				double const et = ebase + static_cast<double>(vs_t);
 				c_hi = __double2float_rd(static_cast<double>(hi_m) - et);
 				c_lo = __double2float_ru(static_cast<double>(lo_p) + et);
@@ -623,11 +632,11 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc, int const num_sms
 #pragma unroll
 					for (int e = 0; e < 4; ++e) {
 						float delta = dlo;
-						if (K > 1) {
+						if (KS > 1) {
 							float const uf = __fadd_rn(ub, static_cast<float>(e));
-							float acc = df[K - 1];
+							float acc = df[KS - 1];
 #pragma unroll
-							for (int k = K - 2; k >= 1; --k) {
+							for (int k = KS - 2; k >= 1; --k) {
 								acc = __fmaf_rn(acc, uf, df[k]);
 							}
 							delta = __fmaf_rn(acc, uf, dlo);
@@ -983,6 +992,14 @@ cudaError_t LaunchScreenKNC(PolyFitParams const &p, int num_sms, cudaStream_t st
 		per_sm = v;
 	}
 	size_t grid = static_cast<size_t>(num_sms) * per_sm;
+	{
+		// tuning knob: resident CTAs per SM (persistent grid = #SM x this), at most the occupancy limit
+		char const *e = getenv("SAKURA_B200_SCREEN_CTAS");
+		int const v = (e != nullptr) ? atoi(e) : 0;
+		if (v >= 1 && v < per_sm) {
+			grid = static_cast<size_t>(num_sms) * v;
+		}
+	}
 	if (grid > p.num_spectra) {
 		grid = p.num_spectra;
 	}
