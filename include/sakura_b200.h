@@ -290,6 +290,79 @@ sakura_Status sakura_CalibrateAndLSQFitPolynomialFloatBatchDevice(
 		float d_residual[], bool d_final_mask[], float d_rms[], int32_t d_status[],
 		int32_t d_lsqfit_status[], void *cuda_stream) SAKURA_B200_NOEXCEPT;
 
+/* ---- boolean-filter builders: the masks the fit consumes ---------------
+ * Same names, signatures, argument checks (NULL / unaligned data, result or bound arrays =>
+ * kInvalidArgument, also with zero conditions) and element semantics as the reference's
+ * sakura.h:418-682 / bool_filter_collection.cc: host arrays in, host arrays out (staged through
+ * the GPU). The *Device variants take device arrays (any alignment; 16-byte aligned arrays take
+ * the 128-bit path), host bound arrays, run asynchronously on `cuda_stream`, and can AND the
+ * filter into an existing mask in the same pass (`d_and_with`, may be NULL or alias `d_result`):
+ * the merge every caller does next (bench/e2eReduce/src/main.cc:150-229). */
+
+/** Replaces sakura_SetTrueIfInRangesInclusiveFloat, sakura.h:418 (bool_filter_collection.cc:666). */
+sakura_Status sakura_SetTrueIfInRangesInclusiveFloat(size_t num_data, float const data[],
+		size_t num_condition, float const lower_bounds[], float const upper_bounds[],
+		bool result[]) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_SetTrueIfInRangesInclusiveInt, sakura.h:427. */
+sakura_Status sakura_SetTrueIfInRangesInclusiveInt(size_t num_data, int const data[],
+		size_t num_condition, int const lower_bounds[], int const upper_bounds[],
+		bool result[]) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_SetTrueIfInRangesExclusiveFloat, sakura.h:467. */
+sakura_Status sakura_SetTrueIfInRangesExclusiveFloat(size_t num_data, float const data[],
+		size_t num_condition, float const lower_bounds[], float const upper_bounds[],
+		bool result[]) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_SetTrueIfInRangesExclusiveInt, sakura.h:476. */
+sakura_Status sakura_SetTrueIfInRangesExclusiveInt(size_t num_data, int const data[],
+		size_t num_condition, int const lower_bounds[], int const upper_bounds[],
+		bool result[]) SAKURA_B200_NOEXCEPT;
+/** Replace sakura_SetTrueIf{GreaterThan,GreaterThanOrEquals,LessThan,LessThanOrEquals}{Float,Int},
+ *  sakura.h:504-636. */
+sakura_Status sakura_SetTrueIfGreaterThanFloat(size_t num_data, float const data[], float threshold,
+		bool result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_SetTrueIfGreaterThanInt(size_t num_data, int const data[], int threshold,
+		bool result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_SetTrueIfGreaterThanOrEqualsFloat(size_t num_data, float const data[],
+		float threshold, bool result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_SetTrueIfGreaterThanOrEqualsInt(size_t num_data, int const data[], int threshold,
+		bool result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_SetTrueIfLessThanFloat(size_t num_data, float const data[], float threshold,
+		bool result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_SetTrueIfLessThanInt(size_t num_data, int const data[], int threshold,
+		bool result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_SetTrueIfLessThanOrEqualsFloat(size_t num_data, float const data[],
+		float threshold, bool result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_SetTrueIfLessThanOrEqualsInt(size_t num_data, int const data[], int threshold,
+		bool result[]) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_SetFalseIfNanOrInfFloat, sakura.h:651. */
+sakura_Status sakura_SetFalseIfNanOrInfFloat(size_t num_data, float const data[],
+		bool result[]) SAKURA_B200_NOEXCEPT;
+/** Replace sakura_Uint8ToBool / sakura_Uint32ToBool / sakura_InvertBool, sakura.h:667-691
+ *  (InvertBool may run in place). */
+sakura_Status sakura_Uint8ToBool(size_t num_data, uint8_t const data[], bool result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_Uint32ToBool(size_t num_data, uint32_t const data[], bool result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_InvertBool(size_t num_data, bool const data[], bool result[]) SAKURA_B200_NOEXCEPT;
+
+/** NEW. Device-array variants. `inclusive` selects <= / <; bounds are host arrays. */
+sakura_Status sakura_SetTrueIfInRangesFloatDevice(bool inclusive, size_t num_data, float const d_data[],
+		size_t num_condition, float const lower_bounds[], float const upper_bounds[],
+		bool const d_and_with[], bool d_result[], void *cuda_stream) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_SetTrueIfInRangesIntDevice(bool inclusive, size_t num_data, int const d_data[],
+		size_t num_condition, int const lower_bounds[], int const upper_bounds[],
+		bool const d_and_with[], bool d_result[], void *cuda_stream) SAKURA_B200_NOEXCEPT;
+/** NEW. `comparison`: 0 x > t, 1 x >= t, 2 x < t, 3 x <= t. */
+sakura_Status sakura_SetTrueIfComparesFloatDevice(int comparison, size_t num_data, float const d_data[],
+		float threshold, bool const d_and_with[], bool d_result[], void *cuda_stream) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_SetTrueIfComparesIntDevice(int comparison, size_t num_data, int const d_data[],
+		int threshold, bool const d_and_with[], bool d_result[], void *cuda_stream) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_SetFalseIfNanOrInfFloatDevice(size_t num_data, float const d_data[],
+		bool const d_and_with[], bool d_result[], void *cuda_stream) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_Uint8ToBoolDevice(size_t num_data, uint8_t const d_data[], bool const d_and_with[],
+		bool d_result[], void *cuda_stream) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_Uint32ToBoolDevice(size_t num_data, uint32_t const d_data[],
+		bool const d_and_with[], bool d_result[], void *cuda_stream) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_InvertBoolDevice(size_t num_data, bool const d_data[], bool const d_and_with[],
+		bool d_result[], void *cuda_stream) SAKURA_B200_NOEXCEPT;
+
 /* ---- NEW: library introspection (measurement support) --------------------- */
 
 /** Number of CUDA kernels this library has launched in this process so far. */

@@ -336,4 +336,50 @@ int ref_calibrate_batch(size_t num_spectra, size_t num_data, float const *scalin
 	return 0;
 }
 
+/*
+ * Boolean-filter builders (bool_filter_collection.cc), one call of the reference's own function.
+ * op: 0 ranges inclusive, 1 ranges exclusive, 2 >, 3 >=, 4 <, 5 <=, 6 finite (SetFalseIfNanOrInf),
+ * 7 non-zero (Uint8ToBool / Uint32ToBool), 8 InvertBool. type: 0 float, 1 int, 2 uint8, 3 uint32.
+ */
+int ref_bool_filter(int op, int type, size_t num_data, void const *data, size_t num_condition,
+		void const *lower, void const *upper, uint32_t threshold_bits, bool *result) {
+	float tf;
+	int ti;
+	memcpy(&tf, &threshold_bits, 4);
+	memcpy(&ti, &threshold_bits, 4);
+	float const *df = static_cast<float const *>(data);
+	int const *di = static_cast<int const *>(data);
+	float const *lf = static_cast<float const *>(lower), *uf = static_cast<float const *>(upper);
+	int const *li = static_cast<int const *>(lower), *ui = static_cast<int const *>(upper);
+	switch (op) {
+	case 0:
+		return type == 0 ? sakura_SetTrueIfInRangesInclusiveFloat(num_data, df, num_condition, lf, uf, result)
+				: sakura_SetTrueIfInRangesInclusiveInt(num_data, di, num_condition, li, ui, result);
+	case 1:
+		return type == 0 ? sakura_SetTrueIfInRangesExclusiveFloat(num_data, df, num_condition, lf, uf, result)
+				: sakura_SetTrueIfInRangesExclusiveInt(num_data, di, num_condition, li, ui, result);
+	case 2:
+		return type == 0 ? sakura_SetTrueIfGreaterThanFloat(num_data, df, tf, result)
+				: sakura_SetTrueIfGreaterThanInt(num_data, di, ti, result);
+	case 3:
+		return type == 0 ? sakura_SetTrueIfGreaterThanOrEqualsFloat(num_data, df, tf, result)
+				: sakura_SetTrueIfGreaterThanOrEqualsInt(num_data, di, ti, result);
+	case 4:
+		return type == 0 ? sakura_SetTrueIfLessThanFloat(num_data, df, tf, result)
+				: sakura_SetTrueIfLessThanInt(num_data, di, ti, result);
+	case 5:
+		return type == 0 ? sakura_SetTrueIfLessThanOrEqualsFloat(num_data, df, tf, result)
+				: sakura_SetTrueIfLessThanOrEqualsInt(num_data, di, ti, result);
+	case 6:
+		return sakura_SetFalseIfNanOrInfFloat(num_data, df, result);
+	case 7:
+		return type == 2 ? sakura_Uint8ToBool(num_data, static_cast<uint8_t const *>(data), result)
+				: sakura_Uint32ToBool(num_data, static_cast<uint32_t const *>(data), result);
+	case 8:
+		return sakura_InvertBool(num_data, static_cast<bool const *>(data), result);
+	default:
+		return -1;
+	}
+}
+
 } // extern "C"

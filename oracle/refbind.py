@@ -80,6 +80,8 @@ class Oracle:
         L.ref_statistics_batch.argtypes = [i32, sz, sz, vp, sz, vp, sz, vp, vp, i32]
         L.ref_calibrate_batch.argtypes = [sz, sz, vp, sz, f32, vp, sz, vp, sz, vp, sz, vp]
         L.ref_calibrate_batch.restype = i32
+        L.ref_bool_filter.argtypes = [i32, i32, sz, vp, sz, vp, vp, C.c_uint32, vp]
+        L.ref_bool_filter.restype = i32
         for name in ("ref_lsqfit_polynomial_batch", "ref_lsqfit_cubicspline_batch",
                      "ref_lsqfit_sinusoid_batch", "ref_statistics_batch"):
             getattr(L, name).restype = i32
@@ -190,6 +192,32 @@ class Oracle:
         self.lib.ref_calibrate_batch(R, n, sc_ptr, sc_stride, const, _ptr(data), n, _ptr(ref),
                                      ref_stride, _ptr(result), n, _ptr(status))
         return result, status
+
+    FILTER_OPS = {"ranges_inclusive": 0, "ranges_exclusive": 1, "gt": 2, "ge": 3, "lt": 4, "le": 5,
+                  "finite": 6, "nonzero": 7, "invert": 8}
+
+    def bool_filter(self, op: str, data, lower=None, upper=None, threshold=0):
+        """One call of the reference's bool_filter_collection.cc function selected by `op` and the
+        dtype of `data` (float32, int32, uint8, uint32, bool). Returns (result bool[n], status)."""
+        data = np.asarray(data)
+        type_id = {np.dtype(np.float32): 0, np.dtype(np.int32): 1, np.dtype(np.uint8): 2,
+                   np.dtype(np.bool_): 2, np.dtype(np.uint32): 3}[data.dtype]
+        n = data.size
+        # (numpy gives empty arrays arbitrary addresses: hand over aligned dummies instead)
+        data = aligned_copy(data) if n else aligned_empty(8, data.dtype)
+        lo = hi = None
+        nc = 0
+        if lower is not None:
+            nc = np.asarray(lower).size
+            lo = aligned_copy(np.asarray(lower, dtype=data.dtype)) if nc else aligned_empty(8, data.dtype)
+            hi = aligned_copy(np.asarray(upper, dtype=data.dtype)) if nc else aligned_empty(8, data.dtype)
+        thr = np.asarray([threshold], dtype=data.dtype if type_id < 2 else np.uint32)
+        bits = int(thr.view(np.uint32)[0])
+        result = aligned_empty((max(n, 1),), np.bool_)[:n]
+        result[...] = False
+        st = self.lib.ref_bool_filter(self.FILTER_OPS[op], type_id, n, _ptr(data), nc, _ptr(lo),
+                                      _ptr(hi), bits, _ptr(result))
+        return result, int(st)
 
     def statistics_batch(self, data, mask, accurate: bool = True, nthreads: int = 0):
         data, mask = self._rows(data, mask)

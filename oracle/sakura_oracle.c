@@ -1172,6 +1172,80 @@ int ref_calibrate_batch(size_t num_spectra, size_t num_data, float const *scalin
 	return 0;
 }
 
+/* ------------------------------------------------------------------ boolean filters
+ * bool_filter_collection.cc. Ranges: the reference's 8-wide SIMD body evaluates
+ * "lower <= x && x <= upper" (:180-200, :360-380), the scalar remainder of num_data % 8 elements
+ * and the generic form for more than 16 conditions evaluate "(x - lower) * (upper - x) >= 0"
+ * (:213-220, :330-345; int products wrap). Argument rules :535-600: data, result and both bound
+ * arrays non-NULL and 32-byte aligned, also for zero conditions. */
+static int in_range_float(int inclusive, int product, float x, float lo, float hi) {
+	if (product) {
+		float const v = (x - lo) * (hi - x);
+		return inclusive ? (v >= 0.0f) : (v > 0.0f);
+	}
+	/* the AVX float comparisons are the unordered ones (_CMP_NGT_UQ / _CMP_NGE_UQ,
+	 * libsakura/packed_operation.h:1423-1436): a NaN element compares "in range" */
+	return inclusive ? (!(lo > x) && !(x > hi)) : (!(lo >= x) && !(x >= hi));
+}
+
+static int in_range_int(int inclusive, int product, int x, int lo, int hi) {
+	if (product) {
+		int const v = (int) (((unsigned) x - (unsigned) lo) * ((unsigned) hi - (unsigned) x));
+		return inclusive ? (v >= 0) : (v > 0);
+	}
+	return inclusive ? (lo <= x && x <= hi) : (lo < x && x < hi);
+}
+
+int ref_bool_filter(int op, int type, size_t num_data, void const *data, size_t num_condition,
+		void const *lower, void const *upper, uint32_t threshold_bits, unsigned char *result) {
+	if (data == NULL || result == NULL || ((uintptr_t) data % 32) != 0 || ((uintptr_t) result % 32) != 0) {
+		return kStatusInvalidArgument;
+	}
+	if (op <= 1 && (lower == NULL || upper == NULL || ((uintptr_t) lower % 32) != 0
+			|| ((uintptr_t) upper % 32) != 0)) {
+		return kStatusInvalidArgument;
+	}
+	float tf;
+	int ti;
+	memcpy(&tf, &threshold_bits, 4);
+	memcpy(&ti, &threshold_bits, 4);
+	size_t const compare_end = (num_condition <= 16) ? (num_data / 8) * 8 : 0;
+	for (size_t i = 0; i < num_data; ++i) {
+		int r = 0;
+		if (op <= 1) {
+			int const product = i >= compare_end;
+			for (size_t j = 0; j < num_condition; ++j) {
+				if (type == 0) {
+					r |= in_range_float(op == 0, product, ((float const *) data)[i],
+							((float const *) lower)[j], ((float const *) upper)[j]);
+				} else {
+					r |= in_range_int(op == 0, product, ((int const *) data)[i], ((int const *) lower)[j],
+							((int const *) upper)[j]);
+				}
+			}
+		} else if (op <= 5) {
+			if (type == 0) {
+				float const x = ((float const *) data)[i];
+				r = op == 2 ? x > tf : op == 3 ? x >= tf : op == 4 ? x < tf : x <= tf;
+			} else {
+				int const x = ((int const *) data)[i];
+				r = op == 2 ? x > ti : op == 3 ? x >= ti : op == 4 ? x < ti : x <= ti;
+			}
+		} else if (op == 6) {
+			uint32_t bits;
+			memcpy(&bits, (float const *) data + i, 4);
+			r = (bits & 0x7F800000u) != 0x7F800000u; /* :838-842 */
+		} else if (op == 7) {
+			r = type == 2 ? ((unsigned char const *) data)[i] != 0 : ((uint32_t const *) data)[i] != 0;
+		} else {
+			result[i] = (unsigned char) (((unsigned char const *) data)[i] ^ 1u); /* :424 */
+			continue;
+		}
+		result[i] = (unsigned char) r;
+	}
+	return kStatusOK;
+}
+
 /* standalone building blocks for the known-answer tests (numeric_operation.cc:867-968) */
 int oracle_get_lsq_coefficients(size_t num_data, float const *data, unsigned char const *mask,
 		size_t num_model_bases, double const *basis, size_t num_lsq_bases, size_t const *use_idx,

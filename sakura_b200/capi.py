@@ -159,6 +159,28 @@ class SakuraLib:
                      "sakura_LSQFitSinusoidFloatBatch", "sakura_LSQFitSinusoidFloatBatchDevice",
                      "sakura_ComputeStatisticsFloatBatch", "sakura_ComputeStatisticsFloatBatchDevice"):
             getattr(L, name).restype = C.c_int
+        i32c = C.c_int
+        for suffix, t in (("Float", f32), ("Int", i32c)):
+            for incl in ("Inclusive", "Exclusive"):
+                fn = getattr(L, f"sakura_SetTrueIfInRanges{incl}{suffix}")
+                fn.argtypes = [sz, vp, sz, vp, vp, vp]
+                fn.restype = C.c_int
+            for cmp_ in ("GreaterThan", "GreaterThanOrEquals", "LessThan", "LessThanOrEquals"):
+                fn = getattr(L, f"sakura_SetTrueIf{cmp_}{suffix}")
+                fn.argtypes = [sz, vp, t, vp]
+                fn.restype = C.c_int
+            getattr(L, f"sakura_SetTrueIfInRanges{suffix}Device").argtypes = [C.c_bool, sz, vp, sz, vp, vp,
+                                                                             vp, vp, vp]
+            getattr(L, f"sakura_SetTrueIfCompares{suffix}Device").argtypes = [C.c_int, sz, vp, t, vp, vp, vp]
+        for name in ("sakura_SetFalseIfNanOrInfFloat", "sakura_Uint8ToBool", "sakura_Uint32ToBool",
+                     "sakura_InvertBool"):
+            getattr(L, name).argtypes = [sz, vp, vp]
+            getattr(L, name).restype = C.c_int
+            getattr(L, name + "Device").argtypes = [sz, vp, vp, vp, vp]
+            getattr(L, name + "Device").restype = C.c_int
+        for name in ("sakura_SetTrueIfInRangesFloatDevice", "sakura_SetTrueIfInRangesIntDevice",
+                     "sakura_SetTrueIfComparesFloatDevice", "sakura_SetTrueIfComparesIntDevice"):
+            getattr(L, name).restype = C.c_int
         L.sakura_b200_GetKernelLaunchCount.restype = C.c_uint64
         L.sakura_b200_GetLastHandOverCount.argtypes = [vp]
         L.sakura_b200_GetLastHandOverCount.restype = C.c_int64
@@ -318,6 +340,46 @@ class SakuraLib:
             st = self.lib.sakura_CalibrateDataWithArrayScalingFloat(n, _ptr(sc), _ptr(data),
                                                                     _ptr(ref), _ptr(result))
         return st, result
+
+    # ------------------------------------------------------------------ boolean filters
+    _RANGE_OPS = {"ranges_inclusive": "Inclusive", "ranges_exclusive": "Exclusive"}
+    _COMPARE_OPS = {"gt": "GreaterThan", "ge": "GreaterThanOrEquals", "lt": "LessThan",
+                    "le": "LessThanOrEquals"}
+
+    def bool_filter(self, op: str, data, lower=None, upper=None, threshold=0):
+        """Host arrays through the reference-named entry point selected by `op` ("ranges_inclusive",
+        "ranges_exclusive", "gt", "ge", "lt", "le", "finite", "nonzero", "invert") and the dtype of
+        `data`. Returns (result bool[n], status)."""
+        data = np.asarray(data)
+        if not _is_aligned(data) or not data.flags.c_contiguous:
+            data = aligned_copy(data)
+        n = data.size
+        if n == 0:
+            data = aligned_empty(8, data.dtype)
+        suffix = {np.dtype(np.float32): "Float", np.dtype(np.int32): "Int"}.get(data.dtype)
+        result = aligned_empty((max(n, 1),), np.bool_)
+        result[...] = False
+        if op in self._RANGE_OPS:
+            lo = aligned_copy(np.asarray(lower, dtype=data.dtype).reshape(-1))
+            hi = aligned_copy(np.asarray(upper, dtype=data.dtype).reshape(-1))
+            nc = lo.size
+            if nc == 0:
+                lo, hi = aligned_empty(8, data.dtype), aligned_empty(8, data.dtype)
+            fn = getattr(self.lib, f"sakura_SetTrueIfInRanges{self._RANGE_OPS[op]}{suffix}")
+            st = fn(n, _ptr(data), nc, _ptr(lo), _ptr(hi), _ptr(result))
+        elif op in self._COMPARE_OPS:
+            fn = getattr(self.lib, f"sakura_SetTrueIf{self._COMPARE_OPS[op]}{suffix}")
+            st = fn(n, _ptr(data), threshold, _ptr(result))
+        elif op == "finite":
+            st = self.lib.sakura_SetFalseIfNanOrInfFloat(n, _ptr(data), _ptr(result))
+        elif op == "nonzero":
+            fn = self.lib.sakura_Uint32ToBool if data.dtype == np.uint32 else self.lib.sakura_Uint8ToBool
+            st = fn(n, _ptr(data), _ptr(result))
+        elif op == "invert":
+            st = self.lib.sakura_InvertBool(n, _ptr(data), _ptr(result))
+        else:
+            raise ValueError(op)
+        return result[:n], int(st)
 
     # ------------------------------------------------------------------ statistics
     def compute_statistics_batch(self, data, mask) -> np.ndarray:

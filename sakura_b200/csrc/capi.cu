@@ -14,6 +14,7 @@
 #include "lsqfit_sinusoid.cuh"
 #include "lsqfit_spline.cuh"
 #include "calibration.cuh"
+#include "bool_filters.cuh"
 #include "statistics.cuh"
 
 #include <cuda_runtime.h>
@@ -1422,6 +1423,211 @@ sakura_Status sakura_LSQFitPolynomialFloatBatchDevice(
 	return PolynomialBatchDevice(context, order, num_spectra, num_data, d_data, data_stride, d_mask,
 			mask_stride, clip_threshold_sigma, num_fitting_max, num_coeff, d_coeff, d_best_fit,
 			d_residual, d_final_mask, d_rms, d_status, d_lsqfit_status, cuda_stream, nullptr);
+}
+
+// ---------------------------------------------------------------- boolean filters
+namespace {
+
+sakura_Status LaunchFilter(BoolFilterParams &p, size_t num_condition, void const *lower,
+		void const *upper, DeviceBuffer *bounds_buf, cudaStream_t stream) {
+	DeviceInfo info;
+	sakura_Status const st = CurrentDevice(&info);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	p.num_condition = num_condition;
+	// elements the reference's 8-wide SIMD body covers; the scalar remainder (and the generic
+	// form for more than 16 conditions) uses the product predicate (bool_filter_collection.cc)
+	p.compare_end = (num_condition <= 16) ? (p.num_data / 8) * 8 : 0;
+	if (p.op == kFilterRangesInclusive || p.op == kFilterRangesExclusive) {
+		if (num_condition <= static_cast<size_t>(kFilterInlineBounds)) {
+			memcpy(p.lower, lower, num_condition * 4);
+			memcpy(p.upper, upper, num_condition * 4);
+		} else {
+			CUDA_TRY(bounds_buf->Reserve(2 * num_condition * 4));
+			CUDA_TRY(cudaMemcpyAsync(bounds_buf->ptr, lower, num_condition * 4, cudaMemcpyHostToDevice,
+					stream));
+			CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(bounds_buf->ptr) + num_condition * 4, upper,
+					num_condition * 4, cudaMemcpyHostToDevice, stream));
+			// the bound arrays are the caller's: they must be consumed before this call returns
+			CUDA_TRY(cudaStreamSynchronize(stream));
+			p.bounds = bounds_buf->As<uint32_t>();
+		}
+	}
+	cudaError_t const e = LaunchBoolFilter(p, info.num_sms, stream);
+	g_launch_count += 1;
+	g_last_kernel = "bool_filter";
+	if (e != cudaSuccess) {
+		SetError("LaunchBoolFilter", e);
+		return sakura_Status_kUnknownError;
+	}
+	return sakura_Status_kOK;
+}
+
+bool ValidHostArray(void const *q) { // bool_filter_collection.cc:535-543
+	return q != nullptr && sakura_IsAligned(q);
+}
+
+// host arrays: stage through the device (result may alias data: InvertBool in place)
+sakura_Status FilterHost(int op, int type, size_t elem_size, size_t num_data, void const *data,
+		size_t num_condition, void const *lower, void const *upper, uint32_t threshold, bool *result) {
+	CHECK_ARGS(ValidHostArray(data) && ValidHostArray(result)); // :545-551
+	if (op == kFilterRangesInclusive || op == kFilterRangesExclusive) {
+		CHECK_ARGS(ValidHostArray(lower) && ValidHostArray(upper)); // :555-572, also for 0 conditions
+	}
+	if (num_data == 0) {
+		return sakura_Status_kOK;
+	}
+	static thread_local DeviceBuffer d_in, d_out, d_bounds;
+	CUDA_TRY(d_in.Reserve(num_data * elem_size));
+	CUDA_TRY(d_out.Reserve(num_data));
+	cudaStream_t const stream = 0;
+	CUDA_TRY(cudaMemcpyAsync(d_in.ptr, data, num_data * elem_size, cudaMemcpyHostToDevice, stream));
+	BoolFilterParams p;
+	memset(&p, 0, sizeof(p));
+	p.op = op;
+	p.type = type;
+	p.num_data = num_data;
+	p.data = d_in.ptr;
+	p.result = d_out.As<uint8_t>();
+	p.threshold = threshold;
+	sakura_Status const st = LaunchFilter(p, num_condition, lower, upper, &d_bounds, stream);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	CUDA_TRY(cudaMemcpyAsync(result, d_out.ptr, num_data, cudaMemcpyDeviceToHost, stream));
+	CUDA_TRY(cudaStreamSynchronize(stream));
+	return sakura_Status_kOK;
+}
+
+sakura_Status FilterDevice(int op, int type, size_t num_data, void const *d_data, size_t num_condition,
+		void const *lower, void const *upper, uint32_t threshold, bool const *d_and_with, bool *d_result,
+		void *cuda_stream) {
+	CHECK_ARGS(d_data != nullptr && d_result != nullptr);
+	if (op == kFilterRangesInclusive || op == kFilterRangesExclusive) {
+		CHECK_ARGS(num_condition == 0 || (lower != nullptr && upper != nullptr));
+	}
+	if (num_data == 0) {
+		return sakura_Status_kOK;
+	}
+	static thread_local DeviceBuffer d_bounds;
+	BoolFilterParams p;
+	memset(&p, 0, sizeof(p));
+	p.op = op;
+	p.type = type;
+	p.num_data = num_data;
+	p.data = d_data;
+	p.result = reinterpret_cast<uint8_t *>(d_result);
+	p.and_with = reinterpret_cast<uint8_t const *>(d_and_with);
+	p.threshold = threshold;
+	return LaunchFilter(p, num_condition, lower, upper, &d_bounds, static_cast<cudaStream_t>(cuda_stream));
+}
+
+uint32_t RawBits(float v) {
+	uint32_t r;
+	memcpy(&r, &v, 4);
+	return r;
+}
+
+uint32_t RawBits(int v) {
+	return static_cast<uint32_t>(v);
+}
+
+} // namespace
+
+#define SAKURA_B200_RANGES(NAME, TYPE, TYPEID, OP) \
+sakura_Status NAME(size_t num_data, TYPE const data[], size_t num_condition, TYPE const lower_bounds[], \
+		TYPE const upper_bounds[], bool result[]) noexcept { \
+	return FilterHost(OP, TYPEID, sizeof(TYPE), num_data, data, num_condition, lower_bounds, upper_bounds, \
+			0u, result); \
+}
+SAKURA_B200_RANGES(sakura_SetTrueIfInRangesInclusiveFloat, float, kFilterFloat, kFilterRangesInclusive)
+SAKURA_B200_RANGES(sakura_SetTrueIfInRangesInclusiveInt, int, kFilterInt32, kFilterRangesInclusive)
+SAKURA_B200_RANGES(sakura_SetTrueIfInRangesExclusiveFloat, float, kFilterFloat, kFilterRangesExclusive)
+SAKURA_B200_RANGES(sakura_SetTrueIfInRangesExclusiveInt, int, kFilterInt32, kFilterRangesExclusive)
+#undef SAKURA_B200_RANGES
+
+#define SAKURA_B200_COMPARE(NAME, TYPE, TYPEID, OP) \
+sakura_Status NAME(size_t num_data, TYPE const data[], TYPE threshold, bool result[]) noexcept { \
+	return FilterHost(OP, TYPEID, sizeof(TYPE), num_data, data, 0, nullptr, nullptr, RawBits(threshold), \
+			result); \
+}
+SAKURA_B200_COMPARE(sakura_SetTrueIfGreaterThanFloat, float, kFilterFloat, kFilterGreaterThan)
+SAKURA_B200_COMPARE(sakura_SetTrueIfGreaterThanInt, int, kFilterInt32, kFilterGreaterThan)
+SAKURA_B200_COMPARE(sakura_SetTrueIfGreaterThanOrEqualsFloat, float, kFilterFloat, kFilterGreaterThanOrEquals)
+SAKURA_B200_COMPARE(sakura_SetTrueIfGreaterThanOrEqualsInt, int, kFilterInt32, kFilterGreaterThanOrEquals)
+SAKURA_B200_COMPARE(sakura_SetTrueIfLessThanFloat, float, kFilterFloat, kFilterLessThan)
+SAKURA_B200_COMPARE(sakura_SetTrueIfLessThanInt, int, kFilterInt32, kFilterLessThan)
+SAKURA_B200_COMPARE(sakura_SetTrueIfLessThanOrEqualsFloat, float, kFilterFloat, kFilterLessThanOrEquals)
+SAKURA_B200_COMPARE(sakura_SetTrueIfLessThanOrEqualsInt, int, kFilterInt32, kFilterLessThanOrEquals)
+#undef SAKURA_B200_COMPARE
+
+sakura_Status sakura_SetFalseIfNanOrInfFloat(size_t num_data, float const data[], bool result[]) noexcept {
+	return FilterHost(kFilterFiniteFloat, kFilterFloat, 4, num_data, data, 0, nullptr, nullptr, 0u, result);
+}
+
+sakura_Status sakura_Uint8ToBool(size_t num_data, uint8_t const data[], bool result[]) noexcept {
+	return FilterHost(kFilterNonZero, kFilterUint8, 1, num_data, data, 0, nullptr, nullptr, 0u, result);
+}
+
+sakura_Status sakura_Uint32ToBool(size_t num_data, uint32_t const data[], bool result[]) noexcept {
+	return FilterHost(kFilterNonZero, kFilterUint32, 4, num_data, data, 0, nullptr, nullptr, 0u, result);
+}
+
+sakura_Status sakura_InvertBool(size_t num_data, bool const data[], bool result[]) noexcept {
+	return FilterHost(kFilterInvertBool, kFilterUint8, 1, num_data, data, 0, nullptr, nullptr, 0u, result);
+}
+
+sakura_Status sakura_SetTrueIfInRangesFloatDevice(bool inclusive, size_t num_data, float const d_data[],
+		size_t num_condition, float const lower_bounds[], float const upper_bounds[],
+		bool const d_and_with[], bool d_result[], void *cuda_stream) noexcept {
+	return FilterDevice(inclusive ? kFilterRangesInclusive : kFilterRangesExclusive, kFilterFloat, num_data,
+			d_data, num_condition, lower_bounds, upper_bounds, 0u, d_and_with, d_result, cuda_stream);
+}
+
+sakura_Status sakura_SetTrueIfInRangesIntDevice(bool inclusive, size_t num_data, int const d_data[],
+		size_t num_condition, int const lower_bounds[], int const upper_bounds[],
+		bool const d_and_with[], bool d_result[], void *cuda_stream) noexcept {
+	return FilterDevice(inclusive ? kFilterRangesInclusive : kFilterRangesExclusive, kFilterInt32, num_data,
+			d_data, num_condition, lower_bounds, upper_bounds, 0u, d_and_with, d_result, cuda_stream);
+}
+
+sakura_Status sakura_SetTrueIfComparesFloatDevice(int comparison, size_t num_data, float const d_data[],
+		float threshold, bool const d_and_with[], bool d_result[], void *cuda_stream) noexcept {
+	CHECK_ARGS(comparison >= 0 && comparison <= 3);
+	return FilterDevice(kFilterGreaterThan + comparison, kFilterFloat, num_data, d_data, 0, nullptr, nullptr,
+			RawBits(threshold), d_and_with, d_result, cuda_stream);
+}
+
+sakura_Status sakura_SetTrueIfComparesIntDevice(int comparison, size_t num_data, int const d_data[],
+		int threshold, bool const d_and_with[], bool d_result[], void *cuda_stream) noexcept {
+	CHECK_ARGS(comparison >= 0 && comparison <= 3);
+	return FilterDevice(kFilterGreaterThan + comparison, kFilterInt32, num_data, d_data, 0, nullptr, nullptr,
+			RawBits(threshold), d_and_with, d_result, cuda_stream);
+}
+
+sakura_Status sakura_SetFalseIfNanOrInfFloatDevice(size_t num_data, float const d_data[],
+		bool const d_and_with[], bool d_result[], void *cuda_stream) noexcept {
+	return FilterDevice(kFilterFiniteFloat, kFilterFloat, num_data, d_data, 0, nullptr, nullptr, 0u,
+			d_and_with, d_result, cuda_stream);
+}
+
+sakura_Status sakura_Uint8ToBoolDevice(size_t num_data, uint8_t const d_data[], bool const d_and_with[],
+		bool d_result[], void *cuda_stream) noexcept {
+	return FilterDevice(kFilterNonZero, kFilterUint8, num_data, d_data, 0, nullptr, nullptr, 0u, d_and_with,
+			d_result, cuda_stream);
+}
+
+sakura_Status sakura_Uint32ToBoolDevice(size_t num_data, uint32_t const d_data[],
+		bool const d_and_with[], bool d_result[], void *cuda_stream) noexcept {
+	return FilterDevice(kFilterNonZero, kFilterUint32, num_data, d_data, 0, nullptr, nullptr, 0u,
+			d_and_with, d_result, cuda_stream);
+}
+
+sakura_Status sakura_InvertBoolDevice(size_t num_data, bool const d_data[], bool const d_and_with[],
+		bool d_result[], void *cuda_stream) noexcept {
+	return FilterDevice(kFilterInvertBool, kFilterUint8, num_data, d_data, 0, nullptr, nullptr, 0u,
+			d_and_with, d_result, cuda_stream);
 }
 
 // ---------------------------------------------------------------- calibration
