@@ -363,6 +363,48 @@ sakura_Status sakura_Uint32ToBoolDevice(size_t num_data, uint32_t const d_data[]
 sakura_Status sakura_InvertBoolDevice(size_t num_data, bool const d_data[], bool const d_and_with[],
 		bool d_result[], void *cuda_stream) SAKURA_B200_NOEXCEPT;
 
+/* ---- interpolation of many arrays at once ------------------------------
+ * sakura.h:961-1096 / interpolation.cc. Nearest and linear interpolation (and polynomial of order
+ * 0, which the reference maps to nearest) with masked base data, no extrapolation, ascending or
+ * descending positions; same argument rules and results as the reference. Polynomial (order > 0)
+ * and natural-spline interpolation are not implemented: kInvalidArgument, never approximated. */
+typedef enum {
+	sakura_InterpolationMethod_kNearest = 0,
+	sakura_InterpolationMethod_kLinear = 1,
+	sakura_InterpolationMethod_kPolynomial = 2,
+	sakura_InterpolationMethod_kSpline = 3,
+	sakura_InterpolationMethod_kNumElements = 4
+} sakura_InterpolationMethod;
+
+/** Replaces sakura_InterpolateXAxisFloat, sakura.h:1073: data laid out [num_array][num_base]. */
+sakura_Status sakura_InterpolateXAxisFloat(sakura_InterpolationMethod interpolation_method,
+		uint8_t polynomial_order, size_t num_base, double const base_position[/*num_base*/],
+		size_t num_array, float const base_data[/*num_base*num_array*/],
+		bool const base_mask[/*num_base*num_array*/], size_t num_interpolated,
+		double const interpolated_position[/*num_interpolated*/],
+		float interpolated_data[/*num_interpolated*num_array*/],
+		bool interpolated_mask[/*num_interpolated*num_array*/]) SAKURA_B200_NOEXCEPT;
+/** Replaces sakura_InterpolateYAxisFloat, sakura.h:1087: data laid out [num_base][num_array]
+ *  (e.g. Tsys[time][channel] -> one row per spectrum for the calibration). */
+sakura_Status sakura_InterpolateYAxisFloat(sakura_InterpolationMethod interpolation_method,
+		uint8_t polynomial_order, size_t num_base, double const base_position[/*num_base*/],
+		size_t num_array, float const base_data[/*num_base*num_array*/],
+		bool const base_mask[/*num_base*num_array*/], size_t num_interpolated,
+		double const interpolated_position[/*num_interpolated*/],
+		float interpolated_data[/*num_interpolated*num_array*/],
+		bool interpolated_mask[/*num_interpolated*num_array*/]) SAKURA_B200_NOEXCEPT;
+/** NEW. All arrays on the device (positions too); asynchronous on `cuda_stream`. */
+sakura_Status sakura_InterpolateXAxisFloatDevice(sakura_InterpolationMethod interpolation_method,
+		uint8_t polynomial_order, size_t num_base, double const d_base_position[], size_t num_array,
+		float const d_base_data[], bool const d_base_mask[], size_t num_interpolated,
+		double const d_interpolated_position[], float d_interpolated_data[], bool d_interpolated_mask[],
+		void *cuda_stream) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_InterpolateYAxisFloatDevice(sakura_InterpolationMethod interpolation_method,
+		uint8_t polynomial_order, size_t num_base, double const d_base_position[], size_t num_array,
+		float const d_base_data[], bool const d_base_mask[], size_t num_interpolated,
+		double const d_interpolated_position[], float d_interpolated_data[], bool d_interpolated_mask[],
+		void *cuda_stream) SAKURA_B200_NOEXCEPT;
+
 /* ---- NEW: library introspection (measurement support) --------------------- */
 
 /** Number of CUDA kernels this library has launched in this process so far. */

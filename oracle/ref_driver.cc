@@ -382,4 +382,19 @@ int ref_bool_filter(int op, int type, size_t num_data, void const *data, size_t 
 	}
 }
 
+/* sakura_InterpolateXAxisFloat (y_axis == 0) / sakura_InterpolateYAxisFloat (y_axis != 0). */
+int ref_interpolate(int y_axis, int method, int polynomial_order, size_t num_base,
+		double const *base_position, size_t num_array, float const *base_data, bool const *base_mask,
+		size_t num_interpolated, double const *interpolated_position, float *interpolated_data,
+		bool *interpolated_mask) {
+	sakura_InterpolationMethod const m = static_cast<sakura_InterpolationMethod>(method);
+	uint8_t const order = static_cast<uint8_t>(polynomial_order);
+	return y_axis ? sakura_InterpolateYAxisFloat(m, order, num_base, base_position, num_array, base_data,
+					base_mask, num_interpolated, interpolated_position, interpolated_data,
+					interpolated_mask)
+			: sakura_InterpolateXAxisFloat(m, order, num_base, base_position, num_array, base_data,
+					base_mask, num_interpolated, interpolated_position, interpolated_data,
+					interpolated_mask);
+}
+
 } // extern "C"

@@ -82,6 +82,8 @@ class Oracle:
         L.ref_calibrate_batch.restype = i32
         L.ref_bool_filter.argtypes = [i32, i32, sz, vp, sz, vp, vp, C.c_uint32, vp]
         L.ref_bool_filter.restype = i32
+        L.ref_interpolate.argtypes = [i32, i32, i32, sz, vp, sz, vp, vp, sz, vp, vp, vp]
+        L.ref_interpolate.restype = i32
         for name in ("ref_lsqfit_polynomial_batch", "ref_lsqfit_cubicspline_batch",
                      "ref_lsqfit_sinusoid_batch", "ref_statistics_batch"):
             getattr(L, name).restype = i32
@@ -218,6 +220,27 @@ class Oracle:
         st = self.lib.ref_bool_filter(self.FILTER_OPS[op], type_id, n, _ptr(data), nc, _ptr(lo),
                                       _ptr(hi), bits, _ptr(result))
         return result, int(st)
+
+    def interpolate(self, axis: str, method: int, base_position, base_data, base_mask,
+                    interpolated_position, polynomial_order: int = 0, prefill: float = np.nan):
+        """sakura_Interpolate{X,Y}AxisFloat. axis "y": base_data [num_base, num_array] -> result
+        [num_interpolated, num_array]; axis "x": [num_array, num_base] -> [num_array, num_interpolated].
+        Returns (data, mask, status); arrays without a valid base point keep `prefill`."""
+        bd = np.asarray(base_data, dtype=np.float32)
+        bm = np.asarray(base_mask, dtype=np.bool_)
+        bp = aligned_copy(np.asarray(base_position, dtype=np.float64))
+        ip = aligned_copy(np.asarray(interpolated_position, dtype=np.float64))
+        nb, ni = bp.size, ip.size
+        na = bd.shape[1] if axis == "y" else bd.shape[0]
+        shape = (ni, na) if axis == "y" else (na, ni)
+        out = aligned_empty(shape, np.float32)
+        out[...] = prefill
+        om = aligned_empty(shape, np.bool_)
+        om[...] = False
+        bd, bm = aligned_copy(bd), aligned_copy(bm)  # (named: they must outlive the call)
+        st = self.lib.ref_interpolate(1 if axis == "y" else 0, method, polynomial_order, nb, _ptr(bp), na,
+                                      _ptr(bd), _ptr(bm), ni, _ptr(ip), _ptr(out), _ptr(om))
+        return out, om, int(st)
 
     def statistics_batch(self, data, mask, accurate: bool = True, nthreads: int = 0):
         data, mask = self._rows(data, mask)

@@ -1246,6 +1246,87 @@ int ref_bool_filter(int op, int type, size_t num_data, void const *data, size_t 
 	return kStatusOK;
 }
 
+/* ------------------------------------------------------------------ interpolation
+ * interpolation.cc, nearest and linear (polynomial of order 0 is nearest, :1419-1422). For every
+ * array: the valid base points are gathered in ascending order of position (:905-922); no valid
+ * point -> mask false, data untouched (:1182-1185); one -> constant (:1186-1190); otherwise points
+ * below the first / at or above the last valid position take that point's value (:1207-1225) and a
+ * point with b_j <= x < b_{j+1} is interpolated between j and j+1 (Locate, :164-232): nearest
+ * :625-637, linear :691-704 with the final multiply-add fused as the Release build compiles it.
+ * The result for a point depends on its position only, so the reference's handling of descending
+ * interpolated positions (reverse, then write back to front) needs no restatement. */
+int ref_interpolate(int y_axis, int method, int polynomial_order, size_t num_base,
+		double const *base_position, size_t num_array, float const *base_data,
+		unsigned char const *base_mask, size_t num_interpolated, double const *interpolated_position,
+		float *interpolated_data, unsigned char *interpolated_mask) {
+	if (num_base == 0) { /* :1305-1309 */
+		return kStatusInvalidArgument;
+	}
+	if (num_interpolated == 0 || num_array == 0) { /* :1311-1316 */
+		return kStatusOK;
+	}
+	void const *arrays[6] = { base_position, base_data, interpolated_position, interpolated_data,
+			base_mask, interpolated_mask };
+	for (int k = 0; k < 6; ++k) { /* :1318-1335 */
+		if (arrays[k] == NULL || ((uintptr_t) arrays[k] % 32) != 0) {
+			return kStatusInvalidArgument;
+		}
+	}
+	int linear;
+	if (method == 0 || (method == 2 && polynomial_order == 0)) {
+		linear = 0;
+	} else if (method == 1) {
+		linear = 1;
+	} else {
+		return -1; /* polynomial / spline interpolation: not restated */
+	}
+	int const ascending = base_position[num_base - 1] > base_position[0];
+	double *vx = (double *) malloc(num_base * sizeof(double));
+	float *vy = (float *) malloc(num_base * sizeof(float));
+	for (size_t a = 0; a < num_array; ++a) {
+		size_t m = 0;
+		for (size_t k = 0; k < num_base; ++k) {
+			size_t const kb = ascending ? k : num_base - 1 - k;
+			size_t const e = y_axis ? kb * num_array + a : a * num_base + kb;
+			if (base_mask[e]) {
+				vx[m] = base_position[kb];
+				vy[m] = base_data[e];
+				++m;
+			}
+		}
+		for (size_t i = 0; i < num_interpolated; ++i) {
+			size_t const e = y_axis ? i * num_array + a : a * num_interpolated + i;
+			interpolated_mask[e] = (m != 0);
+			if (m == 0) {
+				continue;
+			}
+			double const x = interpolated_position[i];
+			float v;
+			if (m == 1 || x < vx[0]) {
+				v = vy[0];
+			} else if (x >= vx[m - 1]) {
+				v = vy[m - 1];
+			} else {
+				size_t j = 0;
+				while (vx[j + 1] <= x) {
+					++j;
+				}
+				if (linear) {
+					double const dydx = (double) (vy[j + 1] - vy[j]) / (vx[j + 1] - vx[j]);
+					v = (float) fma(dydx, x - vx[j], (double) vy[j]);
+				} else {
+					double const midpoint = (vx[j + 1] + vx[j]) / 2.0;
+					v = (x > midpoint) ? vy[j + 1] : vy[j];
+				}
+			}
+			interpolated_data[e] = v;
+		}
+	}
+	free(vx);
+	free(vy);
+	return kStatusOK;
+}
+
 /* standalone building blocks for the known-answer tests (numeric_operation.cc:867-968) */
 int oracle_get_lsq_coefficients(size_t num_data, float const *data, unsigned char const *mask,
 		size_t num_model_bases, double const *basis, size_t num_lsq_bases, size_t const *use_idx,

@@ -181,6 +181,11 @@ class SakuraLib:
         for name in ("sakura_SetTrueIfInRangesFloatDevice", "sakura_SetTrueIfInRangesIntDevice",
                      "sakura_SetTrueIfComparesFloatDevice", "sakura_SetTrueIfComparesIntDevice"):
             getattr(L, name).restype = C.c_int
+        for name in ("sakura_InterpolateXAxisFloat", "sakura_InterpolateYAxisFloat"):
+            getattr(L, name).argtypes = [C.c_int, C.c_uint8, sz, vp, sz, vp, vp, sz, vp, vp, vp]
+            getattr(L, name).restype = C.c_int
+            getattr(L, name + "Device").argtypes = [C.c_int, C.c_uint8, sz, vp, sz, vp, vp, sz, vp, vp, vp, vp]
+            getattr(L, name + "Device").restype = C.c_int
         L.sakura_b200_GetKernelLaunchCount.restype = C.c_uint64
         L.sakura_b200_GetLastHandOverCount.argtypes = [vp]
         L.sakura_b200_GetLastHandOverCount.restype = C.c_int64
@@ -380,6 +385,29 @@ class SakuraLib:
         else:
             raise ValueError(op)
         return result[:n], int(st)
+
+    # ------------------------------------------------------------------ interpolation
+    def interpolate(self, axis: str, method: int, base_position, base_data, base_mask,
+                    interpolated_position, polynomial_order: int = 0, prefill: float = np.nan):
+        """sakura_Interpolate{X,Y}AxisFloat on host arrays. axis "y": base_data [num_base, num_array]
+        -> [num_interpolated, num_array]; axis "x": [num_array, num_base] -> [num_array,
+        num_interpolated]. Returns (data, mask, status); arrays without a valid base point keep
+        `prefill`."""
+        bd = aligned_copy(np.asarray(base_data, dtype=np.float32))
+        bm = aligned_copy(np.asarray(base_mask, dtype=np.bool_))
+        bp = aligned_copy(np.asarray(base_position, dtype=np.float64))
+        ip = aligned_copy(np.asarray(interpolated_position, dtype=np.float64))
+        nb, ni = bp.size, ip.size
+        na = bd.shape[1] if axis == "y" else bd.shape[0]
+        shape = (ni, na) if axis == "y" else (na, ni)
+        out = aligned_empty(shape, np.float32)
+        out[...] = prefill
+        om = aligned_empty(shape, np.bool_)
+        om[...] = False
+        fn = self.lib.sakura_InterpolateYAxisFloat if axis == "y" else self.lib.sakura_InterpolateXAxisFloat
+        st = fn(method, polynomial_order, nb, _ptr(bp), na, _ptr(bd), _ptr(bm), ni, _ptr(ip), _ptr(out),
+                _ptr(om))
+        return out, om, int(st)
 
     # ------------------------------------------------------------------ statistics
     def compute_statistics_batch(self, data, mask) -> np.ndarray:

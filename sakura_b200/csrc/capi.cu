@@ -15,6 +15,7 @@
 #include "lsqfit_spline.cuh"
 #include "calibration.cuh"
 #include "bool_filters.cuh"
+#include "interpolation.cuh"
 #include "statistics.cuh"
 
 #include <cuda_runtime.h>
@@ -1628,6 +1629,183 @@ sakura_Status sakura_InvertBoolDevice(size_t num_data, bool const d_data[], bool
 		bool d_result[], void *cuda_stream) noexcept {
 	return FilterDevice(kFilterInvertBool, kFilterUint8, num_data, d_data, 0, nullptr, nullptr, 0u,
 			d_and_with, d_result, cuda_stream);
+}
+
+// ---------------------------------------------------------------- interpolation
+namespace {
+
+// argument rules of interpolation.cc:1288-1340 (in that order)
+sakura_Status CheckInterpolate(int method, uint8_t polynomial_order, size_t num_base,
+		void const *base_position, size_t num_array, void const *base_data, void const *base_mask,
+		size_t num_interpolated, void const *interpolated_position, void const *interpolated_data,
+		void const *interpolated_mask, bool host, bool *nothing_to_do, int *linear) {
+	*nothing_to_do = false;
+	CHECK_ARGS(num_base != 0);
+	if (num_interpolated == 0 || num_array == 0) {
+		*nothing_to_do = true;
+		return sakura_Status_kOK;
+	}
+	if (host) {
+		CHECK_ARGS(sakura_IsAligned(base_position) && sakura_IsAligned(base_data)
+				&& sakura_IsAligned(interpolated_position) && sakura_IsAligned(interpolated_data)
+				&& sakura_IsAligned(base_mask) && sakura_IsAligned(interpolated_mask));
+	}
+	CHECK_ARGS(base_position != nullptr && base_data != nullptr && interpolated_position != nullptr
+			&& interpolated_data != nullptr && base_mask != nullptr && interpolated_mask != nullptr);
+	// nearest, linear, and polynomial of order 0 (= nearest, :1419-1422). Polynomial (Neville) and
+	// natural-spline interpolation are not part of this library: rejected, never approximated.
+	if (method == 0 || (method == 2 && polynomial_order == 0)) {
+		*linear = 0;
+	} else if (method == 1) {
+		*linear = 1;
+	} else {
+		snprintf(g_last_error, sizeof(g_last_error),
+				"interpolation method %d is not implemented on the GPU path (nearest and linear are)", method);
+		return sakura_Status_kInvalidArgument;
+	}
+	return sakura_Status_kOK;
+}
+
+sakura_Status InterpolateHost(int y_axis, int method, uint8_t polynomial_order, size_t num_base,
+		double const *base_position, size_t num_array, float const *base_data, bool const *base_mask,
+		size_t num_interpolated, double const *interpolated_position, float *interpolated_data,
+		bool *interpolated_mask) {
+	bool nothing = false;
+	int linear = 0;
+	sakura_Status st = CheckInterpolate(method, polynomial_order, num_base, base_position, num_array,
+			base_data, base_mask, num_interpolated, interpolated_position, interpolated_data,
+			interpolated_mask, true, &nothing, &linear);
+	if (st != sakura_Status_kOK || nothing) {
+		return st;
+	}
+	DeviceInfo info;
+	st = CurrentDevice(&info);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	static thread_local DeviceBuffer d_bp, d_bd, d_bm, d_ip, d_od, d_om;
+	size_t const nbase = num_base * num_array;
+	size_t const nout = num_interpolated * num_array;
+	CUDA_TRY(d_bp.Reserve(num_base * sizeof(double)));
+	CUDA_TRY(d_bd.Reserve(nbase * sizeof(float)));
+	CUDA_TRY(d_bm.Reserve(nbase));
+	CUDA_TRY(d_ip.Reserve(num_interpolated * sizeof(double)));
+	CUDA_TRY(d_od.Reserve(nout * sizeof(float)));
+	CUDA_TRY(d_om.Reserve(nout));
+	cudaStream_t const stream = 0;
+	CUDA_TRY(cudaMemcpyAsync(d_bp.ptr, base_position, num_base * sizeof(double), cudaMemcpyHostToDevice, stream));
+	CUDA_TRY(cudaMemcpyAsync(d_bd.ptr, base_data, nbase * sizeof(float), cudaMemcpyHostToDevice, stream));
+	CUDA_TRY(cudaMemcpyAsync(d_bm.ptr, base_mask, nbase, cudaMemcpyHostToDevice, stream));
+	CUDA_TRY(cudaMemcpyAsync(d_ip.ptr, interpolated_position, num_interpolated * sizeof(double),
+			cudaMemcpyHostToDevice, stream));
+	// arrays without a valid base point keep the caller's output values (interpolation.cc:1182-1185)
+	CUDA_TRY(cudaMemcpyAsync(d_od.ptr, interpolated_data, nout * sizeof(float), cudaMemcpyHostToDevice, stream));
+	InterpolateParams p;
+	memset(&p, 0, sizeof(p));
+	p.y_axis = y_axis;
+	p.linear = linear;
+	p.num_base = num_base;
+	p.num_array = num_array;
+	p.num_interpolated = num_interpolated;
+	p.base_position = d_bp.As<double>();
+	p.base_data = d_bd.As<float>();
+	p.base_mask = d_bm.As<uint8_t>();
+	p.interpolated_position = d_ip.As<double>();
+	p.interpolated_data = d_od.As<float>();
+	p.interpolated_mask = d_om.As<uint8_t>();
+	cudaError_t const e = LaunchInterpolate(p, info.num_sms, stream);
+	g_launch_count += 1;
+	g_last_kernel = "interpolate";
+	if (e != cudaSuccess) {
+		SetError("LaunchInterpolate", e);
+		return sakura_Status_kUnknownError;
+	}
+	CUDA_TRY(cudaMemcpyAsync(interpolated_data, d_od.ptr, nout * sizeof(float), cudaMemcpyDeviceToHost, stream));
+	CUDA_TRY(cudaMemcpyAsync(interpolated_mask, d_om.ptr, nout, cudaMemcpyDeviceToHost, stream));
+	CUDA_TRY(cudaStreamSynchronize(stream));
+	return sakura_Status_kOK;
+}
+
+sakura_Status InterpolateDevice(int y_axis, int method, uint8_t polynomial_order, size_t num_base,
+		double const *d_base_position, size_t num_array, float const *d_base_data, bool const *d_base_mask,
+		size_t num_interpolated, double const *d_interpolated_position, float *d_interpolated_data,
+		bool *d_interpolated_mask, void *cuda_stream) {
+	bool nothing = false;
+	int linear = 0;
+	sakura_Status st = CheckInterpolate(method, polynomial_order, num_base, d_base_position, num_array,
+			d_base_data, d_base_mask, num_interpolated, d_interpolated_position, d_interpolated_data,
+			d_interpolated_mask, false, &nothing, &linear);
+	if (st != sakura_Status_kOK || nothing) {
+		return st;
+	}
+	DeviceInfo info;
+	st = CurrentDevice(&info);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	InterpolateParams p;
+	memset(&p, 0, sizeof(p));
+	p.y_axis = y_axis;
+	p.linear = linear;
+	p.num_base = num_base;
+	p.num_array = num_array;
+	p.num_interpolated = num_interpolated;
+	p.base_position = d_base_position;
+	p.base_data = d_base_data;
+	p.base_mask = reinterpret_cast<uint8_t const *>(d_base_mask);
+	p.interpolated_position = d_interpolated_position;
+	p.interpolated_data = d_interpolated_data;
+	p.interpolated_mask = reinterpret_cast<uint8_t *>(d_interpolated_mask);
+	cudaError_t const e = LaunchInterpolate(p, info.num_sms, static_cast<cudaStream_t>(cuda_stream));
+	g_launch_count += 1;
+	g_last_kernel = "interpolate";
+	if (e != cudaSuccess) {
+		SetError("LaunchInterpolate", e);
+		return sakura_Status_kUnknownError;
+	}
+	return sakura_Status_kOK;
+}
+
+} // namespace
+
+sakura_Status sakura_InterpolateXAxisFloat(sakura_InterpolationMethod interpolation_method,
+		uint8_t polynomial_order, size_t num_base, double const base_position[], size_t num_array,
+		float const base_data[], bool const base_mask[], size_t num_interpolated,
+		double const interpolated_position[], float interpolated_data[],
+		bool interpolated_mask[]) noexcept {
+	return InterpolateHost(0, static_cast<int>(interpolation_method), polynomial_order, num_base,
+			base_position, num_array, base_data, base_mask, num_interpolated, interpolated_position,
+			interpolated_data, interpolated_mask);
+}
+
+sakura_Status sakura_InterpolateYAxisFloat(sakura_InterpolationMethod interpolation_method,
+		uint8_t polynomial_order, size_t num_base, double const base_position[], size_t num_array,
+		float const base_data[], bool const base_mask[], size_t num_interpolated,
+		double const interpolated_position[], float interpolated_data[],
+		bool interpolated_mask[]) noexcept {
+	return InterpolateHost(1, static_cast<int>(interpolation_method), polynomial_order, num_base,
+			base_position, num_array, base_data, base_mask, num_interpolated, interpolated_position,
+			interpolated_data, interpolated_mask);
+}
+
+sakura_Status sakura_InterpolateXAxisFloatDevice(sakura_InterpolationMethod interpolation_method,
+		uint8_t polynomial_order, size_t num_base, double const d_base_position[], size_t num_array,
+		float const d_base_data[], bool const d_base_mask[], size_t num_interpolated,
+		double const d_interpolated_position[], float d_interpolated_data[], bool d_interpolated_mask[],
+		void *cuda_stream) noexcept {
+	return InterpolateDevice(0, static_cast<int>(interpolation_method), polynomial_order, num_base,
+			d_base_position, num_array, d_base_data, d_base_mask, num_interpolated, d_interpolated_position,
+			d_interpolated_data, d_interpolated_mask, cuda_stream);
+}
+
+sakura_Status sakura_InterpolateYAxisFloatDevice(sakura_InterpolationMethod interpolation_method,
+		uint8_t polynomial_order, size_t num_base, double const d_base_position[], size_t num_array,
+		float const d_base_data[], bool const d_base_mask[], size_t num_interpolated,
+		double const d_interpolated_position[], float d_interpolated_data[], bool d_interpolated_mask[],
+		void *cuda_stream) noexcept {
+	return InterpolateDevice(1, static_cast<int>(interpolation_method), polynomial_order, num_base,
+			d_base_position, num_array, d_base_data, d_base_mask, num_interpolated, d_interpolated_position,
+			d_interpolated_data, d_interpolated_mask, cuda_stream);
 }
 
 // ---------------------------------------------------------------- calibration
