@@ -348,7 +348,7 @@ __device__ __forceinline__ bool UpdateAndSolve(Shared<K, NT> &sh, PolyConst cons
 // CAL: position-switch calibration (and NaN/Inf flagging) applied while the row is loaded; only
 // instantiated together with FULL, other shapes calibrate in a pre-pass (capi.cu).
 template<int K, int NT, bool FULL, bool CAL>
-__global__ void __launch_bounds__(NT, (NT == 128 ? (K >= 7 ? 4 : kMinBlocks128) :
+__global__ void __launch_bounds__(NT, (NT == 64 ? (K >= 7 ? 8 : 12) : NT == 128 ? (K >= 7 ? 4 : kMinBlocks128) :
 		(K >= 7 ? 2 : kMinBlocks256)))
 PolyFitKernel(PolyFitParams const p, PolyConst const pc) {
 	constexpr int NW = NT / 32;
@@ -912,6 +912,9 @@ cudaError_t LaunchKN(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
 
 template<int K>
 cudaError_t LaunchK(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
+	if (p.n == 32 * 64) { // 2048 channels (the e2e shape): 64 threads own all of their 32 slots
+		return LaunchKN<K, 64>(p, num_sms, stream);
+	}
 	if (p.n <= 32 * 128) {
 		return LaunchKN<K, 128>(p, num_sms, stream);
 	}
@@ -937,7 +940,7 @@ bool PolyFastSupported(size_t n, size_t K, size_t data_stride, size_t mask_strid
 }
 
 bool PolyFusedCalibrationSupported(size_t n) {
-	return n == 4u * 128u * kSlotGroups || n == 4u * 256u * kSlotGroups;
+	return n == 4u * 64u * kSlotGroups || n == 4u * 128u * kSlotGroups || n == 4u * 256u * kSlotGroups;
 }
 
 namespace {

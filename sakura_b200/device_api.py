@@ -263,6 +263,71 @@ class DeviceFits:
             self._flat(res["lsqfit_status"], ("<i4",), "lsqfit_status", R), self._stream(stream))
         return res
 
+    # ---- mask builders: flat device arrays, optional AND into an existing mask ----
+    def _filter_out(self, data, out):
+        if out is None:
+            out = _torch().empty(tuple(data.shape), dtype=_torch().bool, device=self._device_of(data))
+        return out
+
+    @staticmethod
+    def _addr(obj):
+        return None if obj is None else C.c_void_p(obj.data_ptr() if hasattr(obj, "data_ptr") else
+                                                    obj.__cuda_array_interface__["data"][0])
+
+    def _check(self, st, what):
+        if st != STATUS_OK:
+            raise RuntimeError(f"{what} -> {st}: {self.lib.last_error()}")
+
+    def in_ranges(self, data, lower, upper, inclusive: bool = False, and_with=None, out=None, stream=None):
+        """sakura_SetTrueIfInRanges{Float,Int}Device on a contiguous float32 / int32 device array of any
+        shape; `lower` / `upper` are host sequences; `and_with` (may be `out`) is ANDed in."""
+        is_int = "int" in str(data.dtype)
+        dt = np.int32 if is_int else np.float32
+        lo = np.ascontiguousarray(np.asarray(lower, dtype=dt).reshape(-1))
+        hi = np.ascontiguousarray(np.asarray(upper, dtype=dt).reshape(-1))
+        out = self._filter_out(data, out)
+        fn = self.lib.lib.sakura_SetTrueIfInRangesIntDevice if is_int else self.lib.lib.sakura_SetTrueIfInRangesFloatDevice
+        self._check(fn(bool(inclusive), int(np.prod(data.shape)), self._addr(data), lo.size,
+                       C.c_void_p(lo.ctypes.data), C.c_void_p(hi.ctypes.data), self._addr(and_with),
+                       self._addr(out), self._stream(stream)), "sakura_SetTrueIfInRanges*Device")
+        return out
+
+    def finite(self, data, and_with=None, out=None, stream=None):
+        """sakura_SetFalseIfNanOrInfFloatDevice."""
+        out = self._filter_out(data, out)
+        self._check(self.lib.lib.sakura_SetFalseIfNanOrInfFloatDevice(
+            int(np.prod(data.shape)), self._addr(data), self._addr(and_with), self._addr(out),
+            self._stream(stream)), "sakura_SetFalseIfNanOrInfFloatDevice")
+        return out
+
+    def uint8_to_bool(self, data, invert: bool = False, and_with=None, out=None, stream=None):
+        """sakura_Uint8ToBoolDevice (and sakura_InvertBoolDevice on the result when `invert`)."""
+        out = self._filter_out(data, out)
+        n = int(np.prod(data.shape))
+        self._check(self.lib.lib.sakura_Uint8ToBoolDevice(n, self._addr(data), None if invert else self._addr(and_with),
+                                                        self._addr(out), self._stream(stream)), "sakura_Uint8ToBoolDevice")
+        if invert:
+            self._check(self.lib.lib.sakura_InvertBoolDevice(n, self._addr(out), self._addr(and_with), self._addr(out),
+                                                           self._stream(stream)), "sakura_InvertBoolDevice")
+        return out
+
+    def interpolate_y(self, method: int, base_position, base_data, base_mask, interpolated_position,
+                      out=None, out_mask=None, stream=None):
+        """sakura_InterpolateYAxisFloatDevice: base_data [num_base, num_array] -> [num_interpolated,
+        num_array] (float64 positions on the device). Returns (data, mask)."""
+        torch = _torch()
+        nb, na = base_data.shape
+        ni = int(interpolated_position.shape[0])
+        if out is None:
+            out = torch.empty((ni, na), dtype=torch.float32, device=self._device_of(base_data))
+        if out_mask is None:
+            out_mask = torch.empty((ni, na), dtype=torch.bool, device=self._device_of(base_data))
+        self._check(self.lib.lib.sakura_InterpolateYAxisFloatDevice(
+            method, 0, nb, self._addr(base_position), na, self._addr(base_data), self._addr(base_mask), ni,
+            self._addr(interpolated_position), self._addr(out), self._addr(out_mask), self._stream(stream)),
+            "sakura_InterpolateYAxisFloatDevice")
+        return out, out_mask
+
     def statistics(self, data, mask, stream=None):
         """sakura_ComputeStatisticsFloatBatchDevice; returns a torch uint8 tensor [R, 48] whose rows
         are sakura_StatisticsResultFloat records (view it with capi.STAT_DTYPE after .cpu())."""
