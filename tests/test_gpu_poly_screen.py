@@ -113,3 +113,39 @@ def test_screen_dense_flags_and_runs(lib):
     p, _, _ = fit(lib, 5, data, mask, 3.0, 6, False, want_best_fit=True)
     assert_same(s, p, data)
     assert (s["status"] != 0).sum() == (p["status"] != 0).sum()
+
+
+@pytest.mark.parametrize("rows,n,nfit,clip", [(1 << 17, 4096, 5, 3.0), (1 << 16, 4096, 9, 2.5), (1 << 15, 8192, 6, 3.0)])
+def test_screen_large_device_batches(lib, rows, n, nfit, clip):
+    """Device-resident batches: identical clip decisions with and without screening on every row,
+    bit-identical results from run to run (fixed reduction orders, no atomics in the data path)."""
+    import torch
+    import bench
+    from sakura_b200.device_api import DeviceFits
+    dev = DeviceFits(lib)
+    data, mask = bench.generate_on_device(torch, rows, n, seed=rows + nfit, device=torch.device("cuda", 0))
+    st, ctx = lib.create_polynomial_context(5, n)
+    assert st == STATUS_OK
+    old = os.environ.get("SAKURA_B200_POLY_SCREEN")
+    try:
+        os.environ["SAKURA_B200_POLY_SCREEN"] = "1"
+        a = dev.polynomial(ctx, 5, data, mask, clip, nfit)
+        assert lib.last_kernel_name() == "poly_screen"
+        handed = lib.last_handover_count(ctx)
+        b = dev.polynomial(ctx, 5, data, mask, clip, nfit)
+        os.environ["SAKURA_B200_POLY_SCREEN"] = "0"
+        c = dev.polynomial(ctx, 5, data, mask, clip, nfit)
+        assert lib.last_kernel_name() == "poly_fast"
+    finally:
+        if old is None:
+            del os.environ["SAKURA_B200_POLY_SCREEN"]
+        else:
+            os.environ["SAKURA_B200_POLY_SCREEN"] = old
+    lib.destroy_context(ctx)
+    assert 0 <= handed <= rows // 200, handed
+    for key in ("final_mask", "status", "lsqfit_status", "rms", "coeff", "residual"):
+        assert torch.equal(a[key], b[key]), key                   # run-to-run
+    assert torch.equal(a["final_mask"], c["final_mask"])
+    assert torch.equal(a["status"], c["status"])
+    rel = ((a["rms"] - c["rms"]).abs() / c["rms"].abs()).max().item()
+    assert rel <= 1e-6, rel
