@@ -332,7 +332,70 @@ def side_configs(lib, torch, device, rows: int = 16384, n: int = 8192, reps: int
                      "peak_source": "FP64 DMMA/DFMA issue rate measured on this GPU (64 FMA/clk/SM, "
                                     "tools/microbench.cu; ncu dmma sub-pipe) x 148 SMs x max SM clock"}}
     lib.destroy_context(ctx)
+    del data, mask, res, fm, co
+    out["config_c5_chain"] = chain_config(lib, torch, device)
     return out
+
+
+def chain_config(lib, torch, device, rows: int = 1 << 17, n: int = 2048, reps: int = 3) -> dict:
+    """BASELINE configs[4] (the e2eReduce chain, bench/e2eReduce/src/main.cc:80-240) on device arrays
+    at reduced row count: linear Tsys interpolation to one row per spectrum, uint8 flags -> mask with
+    edge flags, calibration fused into the poly-5 fit (NaN/Inf flags merged, 5 fits), clipping of the
+    residual merged into the mask, statistics. One timed pass = all five steps back to back."""
+    from sakura_b200.device_api import DeviceFits
+    dev = DeviceFits(lib)
+    sky, mask0 = generate_on_device(torch, rows, n, seed=20240611 + 11, device=device)
+    off = 300.0 + 20.0 * torch.randn(rows, n, device=device)
+    on = off * (1.0 + sky / 250.0)
+    flags = (~mask0).to(torch.uint8) * 4
+    del sky, mask0
+    t_base = torch.linspace(0.0, 100.0, 6, dtype=torch.float64, device=device)
+    tsys_base = (150.0 + 10.0 * torch.randn(6, n, device=device)).float()
+    tsys_valid = torch.rand(6, n, device=device) < 0.98
+    t_rows = torch.sort(torch.rand(rows, dtype=torch.float64, device=device) * 110.0 - 5.0).values
+    chan = torch.arange(n, dtype=torch.int32, device=device).repeat(rows, 1)
+    st, ctx = lib.create_polynomial_context(5, n)
+    tsys = torch.empty(rows, n, dtype=torch.float32, device=device)
+    tsys_m = torch.empty(rows, n, dtype=torch.bool, device=device)
+    mask = torch.empty(rows, n, dtype=torch.bool, device=device)
+    clipm = torch.empty(rows, n, dtype=torch.bool, device=device)
+    res = dev.polynomial(ctx, 5, on, flags == 0, 3.0, 5)
+    res.pop("call_status")
+    kernels = []
+
+    def chain(record=False):
+        dev.interpolate_y(1, t_base, tsys_base, tsys_valid, t_rows, out=tsys, out_mask=tsys_m)
+        record and kernels.append(lib.last_kernel_name())
+        dev.uint8_to_bool(flags, invert=True, out=mask)
+        dev.in_ranges(chan, [31], [n - 32], inclusive=False, and_with=mask, out=mask)
+        record and kernels.append(lib.last_kernel_name())
+        dev.calibrate_and_polynomial(ctx, 5, tsys, on, off, mask, 3.0, 5, flag_nan_or_inf=True, out=res)
+        record and kernels.append(lib.last_kernel_name())
+        dev.in_ranges(res["residual"], [-5.0], [5.0], inclusive=False, and_with=res["final_mask"], out=clipm)
+        stats = dev.statistics(res["residual"], clipm)
+        record and kernels.append(lib.last_kernel_name())
+        return stats
+
+    chain(record=True)
+    chain()
+    torch.cuda.synchronize(device)
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        chain()
+    e1.record()
+    torch.cuda.synchronize(device)
+    ms = e0.elapsed_time(e1) / reps
+    rows_ok = int((res["status"] == 0).sum().item())
+    lib.destroy_context(ctx)
+    bps = n * (4 + 1 + 1 + 4) + 48 + 8 + 48  # SURVEY 8(d), C5 fused figure
+    return {"workload": f"{rows} x {n} ch: Tsys interpolation + mask builders + calibrate&fit (poly-5, 5 fits) "
+                        "+ residual clipping + statistics, device arrays",
+            "value": rows / (ms * 1e-3), "unit": UNIT, "ms": ms, "kernels": kernels, "rows_ok": rows_ok,
+            "roofline": {"bound": "hbm", "bytes_per_spectrum": bps,
+                         "achieved": rows * bps / (ms * 1e-3) / 1e9, "peak": measured_peak_gbs()[0],
+                         "unit": "GB/s", "frac": rows * bps / (ms * 1e-3) / 1e9 / measured_peak_gbs()[0]}}
 
 
 # ----------------------------------------------------------------------------- our arm
