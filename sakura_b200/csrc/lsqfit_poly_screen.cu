@@ -74,6 +74,7 @@ struct ScreenShared {
 	double cz[K]; // model coefficients in the channel index z
 	double cx[K]; // ... in x = z/(n-1)
 	double cxs[K]; // coefficients of the model the stored r~ refers to
+	double kappa, ikappa; // rms of the previous fit and its reciprocal (scale of the next fit's bounds)
 	double c1s; // sum |cxs_k|
 	double es_block; // 2^-40 (A + C1) of the stored model
 	double ebase; // thread-independent part of the screening band
@@ -196,18 +197,14 @@ __device__ __forceinline__ double warp_max_upper(double a) {
 	return static_cast<double>(__uint_as_float(__reduce_max_sync(0xffffffffu, bits)));
 }
 
-/** >= sqrt(v) for v >= 0 (float square root of the value rounded up; +Inf when out of float range) */
-__device__ __forceinline__ double sqrt_upper(double v) {
-	return static_cast<double>(__fsqrt_ru(__double2float_ru(v))) * (1.0 + 0x1p-20);
-}
-
-/** sqrt(v) to ~1e-13 relative for v in [1e-30, 1e30] (float rsqrt estimate + two Newton steps) */
-__device__ __forceinline__ double sqrt_fast(double v) {
+/** 1/sqrt(v) to ~1e-13 relative for v in [1e-30, 1e30] (float rsqrt estimate + two Newton steps);
+ *  sqrt(v) = v * rsqrt_fast(v) */
+__device__ __forceinline__ double rsqrt_fast(double v) {
 	double r = static_cast<double>(rsqrtf(static_cast<float>(v)));
 	double const hv = 0.5 * v;
 	r = fma(r, fma(-hv * r, r, 0.5), r);
 	r = fma(r, fma(-hv * r, r, 0.5), r);
-	return v * r;
+	return r;
 }
 
 // One warp: apply the per-warp moment totals, solve, derive the control block of the next pass.
@@ -297,36 +294,44 @@ __device__ __forceinline__ void Control(ScreenShared<K, NT> &sh, PolyConst const
 				}
 				ss = fma(cx[k], g - 2.0 * T[k], ss);
 			}
-			double const ymag = sqrt_upper(N * Q); // >= sum |y|
-			double const w2 = Q + 2.0 * c1 * ymag + c1 * c1 * N;
-			double const e64_ss = kTiny40 * w2;
-			double const e64_sum = kTiny40 * (ymag + c1 * N);
+			// The bounds are kept free of square roots and divisions on the dependent chain (this warp is
+			// what the other three wait for): products of the form a sqrt(N ss) are bounded by
+			// (a^2 N + ss) / 2, and sum |rho| / N <= sqrt(ss / N) reuses the rms computed anyway.
+			double const e64_ss = kTiny40 * 2.0 * (Q + c1 * c1 * N); // >= 2^-40 (Q + 2 c1 sum|y| + c1^2 N)
 			double const ssc = fmax(ss + e64_ss, 0.0);
-			double const rt = sqrt_upper(N * ssc); // >= sum |rho|
-			// what rounding the model and the residual to float can change (|e_i| <= u (A + |rho_i|))
-			double const d_ss = 2.0 * kU32 * kSlack * (A * rt + ssc)
-					+ 2.0 * kU32 * kU32 * (N * A * A + ssc) + e64_ss + kTiny44 * ssc;
-			double const d_sum = kU32 * kSlack * (N * A + rt) + e64_sum;
-			// (1/N is good to an ulp or two: absorbed by the 2^-40 nudges below)
-			double const mean_m = (sum_r - d_sum) * inv_n;
-			double const mean_p = (sum_r + d_sum) * inv_n;
-			double const q_m = (ss - d_ss) * inv_n;
+			// what rounding the model and the residual to float can change (|e_i| <= u (A + |rho_i|)):
+			// 2 u (A sum|rho| + ss) + 2 u^2 (N A^2 + ss). sum|rho| <= sqrt(N ss) <= (N kappa + ss / kappa) / 2
+			// for any kappa > 0: the previous fit's rms (tight within a few per cent), A for the first fit
+			double const a2n = A * A * N;
+			double const a_sum_rho = first ? 0.5 * (a2n + ssc) : 0.5 * A * fma(N, sh.kappa, ssc * sh.ikappa);
+			double const d_ss = 2.0 * kU32 * kSlack * (a_sum_rho + ssc) + 2.0 * kU32 * kU32 * (a2n + ssc) + e64_ss
+					+ kTiny44 * ssc;
+			double const q_m = (ss - d_ss) * inv_n; // (1/N is good to an ulp or two: absorbed by the nudges)
 			double const q_p = (ss + d_ss) * inv_n;
-			double const m2a = mean_m * mean_m;
-			double const m2b = mean_p * mean_p;
-			double const m2max = fmax(m2a, m2b);
-			double const m2min = (mean_m <= 0.0 && mean_p >= 0.0) ? 0.0 : fmin(m2a, m2b);
-			double const var_m = q_m - m2max - kTiny40 * q_p;
-			double const var_p = q_p - m2min + kTiny40 * q_p;
-			if (var_m > 1e-30 && var_p < 1e30 && clip > 0.0f) {
+			if (q_m > 1e-30 && q_p < 1e30 && clip > 0.0f) {
+				double const r_m = rsqrt_fast(q_m);
+				double const r_p = rsqrt_fast(q_p);
+				double const s_p = q_p * r_p * (1.0 + kTiny40); // >= sqrt(ss/N) >= sum|rho| / N
+				if (lane == 0) {
+					sh.kappa = s_p;
+					sh.ikappa = r_p;
+				}
+				// |mean| <= |sum r| / N + u (A + sum|rho| / N) + 2^-40 (sum|y| / N + c1), sum|y| <= N A + sum|rho|
+				double const d_mean = kU32 * kSlack * (A + s_p) + kTiny40 * (A + s_p + c1);
+				double const mean_c = sum_r * inv_n;
+				double const mean_m = mean_c - d_mean;
+				double const mean_p = mean_c + d_mean;
+				double const mabs = fabs(mean_c) + d_mean;
+				double const m2max = mabs * mabs;
+				// var = q - mean^2 in [q_m - m2max, q_p]; sqrt(q_m - m2) >= sqrt(q_m) - m2 / sqrt(q_m)
 				double const sigma = static_cast<double>(clip);
-				double const rms_m = sqrt_fast(var_m) * (1.0 - kTiny40);
-				double const rms_p = sqrt_fast(var_p) * (1.0 + kTiny40);
+				double const rms_m = fma(-m2max * (1.0 + kTiny40), r_m, q_m * r_m) * (1.0 - kTiny40);
+				double const rms_p = s_p;
 				// thresholds as make_thresholds (device_common.cuh) forms them; conversions to float
 				// round to nearest and are monotone, the FP64 roundings are covered by the nudges
 				float const thr_m = static_cast<float>(sigma * rms_m * (1.0 - kTiny40));
 				float const thr_p = static_cast<float>(sigma * rms_p * (1.0 + kTiny40));
-				double const nudge = kTiny40 * (fabs(mean_m) + fabs(mean_p) + static_cast<double>(thr_p));
+				double const nudge = kTiny40 * (mabs + static_cast<double>(thr_p));
 				lo_m = static_cast<float>(mean_m - static_cast<double>(thr_p) - nudge);
 				lo_p = static_cast<float>(mean_p - static_cast<double>(thr_m) + nudge);
 				hi_m = static_cast<float>(mean_m + static_cast<double>(thr_m) - nudge);
@@ -338,8 +343,8 @@ __device__ __forceinline__ void Control(ScreenShared<K, NT> &sh, PolyConst const
 						&& fabsf(lo_m) <= FLT_MAX && fabsf(hi_p) <= FLT_MAX
 						&& __fsub_rn(hi_m, lo_p) >= 0x1p-40f;
 				if (by_compare) {
-					double const theta = fmax(fmax(fabs(static_cast<double>(lo_m)), fabs(static_cast<double>(lo_p))),
-							fmax(fabs(static_cast<double>(hi_m)), fabs(static_cast<double>(hi_p))));
+					// lo_m <= lo_p < 0 < hi_m <= hi_p here
+					double const theta = static_cast<double>(fmaxf(-lo_m, hi_p));
 					if (have_stored && D <= kStaleFraction * static_cast<double>(thr_m)) {
 						mode = kModeStale;
 						ebase = kU32 * kSlack * (A + 6.0 * (theta + D)) + kTiny40 * (A + c1) + sh.es_block + D;

@@ -68,7 +68,9 @@ def test_screen_equals_per_channel_kernel(lib, oracle, n, order, nfit):
     assert_same(s, p, data, loose=order >= 6)
     # the edge-case rows (constant data, exactly K valid channels, ...) are handed over by design;
     # ordinary rows almost never are
-    assert 0 <= handed <= 16 + rows // 50, handed
+    # (orders 6 and 7: the monomial coefficients are large, the FP64 slack terms of the bounds grow
+    # with their squares and more rows are handed over)
+    assert 0 <= handed <= 16 + rows // (10 if order >= 6 else 50), handed
     if order <= 5:
         o = oracle.lsqfit_polynomial_batch(order, data, mask, 3.0, nfit, want_best_fit=True)
         reported = compare_fit(s, o, data, 3.0, poly_rescale_n=n)
