@@ -414,8 +414,8 @@ def run_ours(args) -> None:
     if world > 1:
         import torch.distributed as dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: one JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            del os.environ["NCCL_DEBUG"]  # keep NCCL's version banner off stdout: one JSON line only
         dist_mod.init_process_group("nccl", device_id=device)
         dist = dist_mod
 
