@@ -414,9 +414,19 @@ def run_ours(args) -> None:
     if world > 1:
         import torch.distributed as dist_mod
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
-            del os.environ["NCCL_DEBUG"]  # keep NCCL's version banner off stdout: one JSON line only
-        dist_mod.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner on stdout when the first communicator is created: send
+        # file descriptor 1 to stderr meanwhile, so that stdout carries the one JSON line only
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist_mod.init_process_group("nccl", device_id=device)
+            dist_mod.barrier()
+            torch.cuda.synchronize(device)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
         dist = dist_mod
 
     lib = SakuraLib()
