@@ -151,3 +151,35 @@ def test_screen_large_device_batches(lib, rows, n, nfit, clip):
     assert torch.equal(a["status"], c["status"])
     rel = ((a["rms"] - c["rms"]).abs() / c["rms"].abs()).max().item()
     assert rel <= 1e-6, rel
+
+
+def test_screen_non_finite_and_degenerate_rows(lib):
+    """NaN / Inf in a valid channel, constant rows, rows of zeros, huge and denormal values: the
+    screening kernel must hand such rows over (or decide them identically); whatever the
+    per-channel kernel produces for them is what comes out."""
+    data, mask = synth.make_spectra(96, 4096, seed=21)
+    data[3, 100] = np.nan
+    mask[3, 100] = True
+    data[5, 2000] = np.inf
+    mask[5, 2000] = True
+    data[7, 17] = -np.inf
+    mask[7, 17] = True
+    data[9] = 2.5
+    data[11] = 0.0
+    data[13] *= np.float32(1e30)
+    data[15] *= np.float32(1e-42)
+    data[17, ::2] = 0.0                       # half of the row exactly on the model
+    data[19] = np.arange(4096, dtype=np.float32)  # exactly polynomial: residual is rounding noise
+    s, kernel, handed = fit(lib, 5, data, mask, 3.0, 5, True, want_best_fit=True)
+    assert kernel == "poly_screen"
+    p, _, _ = fit(lib, 5, data, mask, 3.0, 5, False, want_best_fit=True)
+    assert np.array_equal(s["status"], p["status"])
+    assert np.array_equal(s["lsqfit_status"], p["lsqfit_status"])
+    assert np.array_equal(s["final_mask"], p["final_mask"])
+    special = [3, 5, 7, 9, 11, 13, 15, 19]
+    for key in ("rms", "residual", "coeff", "best_fit"):
+        a, b = s[key][special], p[key][special]
+        assert np.array_equal(np.isnan(a), np.isnan(b)), key
+        with np.errstate(over="ignore"):
+            assert np.array_equal(np.nan_to_num(a).view(np.uint8), np.nan_to_num(b).view(np.uint8)), key
+    assert handed >= len(special) - 1
