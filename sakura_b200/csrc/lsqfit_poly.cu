@@ -948,8 +948,9 @@ namespace {
 cudaError_t LaunchPolyFitKernel(PolyFitParams const &p, int num_sms, cudaStream_t stream);
 
 bool ScreeningEnabled(int num_fitting_max) {
-	// Screening pays from the fourth fit on (measured on B200, 4096 channels, order 5: 7.1e7 against
-	// 7.8e7 spectra/s at one fit, 3.5e7 / 3.6e7 at three, 2.7e7 / 2.6e7 at five).
+	// Screening pays from the third fit on (measured on B200, 4096 channels, order 5: 7.2e7 against
+	// 7.9e7 spectra/s at one fit, 4.85e7 / 5.0e7 at two, 3.73e7 / 3.70e7 at three, 3.16e7 / 3.0e7 at
+	// four, 2.88e7 / 2.66e7 at five).
 	// SAKURA_B200_POLY_SCREEN=0 runs every row through PolyFitKernel, =1 screens whatever the number
 	// of fits (the parity tests compare the two kernels); read per call so that a test can switch
 	// within one process.
@@ -957,7 +958,7 @@ bool ScreeningEnabled(int num_fitting_max) {
 	if (e != nullptr && (e[0] == '0' || e[0] == '1')) {
 		return e[0] == '1';
 	}
-	return num_fitting_max >= 4;
+	return num_fitting_max >= 3;
 }
 
 } // namespace
