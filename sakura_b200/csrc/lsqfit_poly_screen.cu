@@ -11,8 +11,9 @@
 //     bound on what the reference's float residuals would add to them. That gives an INTERVAL for
 //     each of the two float clip thresholds of baseline.cc:1200-1207 (usually 0-2 ulp wide);
 //   * every channel keeps an approximate float residual r~ in shared memory with a known error
-//     bound. A "refresh" pass recomputes it from the current model in FP32 (local Horner form
-//     around the thread's first channel, the constant term split in two floats); a "stale" pass
+//     bound. A "refresh" pass recomputes it from the current model in FP32 (local quadratic
+//     around the thread's first channel, the constant term split in two floats, the terms of
+//     order >= 3 -- ~1e-5 of the model's variation over 32 channels -- in the band); a "stale" pass
 //     reuses the stored value and widens the band by a bound on how far the model has moved since
 //     (maximum over 32 Chebyshev nodes, Ehlich-Zeller inequality). A channel whose r~ lies inside
 //     both thresholds by more than the band is provably not clipped and costs ~3-10 FP32
@@ -26,12 +27,14 @@
 //   * the last fit's residual, best-fit model and statistics (the reported rms) are evaluated
 //     exactly, once, in FP64 as PolyFitKernel's pass A does.
 //
-// Layout: one CTA of NT threads per spectrum of n = 32 NT channels, persistent grid. The row is
-// loaded with coalesced 128-bit loads (thread t: float4 groups t, t+NT, ...; the data moments are
-// accumulated in that interleaved order, which spreads flagged runs evenly over the lanes), then
-// every thread owns 32 CONSECUTIVE channels (read from shared memory rows padded to 36 floats:
-// conflict-free 128-bit accesses) so that the local polynomial variable is a compile-time constant
-// 0..31 and FP32 accuracy suffices for the screening value.
+// Layout: one CTA of NT threads per spectrum of n = 32 NT channels, persistent grid, 6 CTAs per SM.
+// The row is loaded with coalesced 128-bit loads (thread t: float4 groups t, t+NT, ...; the power
+// sums of the flagged channels are taken in that interleaved ownership, which spreads flagged runs
+// evenly over the lanes), then every thread owns 32 CONSECUTIVE channels (XOR-swizzled rows in
+// shared memory: conflict-free 128-bit accesses in both patterns) so that the local polynomial
+// variable runs over 0..31 and FP32 accuracy suffices for the screening value. One warp per row
+// (rotating) runs the serial part of an iteration -- downdate, solve, bounds, thresholds -- between
+// two block barriers; everything per channel is a rolled loop (instruction-cache footprint).
 #include "lsqfit_poly.cuh"
 #include "device_common.cuh"
 #include "poly_device.cuh"
