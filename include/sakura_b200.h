@@ -363,6 +363,42 @@ sakura_Status sakura_Uint32ToBoolDevice(size_t num_data, uint32_t const d_data[]
 sakura_Status sakura_InvertBoolDevice(size_t num_data, bool const d_data[], bool const d_and_with[],
 		bool d_result[], void *cuda_stream) SAKURA_B200_NOEXCEPT;
 
+/* ---- bit operations with an edit mask: from a bool mask back to flag bytes ----------------
+ * sakura.h:693-956 / bit_operation.cc: result[i] = edit_mask[i] ? (data[i] OP bit_mask) : data[i];
+ * same names, signatures and argument rules (NULL / unaligned => kInvalidArgument); `result` may be
+ * `data` (bench/e2eReduce/src/main.cc:59-78 ORs bit 7 into the flag bytes where the mask says so). */
+sakura_Status sakura_OperateBitwiseAndUint8(uint8_t bit_mask, size_t num_data, uint8_t const data[],
+		bool const edit_mask[], uint8_t result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_OperateBitwiseAndUint32(uint32_t bit_mask, size_t num_data, uint32_t const data[],
+		bool const edit_mask[], uint32_t result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_OperateBitwiseConverseNonImplicationUint8(uint8_t bit_mask, size_t num_data,
+		uint8_t const data[], bool const edit_mask[], uint8_t result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_OperateBitwiseConverseNonImplicationUint32(uint32_t bit_mask, size_t num_data,
+		uint32_t const data[], bool const edit_mask[], uint32_t result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_OperateBitwiseImplicationUint8(uint8_t bit_mask, size_t num_data, uint8_t const data[],
+		bool const edit_mask[], uint8_t result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_OperateBitwiseImplicationUint32(uint32_t bit_mask, size_t num_data,
+		uint32_t const data[], bool const edit_mask[], uint32_t result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_OperateBitwiseNotUint8(size_t num_data, uint8_t const data[], bool const edit_mask[],
+		uint8_t result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_OperateBitwiseNotUint32(size_t num_data, uint32_t const data[], bool const edit_mask[],
+		uint32_t result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_OperateBitwiseOrUint8(uint8_t bit_mask, size_t num_data, uint8_t const data[],
+		bool const edit_mask[], uint8_t result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_OperateBitwiseOrUint32(uint32_t bit_mask, size_t num_data, uint32_t const data[],
+		bool const edit_mask[], uint32_t result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_OperateBitwiseXorUint8(uint8_t bit_mask, size_t num_data, uint8_t const data[],
+		bool const edit_mask[], uint8_t result[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_OperateBitwiseXorUint32(uint32_t bit_mask, size_t num_data, uint32_t const data[],
+		bool const edit_mask[], uint32_t result[]) SAKURA_B200_NOEXCEPT;
+/** NEW. Device arrays; `operation`: 0 And, 1 ConverseNonImplication, 2 Implication, 3 Not, 4 Or, 5 Xor. */
+sakura_Status sakura_OperateBitwiseUint8Device(int operation, uint8_t bit_mask, size_t num_data,
+		uint8_t const d_data[], bool const d_edit_mask[], uint8_t d_result[], void *cuda_stream)
+		SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_OperateBitwiseUint32Device(int operation, uint32_t bit_mask, size_t num_data,
+		uint32_t const d_data[], bool const d_edit_mask[], uint32_t d_result[], void *cuda_stream)
+		SAKURA_B200_NOEXCEPT;
+
 /* ---- interpolation of many arrays at once ------------------------------
  * sakura.h:961-1096 / interpolation.cc. Nearest and linear interpolation (and polynomial of order
  * 0, which the reference maps to nearest) with masked base data, no extrapolation, ascending or

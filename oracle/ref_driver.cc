@@ -382,6 +382,38 @@ int ref_bool_filter(int op, int type, size_t num_data, void const *data, size_t 
 	}
 }
 
+/* bit_operation.cc: op 0 And, 1 ConverseNonImplication, 2 Implication, 3 Not, 4 Or, 5 Xor */
+int ref_bit_operation(int op, int wide, uint32_t bit_mask, size_t num_data, void const *data,
+		bool const *edit_mask, void *result) {
+	uint8_t const *d8 = static_cast<uint8_t const *>(data);
+	uint32_t const *d32 = static_cast<uint32_t const *>(data);
+	uint8_t *r8 = static_cast<uint8_t *>(result);
+	uint32_t *r32 = static_cast<uint32_t *>(result);
+	uint8_t const m8 = static_cast<uint8_t>(bit_mask);
+	switch (op) {
+	case 0:
+		return wide ? sakura_OperateBitwiseAndUint32(bit_mask, num_data, d32, edit_mask, r32)
+				: sakura_OperateBitwiseAndUint8(m8, num_data, d8, edit_mask, r8);
+	case 1:
+		return wide ? sakura_OperateBitwiseConverseNonImplicationUint32(bit_mask, num_data, d32, edit_mask, r32)
+				: sakura_OperateBitwiseConverseNonImplicationUint8(m8, num_data, d8, edit_mask, r8);
+	case 2:
+		return wide ? sakura_OperateBitwiseImplicationUint32(bit_mask, num_data, d32, edit_mask, r32)
+				: sakura_OperateBitwiseImplicationUint8(m8, num_data, d8, edit_mask, r8);
+	case 3:
+		return wide ? sakura_OperateBitwiseNotUint32(num_data, d32, edit_mask, r32)
+				: sakura_OperateBitwiseNotUint8(num_data, d8, edit_mask, r8);
+	case 4:
+		return wide ? sakura_OperateBitwiseOrUint32(bit_mask, num_data, d32, edit_mask, r32)
+				: sakura_OperateBitwiseOrUint8(m8, num_data, d8, edit_mask, r8);
+	case 5:
+		return wide ? sakura_OperateBitwiseXorUint32(bit_mask, num_data, d32, edit_mask, r32)
+				: sakura_OperateBitwiseXorUint8(m8, num_data, d8, edit_mask, r8);
+	default:
+		return -1;
+	}
+}
+
 /* sakura_InterpolateXAxisFloat (y_axis == 0) / sakura_InterpolateYAxisFloat (y_axis != 0). */
 int ref_interpolate(int y_axis, int method, int polynomial_order, size_t num_base,
 		double const *base_position, size_t num_array, float const *base_data, bool const *base_mask,

@@ -82,6 +82,8 @@ class Oracle:
         L.ref_calibrate_batch.restype = i32
         L.ref_bool_filter.argtypes = [i32, i32, sz, vp, sz, vp, vp, C.c_uint32, vp]
         L.ref_bool_filter.restype = i32
+        L.ref_bit_operation.argtypes = [i32, i32, C.c_uint32, sz, vp, vp, vp]
+        L.ref_bit_operation.restype = i32
         L.ref_interpolate.argtypes = [i32, i32, i32, sz, vp, sz, vp, vp, sz, vp, vp, vp]
         L.ref_interpolate.restype = i32
         for name in ("ref_lsqfit_polynomial_batch", "ref_lsqfit_cubicspline_batch",
@@ -220,6 +222,22 @@ class Oracle:
         st = self.lib.ref_bool_filter(self.FILTER_OPS[op], type_id, n, _ptr(data), nc, _ptr(lo),
                                       _ptr(hi), bits, _ptr(result))
         return result, int(st)
+
+    BIT_OPS = {"and": 0, "converse_nonimplication": 1, "implication": 2, "not": 3, "or": 4, "xor": 5}
+
+    def bit_operation(self, op: str, bit_mask: int, data, edit_mask):
+        """sakura_OperateBitwise<Op>{Uint8,Uint32} selected by `op` and the dtype of `data`.
+        Returns (result, status)."""
+        data = np.asarray(data)
+        wide = 1 if data.dtype == np.uint32 else 0
+        n = data.size
+        d = aligned_copy(data) if n else aligned_empty(8, data.dtype)
+        m = aligned_copy(np.asarray(edit_mask).view(np.uint8)) if n else aligned_empty(8, np.uint8)
+        out = aligned_empty((max(n, 1),), data.dtype)[:n]
+        out[...] = 0
+        st = self.lib.ref_bit_operation(self.BIT_OPS[op], wide, int(bit_mask) & 0xffffffff, n, _ptr(d), _ptr(m),
+                                        _ptr(out) if n else _ptr(aligned_empty(8, data.dtype)))
+        return out, int(st)
 
     def interpolate(self, axis: str, method: int, base_position, base_data, base_mask,
                     interpolated_position, polynomial_order: int = 0, prefill: float = np.nan):

@@ -1246,6 +1246,37 @@ int ref_bool_filter(int op, int type, size_t num_data, void const *data, size_t 
 	return kStatusOK;
 }
 
+/* ------------------------------------------------------------------ bit operations
+ * bit_operation.cc:60-190, the expressions as written there: x = (T) mask - 1 from the edit-mask
+ * byte; arguments NULL or not 32-byte aligned -> kInvalidArgument (:41-52). */
+int ref_bit_operation(int op, int wide, uint32_t bit_mask, size_t num_data, void const *data,
+		unsigned char const *edit_mask, void *result) {
+	if (data == NULL || result == NULL || edit_mask == NULL || ((uintptr_t) data % 32) != 0
+			|| ((uintptr_t) result % 32) != 0 || ((uintptr_t) edit_mask % 32) != 0) {
+		return kStatusInvalidArgument;
+	}
+	for (size_t i = 0; i < num_data; ++i) {
+		uint32_t const d = wide ? ((uint32_t const *) data)[i] : ((unsigned char const *) data)[i];
+		uint32_t const x = (uint32_t) edit_mask[i] - 1u;
+		uint32_t const nx = ~x;
+		uint32_t r;
+		switch (op) {
+		case 0: r = d & (bit_mask | x); break;
+		case 1: r = (d ^ nx) & (bit_mask | x); break;
+		case 2: r = (d ^ nx) | (bit_mask & nx); break;
+		case 3: r = d ^ nx; break;
+		case 4: r = d | (bit_mask & nx); break;
+		default: r = d ^ (bit_mask & nx); break;
+		}
+		if (wide) {
+			((uint32_t *) result)[i] = r;
+		} else {
+			((unsigned char *) result)[i] = (unsigned char) r;
+		}
+	}
+	return kStatusOK;
+}
+
 /* ------------------------------------------------------------------ interpolation
  * interpolation.cc, nearest and linear (polynomial of order 0 is nearest, :1419-1422). For every
  * array: the valid base points are gathered in ascending order of position (:905-922); no valid

@@ -181,6 +181,13 @@ class SakuraLib:
         for name in ("sakura_SetTrueIfInRangesFloatDevice", "sakura_SetTrueIfInRangesIntDevice",
                      "sakura_SetTrueIfComparesFloatDevice", "sakura_SetTrueIfComparesIntDevice"):
             getattr(L, name).restype = C.c_int
+        for op in ("And", "ConverseNonImplication", "Implication", "Or", "Xor"):
+            getattr(L, f"sakura_OperateBitwise{op}Uint8").argtypes = [C.c_uint8, sz, vp, vp, vp]
+            getattr(L, f"sakura_OperateBitwise{op}Uint32").argtypes = [C.c_uint32, sz, vp, vp, vp]
+        L.sakura_OperateBitwiseNotUint8.argtypes = [sz, vp, vp, vp]
+        L.sakura_OperateBitwiseNotUint32.argtypes = [sz, vp, vp, vp]
+        L.sakura_OperateBitwiseUint8Device.argtypes = [C.c_int, C.c_uint8, sz, vp, vp, vp, vp]
+        L.sakura_OperateBitwiseUint32Device.argtypes = [C.c_int, C.c_uint32, sz, vp, vp, vp, vp]
         for name in ("sakura_InterpolateXAxisFloat", "sakura_InterpolateYAxisFloat"):
             getattr(L, name).argtypes = [C.c_int, C.c_uint8, sz, vp, sz, vp, vp, sz, vp, vp, vp]
             getattr(L, name).restype = C.c_int
@@ -385,6 +392,25 @@ class SakuraLib:
         else:
             raise ValueError(op)
         return result[:n], int(st)
+
+    # ------------------------------------------------------------------ bit operations
+    _BIT_NAMES = {"and": "And", "converse_nonimplication": "ConverseNonImplication",
+                  "implication": "Implication", "not": "Not", "or": "Or", "xor": "Xor"}
+
+    def bit_operation(self, op: str, bit_mask: int, data, edit_mask, in_place: bool = False):
+        """sakura_OperateBitwise<Op>{Uint8,Uint32} on host arrays; returns (result, status)."""
+        data = np.asarray(data)
+        suffix = "Uint32" if data.dtype == np.uint32 else "Uint8"
+        n = data.size
+        d = aligned_copy(data) if n else aligned_empty(8, data.dtype)
+        m = aligned_copy(np.asarray(edit_mask).view(np.uint8)) if n else aligned_empty(8, np.uint8)
+        out = d if in_place else aligned_empty((max(n, 1),), data.dtype)
+        fn = getattr(self.lib, f"sakura_OperateBitwise{self._BIT_NAMES[op]}{suffix}")
+        if op == "not":
+            st = fn(n, _ptr(d), _ptr(m), _ptr(out))
+        else:
+            st = fn(int(bit_mask), n, _ptr(d), _ptr(m), _ptr(out))
+        return out[:n], int(st)
 
     # ------------------------------------------------------------------ interpolation
     def interpolate(self, axis: str, method: int, base_position, base_data, base_mask,

@@ -257,6 +257,89 @@ cudaError_t Dispatch32(BoolFilterParams const &p, bool vector, unsigned grid, cu
 
 } // namespace
 
+// bit_operation.cc:60-190, the expressions as written there (x derived from the edit-mask byte)
+template<typename T>
+__device__ __forceinline__ T BitOperate(int op, T d, T bm, uint8_t mask) {
+	T const x = static_cast<T>(static_cast<T>(mask) - static_cast<T>(1));
+	T const nx = static_cast<T>(~x);
+	switch (op) {
+	case kBitAnd:
+		return static_cast<T>(d & (bm | x));
+	case kBitConverseNonImplication:
+		return static_cast<T>((d ^ nx) & (bm | x));
+	case kBitImplication:
+		return static_cast<T>((d ^ nx) | (bm & nx));
+	case kBitNot:
+		return static_cast<T>(d ^ nx);
+	case kBitOr:
+		return static_cast<T>(d | (bm & nx));
+	default:
+		return static_cast<T>(d ^ (bm & nx));
+	}
+}
+
+template<typename T>
+__global__ void __launch_bounds__(256)
+BitOperationKernel(BitOperationParams const p) {
+	size_t const stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+	T const *in = static_cast<T const *>(p.data);
+	T *out = static_cast<T *>(p.result);
+	T const bm = static_cast<T>(p.bit_mask);
+	int const op = p.op;
+	// four elements per thread when everything is 4-element aligned (uint8: one word each of data,
+	// mask and result; uint32: 128-bit data accesses)
+	bool const vec = (reinterpret_cast<uintptr_t>(p.data) % (4 * sizeof(T))) == 0
+			&& (reinterpret_cast<uintptr_t>(p.result) % (4 * sizeof(T))) == 0
+			&& (reinterpret_cast<uintptr_t>(p.edit_mask) % 4) == 0;
+	size_t const n4 = vec ? p.num_data / 4 : 0;
+	for (size_t g = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; g < n4; g += stride) {
+		uint32_t const m = reinterpret_cast<uint32_t const *>(p.edit_mask)[g];
+		T v[4];
+		if (sizeof(T) == 1) {
+			uint32_t const w = reinterpret_cast<uint32_t const *>(in)[g];
+			uint32_t r = 0u;
+#pragma unroll
+			for (int e = 0; e < 4; ++e) {
+				r |= static_cast<uint32_t>(BitOperate<T>(op, static_cast<T>(w >> (8 * e)), bm,
+						static_cast<uint8_t>(m >> (8 * e)))) << (8 * e);
+			}
+			reinterpret_cast<uint32_t *>(out)[g] = r;
+		} else {
+			uint4 const w = reinterpret_cast<uint4 const *>(in)[g];
+			v[0] = static_cast<T>(w.x);
+			v[1] = static_cast<T>(w.y);
+			v[2] = static_cast<T>(w.z);
+			v[3] = static_cast<T>(w.w);
+#pragma unroll
+			for (int e = 0; e < 4; ++e) {
+				v[e] = BitOperate<T>(op, v[e], bm, static_cast<uint8_t>(m >> (8 * e)));
+			}
+			reinterpret_cast<uint4 *>(out)[g] = make_uint4(v[0], v[1], v[2], v[3]);
+		}
+	}
+	for (size_t i = n4 * 4 + static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < p.num_data;
+			i += stride) {
+		out[i] = BitOperate<T>(op, in[i], bm, p.edit_mask[i]);
+	}
+}
+
+cudaError_t LaunchBitOperation(BitOperationParams const &p, int num_sms, cudaStream_t stream) {
+	if (p.num_data == 0) {
+		return cudaSuccess;
+	}
+	size_t blocks = (p.num_data / 4 + 255) / 256 + 1;
+	size_t const cap = static_cast<size_t>(num_sms) * 16;
+	if (blocks > cap) {
+		blocks = cap;
+	}
+	if (p.wide) {
+		BitOperationKernel<uint32_t><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
+	} else {
+		BitOperationKernel<uint8_t><<<static_cast<unsigned>(blocks), 256, 0, stream>>>(p);
+	}
+	return cudaGetLastError();
+}
+
 cudaError_t LaunchBoolFilter(BoolFilterParams const &p, int num_sms, cudaStream_t stream) {
 	if (p.num_data == 0) {
 		return cudaSuccess;

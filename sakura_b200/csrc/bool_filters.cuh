@@ -52,6 +52,30 @@ struct BoolFilterParams {
 
 cudaError_t LaunchBoolFilter(BoolFilterParams const &p, int num_sms, cudaStream_t stream);
 
+// ---- bit operations with an edit mask (libsakura/src/bit_operation.cc): the way back from a bool
+// mask to the flag bytes of a data set (bench/e2eReduce/src/main.cc:59-78)
+enum BitOp : int {
+	kBitAnd = 0, // data & bit_mask
+	kBitConverseNonImplication = 1, // ~data & bit_mask
+	kBitImplication = 2, // ~data | bit_mask
+	kBitNot = 3, // ~data
+	kBitOr = 4, // data | bit_mask
+	kBitXor = 5 // data ^ bit_mask
+};
+
+struct BitOperationParams {
+	int op;
+	int wide; // 1: uint32 elements, 0: uint8
+	uint32_t bit_mask;
+	size_t num_data;
+	void const *data;
+	uint8_t const *edit_mask; // elements whose byte is 0 keep their value (any other value: as written
+	                          // in bit_operation.cc, "mask - 1" in the element type)
+	void *result; // may alias data
+};
+
+cudaError_t LaunchBitOperation(BitOperationParams const &p, int num_sms, cudaStream_t stream);
+
 } // namespace sakura_b200
 
 #endif

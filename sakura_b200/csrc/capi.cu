@@ -1631,6 +1631,120 @@ sakura_Status sakura_InvertBoolDevice(size_t num_data, bool const d_data[], bool
 			d_and_with, d_result, cuda_stream);
 }
 
+// ---------------------------------------------------------------- bit operations (bit_operation.cc)
+namespace {
+
+sakura_Status BitOperationHost(int op, int wide, uint32_t bit_mask, size_t num_data, void const *data,
+		bool const *edit_mask, void *result) {
+	// bit_operation.cc:41-52: NULL or unaligned data, result or edit_mask
+	CHECK_ARGS(data != nullptr && result != nullptr && edit_mask != nullptr);
+	CHECK_ARGS(sakura_IsAligned(data) && sakura_IsAligned(result) && sakura_IsAligned(edit_mask));
+	if (num_data == 0) {
+		return sakura_Status_kOK;
+	}
+	DeviceInfo info;
+	sakura_Status const st = CurrentDevice(&info);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	size_t const bytes = num_data * (wide ? 4 : 1);
+	static thread_local DeviceBuffer d_in, d_mask, d_out;
+	CUDA_TRY(d_in.Reserve(bytes));
+	CUDA_TRY(d_mask.Reserve(num_data));
+	CUDA_TRY(d_out.Reserve(bytes));
+	cudaStream_t const stream = 0;
+	CUDA_TRY(cudaMemcpyAsync(d_in.ptr, data, bytes, cudaMemcpyHostToDevice, stream));
+	CUDA_TRY(cudaMemcpyAsync(d_mask.ptr, edit_mask, num_data, cudaMemcpyHostToDevice, stream));
+	BitOperationParams p;
+	memset(&p, 0, sizeof(p));
+	p.op = op;
+	p.wide = wide;
+	p.bit_mask = bit_mask;
+	p.num_data = num_data;
+	p.data = d_in.ptr;
+	p.edit_mask = d_mask.As<uint8_t>();
+	p.result = d_out.ptr;
+	cudaError_t const e = LaunchBitOperation(p, info.num_sms, stream);
+	g_launch_count += 1;
+	g_last_kernel = "bit_operation";
+	if (e != cudaSuccess) {
+		SetError("LaunchBitOperation", e);
+		return sakura_Status_kUnknownError;
+	}
+	CUDA_TRY(cudaMemcpyAsync(result, d_out.ptr, bytes, cudaMemcpyDeviceToHost, stream)); // result may alias data
+	CUDA_TRY(cudaStreamSynchronize(stream));
+	return sakura_Status_kOK;
+}
+
+sakura_Status BitOperationDevice(int op, int wide, uint32_t bit_mask, size_t num_data, void const *d_data,
+		bool const *d_edit_mask, void *d_result, void *cuda_stream) {
+	CHECK_ARGS(op >= kBitAnd && op <= kBitXor);
+	CHECK_ARGS(d_data != nullptr && d_result != nullptr && d_edit_mask != nullptr);
+	if (num_data == 0) {
+		return sakura_Status_kOK;
+	}
+	DeviceInfo info;
+	sakura_Status const st = CurrentDevice(&info);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	BitOperationParams p;
+	memset(&p, 0, sizeof(p));
+	p.op = op;
+	p.wide = wide;
+	p.bit_mask = bit_mask;
+	p.num_data = num_data;
+	p.data = d_data;
+	p.edit_mask = reinterpret_cast<uint8_t const *>(d_edit_mask);
+	p.result = d_result;
+	cudaError_t const e = LaunchBitOperation(p, info.num_sms, static_cast<cudaStream_t>(cuda_stream));
+	g_launch_count += 1;
+	g_last_kernel = "bit_operation";
+	if (e != cudaSuccess) {
+		SetError("LaunchBitOperation", e);
+		return sakura_Status_kUnknownError;
+	}
+	return sakura_Status_kOK;
+}
+
+} // namespace
+
+#define SAKURA_B200_BITOP(NAME, OP) \
+sakura_Status sakura_OperateBitwise##NAME##Uint8(uint8_t bit_mask, size_t num_data, uint8_t const data[], \
+		bool const edit_mask[], uint8_t result[]) noexcept { \
+	return BitOperationHost(OP, 0, bit_mask, num_data, data, edit_mask, result); \
+} \
+sakura_Status sakura_OperateBitwise##NAME##Uint32(uint32_t bit_mask, size_t num_data, uint32_t const data[], \
+		bool const edit_mask[], uint32_t result[]) noexcept { \
+	return BitOperationHost(OP, 1, bit_mask, num_data, data, edit_mask, result); \
+}
+SAKURA_B200_BITOP(And, kBitAnd)
+SAKURA_B200_BITOP(ConverseNonImplication, kBitConverseNonImplication)
+SAKURA_B200_BITOP(Implication, kBitImplication)
+SAKURA_B200_BITOP(Or, kBitOr)
+SAKURA_B200_BITOP(Xor, kBitXor)
+#undef SAKURA_B200_BITOP
+
+sakura_Status sakura_OperateBitwiseNotUint8(size_t num_data, uint8_t const data[], bool const edit_mask[],
+		uint8_t result[]) noexcept {
+	return BitOperationHost(kBitNot, 0, 0u, num_data, data, edit_mask, result);
+}
+
+sakura_Status sakura_OperateBitwiseNotUint32(size_t num_data, uint32_t const data[], bool const edit_mask[],
+		uint32_t result[]) noexcept {
+	return BitOperationHost(kBitNot, 1, 0u, num_data, data, edit_mask, result);
+}
+
+sakura_Status sakura_OperateBitwiseUint8Device(int operation, uint8_t bit_mask, size_t num_data,
+		uint8_t const d_data[], bool const d_edit_mask[], uint8_t d_result[], void *cuda_stream) noexcept {
+	return BitOperationDevice(operation, 0, bit_mask, num_data, d_data, d_edit_mask, d_result, cuda_stream);
+}
+
+sakura_Status sakura_OperateBitwiseUint32Device(int operation, uint32_t bit_mask, size_t num_data,
+		uint32_t const d_data[], bool const d_edit_mask[], uint32_t d_result[], void *cuda_stream) noexcept {
+	return BitOperationDevice(operation, 1, bit_mask, num_data, d_data, d_edit_mask, d_result, cuda_stream);
+}
+
 // ---------------------------------------------------------------- interpolation
 namespace {
 
