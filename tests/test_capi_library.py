@@ -16,6 +16,7 @@ from sakura_b200.capi import (ALIGNMENT, LSQFIT_NG, LSQFIT_TYPE_CHEBYSHEV, LSQFI
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 HEADER = os.path.join(ROOT, "include", "sakura_b200.h")
 IA = STATUS_INVALID_ARGUMENT
+OK = 0
 
 
 def declared_symbols():
@@ -211,4 +212,52 @@ def test_statistics_and_blocks_invalid_arguments(hostlib):
     sol = L.sakura_SolveSimultaneousEquationsByLUDouble
     assert sol(2, None, b.ctypes.data, G.ctypes.data) == IA
     assert sol(2, G.ctypes.data, b.ctypes.data, b.ctypes.data) == IA  # in_vector == out
+    assert hostlib.kernel_launch_count() == 0
+
+
+def test_mask_chain_invalid_arguments(hostlib):
+    """Mask builders, bit operations, interpolation: the reference's argument rules are applied
+    before anything touches the GPU (bool_filter_collection.cc:535-600, bit_operation.cc:41-52,
+    interpolation.cc:1288-1340); zero-length calls are kOK without a launch."""
+    L = hostlib.lib
+    f = aligned_copy(np.zeros(16, dtype=np.float32))
+    i = aligned_copy(np.zeros(16, dtype=np.int32))
+    u8 = aligned_copy(np.zeros(16, dtype=np.uint8))
+    r = aligned_empty(16, np.bool_)
+    lo = aligned_copy(np.zeros(2, dtype=np.float32))
+    hi = aligned_copy(np.ones(2, dtype=np.float32))
+    p = lambda a, off=0: C.c_void_p(a.ctypes.data + off)
+    for fn in (L.sakura_SetTrueIfInRangesInclusiveFloat, L.sakura_SetTrueIfInRangesExclusiveFloat):
+        assert fn(16, None, 2, p(lo), p(hi), p(r)) == IA
+        assert fn(16, p(f, 4), 2, p(lo), p(hi), p(r)) == IA
+        assert fn(16, p(f), 2, None, p(hi), p(r)) == IA
+        assert fn(16, p(f), 0, None, None, p(r)) == IA
+        assert fn(16, p(f), 2, p(lo), p(hi, 4), p(r)) == IA
+        assert fn(16, p(f), 2, p(lo), p(hi), None) == IA
+        assert fn(0, p(f), 2, p(lo), p(hi), p(r)) == OK
+    assert L.sakura_SetTrueIfLessThanInt(16, p(i, 4), 0, p(r)) == IA
+    assert L.sakura_SetTrueIfGreaterThanOrEqualsFloat(16, p(f), 0.0, None) == IA
+    assert L.sakura_SetFalseIfNanOrInfFloat(16, None, p(r)) == IA
+    assert L.sakura_Uint8ToBool(16, p(u8, 1), p(r)) == IA
+    assert L.sakura_Uint32ToBool(16, None, p(r)) == IA
+    assert L.sakura_InvertBool(16, p(r), p(r, 1)) == IA
+    assert L.sakura_InvertBool(0, p(r), p(r)) == OK
+    assert L.sakura_OperateBitwiseOrUint8(128, 16, None, p(r), p(u8)) == IA
+    assert L.sakura_OperateBitwiseAndUint32(1, 4, p(i), p(r, 1), p(i)) == IA
+    assert L.sakura_OperateBitwiseNotUint8(16, p(u8), p(r), None) == IA
+    assert L.sakura_OperateBitwiseXorUint8(1, 0, p(u8), p(r), p(u8)) == OK
+    xb = aligned_copy(np.array([0.0, 1.0]))
+    yb = aligned_copy(np.zeros((2, 4), dtype=np.float32))
+    mb = aligned_copy(np.ones((2, 4), dtype=np.bool_))
+    xi = aligned_copy(np.array([0.5]))
+    out = aligned_empty((1, 4), np.float32)
+    om = aligned_empty((1, 4), np.bool_)
+    for fn in (L.sakura_InterpolateXAxisFloat, L.sakura_InterpolateYAxisFloat):
+        assert fn(1, 0, 0, p(xb), 4, p(yb), p(mb), 1, p(xi), p(out), p(om)) == IA
+        assert fn(1, 0, 2, p(xb), 4, p(yb), p(mb), 0, p(xi), p(out), p(om)) == OK
+        assert fn(1, 0, 2, p(xb), 0, p(yb), p(mb), 1, p(xi), p(out), p(om)) == OK
+        assert fn(1, 0, 2, p(xb, 8), 4, p(yb), p(mb), 1, p(xi), p(out), p(om)) == IA
+        assert fn(1, 0, 2, p(xb), 4, None, p(mb), 1, p(xi), p(out), p(om)) == IA
+        assert fn(3, 0, 2, p(xb), 4, p(yb), p(mb), 1, p(xi), p(out), p(om)) == IA   # spline: not implemented
+        assert fn(7, 0, 2, p(xb), 4, p(yb), p(mb), 1, p(xi), p(out), p(om)) == IA   # no such method
     assert hostlib.kernel_launch_count() == 0
