@@ -983,12 +983,13 @@ template<int K, int NT, bool CAL>
 cudaError_t LaunchScreenKNC(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
 	constexpr size_t smem = ScreenSharedBytes<K, NT>();
 	static int per_sm = 0;
+	// (per device: a process may drive several GPUs)
+	cudaError_t err = cudaFuncSetAttribute(PolyScreenFitKernel<K, NT, CAL>,
+			cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+	if (err != cudaSuccess) {
+		return err;
+	}
 	if (per_sm == 0) {
-		cudaError_t err = cudaFuncSetAttribute(PolyScreenFitKernel<K, NT, CAL>,
-				cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-		if (err != cudaSuccess) {
-			return err;
-		}
 		int v = 0;
 		err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&v, PolyScreenFitKernel<K, NT, CAL>, NT, smem);
 		if (err != cudaSuccess) {
