@@ -143,6 +143,20 @@ __device__ __forceinline__ void or_if_outside(uint32_t &word, float r, float lo,
 			"@p or.b32 %0, %0, %4;\n\t}" : "+r"(word) : "f"(r), "f"(lo), "f"(hi), "r"(bit));
 }
 
+/** pw[k] = x^k, k < N, as a product tree (x^k = x^(k/2) x^(k - k/2)): N - 2 multiplications like the
+ *  running product, but a dependent chain of log2 N instead of N of them (FP64 latency is 8 cycles) */
+template<int N>
+__device__ __forceinline__ void PowerTree(double x, double (&pw)[N]) {
+	pw[0] = 1.0;
+	if (N > 1) {
+		pw[1] = x;
+	}
+#pragma unroll
+	for (int k = 2; k < N; ++k) {
+		pw[k] = pw[k >> 1] * pw[k - (k >> 1)];
+	}
+}
+
 // Power sums sum x^k (k < 2K-1) over the channels whose bit is set in `bits`, in the INTERLEAVED
 // ownership of the load pass (bit 4j+e of thread t <-> channel 4(t + NT j) + e); per-lane partials
 // are transposed through `scratch` (NS rows of 33 doubles per warp) and row k is added up by lane k
@@ -169,11 +183,11 @@ __device__ __forceinline__ void WarpFlaggedPowerSums(uint32_t bits, double zbase
 			bits &= bits - 1u;
 			uint32_t const off = static_cast<uint32_t>((s >> 2) * (4 * NT) + (s & 3));
 			double const x = (zbase + u32_to_double(off)) * h;
-			double pw = 1.0;
+			double pw[NS];
+			PowerTree<NS>(x, pw);
 #pragma unroll
 			for (int k = 0; k < NS; ++k) {
-				ps[k] += pw;
-				pw *= x;
+				ps[k] += pw[k];
 			}
 		} while (bits != 0u);
 #pragma unroll
@@ -753,14 +767,14 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc, int const num_sms
 					int const ch = 1024 * warp + 8 * (lane + 32 * (s >> 3)) + (s & 7);
 					double const x = static_cast<double>(ch) * pc.h;
 					double const yd = static_cast<double>(sdata[channel_index(ch >> 5, ch & 31)]);
-					double pw = 1.0;
+					double pw[NS];
+					PowerTree<NS>(x, pw);
 #pragma unroll
 					for (int k = 0; k < NS; ++k) {
-						ps[k] += pw;
+						ps[k] += pw[k];
 						if (k < K) {
-							pt[k] = fma(yd, pw, pt[k]);
+							pt[k] = fma(yd, pw[k], pt[k]);
 						}
-						pw *= x;
 					}
 					qq = fma(yd, yd, qq);
 				}
