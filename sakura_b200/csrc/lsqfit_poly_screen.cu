@@ -160,7 +160,7 @@ __device__ __forceinline__ void PowerTree(double x, double (&pw)[N]) {
 // Power sums sum x^k (k < 2K-1) over the channels whose bit is set in `bits`, in the INTERLEAVED
 // ownership of the load pass (bit 4j+e of thread t <-> channel 4(t + NT j) + e); per-lane partials
 // are transposed through `scratch` (NS rows of 33 doubles per warp) and row k is added up by lane k
-// over the lanes that had any bit, in lane order: deterministic, no atomics.
+// in a fixed order: deterministic, no atomics.
 template<int K, int NT>
 __device__ __forceinline__ void WarpFlaggedPowerSums(uint32_t bits, double zbase, double h, int lane,
 		double *scratch, double *wtot) {
@@ -172,13 +172,13 @@ __device__ __forceinline__ void WarpFlaggedPowerSums(uint32_t bits, double zbase
 		}
 		return;
 	}
-	if (bits != 0u) {
+	{
 		double ps[NS];
 #pragma unroll
 		for (int k = 0; k < NS; ++k) {
 			ps[k] = 0.0;
 		}
-		do {
+		while (bits != 0u) {
 			int const s = __ffs(bits) - 1;
 			bits &= bits - 1u;
 			uint32_t const off = static_cast<uint32_t>((s >> 2) * (4 * NT) + (s & 3));
@@ -189,19 +189,25 @@ __device__ __forceinline__ void WarpFlaggedPowerSums(uint32_t bits, double zbase
 			for (int k = 0; k < NS; ++k) {
 				ps[k] += pw[k];
 			}
-		} while (bits != 0u);
+		}
 #pragma unroll
 		for (int k = 0; k < NS; ++k) {
-			scratch[k * 33 + lane] = ps[k];
+			scratch[k * 33 + lane] = ps[k]; // every lane writes (zeros without bits)
 		}
 	}
 	__syncwarp();
 	if (lane < NS) {
-		double tot = 0.0;
+		// fixed order, four independent partial sums (a single running sum is a chain of 32 FP64 adds)
 		double const *rowp = scratch + lane * 33;
-		for (uint32_t m = active; m != 0u; m &= m - 1u) {
-			tot += rowp[__ffs(m) - 1];
+		double t0 = 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+#pragma unroll
+		for (int l = 0; l < 32; l += 4) {
+			t0 += rowp[l];
+			t1 += rowp[l + 1];
+			t2 += rowp[l + 2];
+			t3 += rowp[l + 3];
 		}
+		double const tot = (t0 + t1) + (t2 + t3);
 		wtot[lane] = tot;
 	}
 	__syncwarp();
