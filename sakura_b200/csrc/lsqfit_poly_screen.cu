@@ -810,15 +810,23 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc, int const num_sms
 				// a fixed order, no atomics, no reduction scratch.
 				double s_acc = 0.0, t_acc = 0.0, q_acc = 0.0;
 				if (total > 0) {
-					int incl = mine;
+					// position of this lane's first entry: one ballot when no lane holds more than one
+					// channel (the usual case late in a fit), else a prefix sum over the lanes
+					int first_entry;
+					if (__all_sync(0xffffffffu, mine <= 1)) {
+						first_entry = __popc(__ballot_sync(0xffffffffu, mine != 0) & ((1u << lane) - 1u));
+					} else {
+						int incl = mine;
 #pragma unroll
-					for (int o = 1; o < 32; o <<= 1) {
-						int const v = __shfl_up_sync(0xffffffffu, incl, o);
-						incl += (lane >= o) ? v : 0;
+						for (int o = 1; o < 32; o <<= 1) {
+							int const v = __shfl_up_sync(0xffffffffu, incl, o);
+							incl += (lane >= o) ? v : 0;
+						}
+						first_entry = incl - mine;
 					}
 					{
 						uint32_t b = clipped;
-						int r = incl - mine;
+						int r = first_entry;
 						while (b != 0u) {
 							int const s = __ffs(b) - 1;
 							b &= b - 1u;
@@ -833,10 +841,10 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc, int const num_sms
 						double const x2 = xy.x * xy.x;
 						double const x4 = x2 * x2;
 						double const x8 = x4 * x4;
-						double pw = (lane & 1) ? xy.x : 1.0;
-						pw *= (lane & 2) ? x2 : 1.0;
-						pw *= (lane & 4) ? x4 : 1.0;
-						pw *= (lane & 8) ? x8 : 1.0;
+						// x^lane from the binary digits of the lane number, as a two-level product
+						double const f01 = ((lane & 1) ? xy.x : 1.0) * ((lane & 2) ? x2 : 1.0);
+						double const f23 = ((lane & 4) ? x4 : 1.0) * ((lane & 8) ? x8 : 1.0);
+						double const pw = f01 * f23;
 						s_acc += pw;
 						t_acc = fma(xy.y, pw, t_acc);
 						q_acc = fma(xy.y, xy.y, q_acc);
