@@ -949,8 +949,8 @@ cudaError_t LaunchPolyFitKernel(PolyFitParams const &p, int num_sms, cudaStream_
 
 bool ScreeningEnabled(int num_fitting_max) {
 	// Screening pays from the third fit on (measured on B200, 4096 channels, order 5: 7.2e7 against
-	// 7.9e7 spectra/s at one fit, 4.85e7 / 5.0e7 at two, 3.73e7 / 3.70e7 at three, 3.16e7 / 3.0e7 at
-	// four, 2.88e7 / 2.66e7 at five).
+	// 7.9e7 spectra/s at one fit, 4.85e7 / 5.0e7 at two, 3.94e7 / 3.70e7 at three, 3.05e7 / 2.66e7 at
+	// five).
 	// SAKURA_B200_POLY_SCREEN=0 runs every row through PolyFitKernel, =1 screens whatever the number
 	// of fits (the parity tests compare the two kernels); read per call so that a test can switch
 	// within one process.
