@@ -744,17 +744,20 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc, int const num_sms
 			int const mine = __popc(clipped);
 			int const total = __reduce_add_sync(0xffffffffu, mine);
 			if (total > kHeavyClipped) {
-				// Many channels, typically runs that fill a few threads' words: the warp's 128 bytes
-				// of clipped bits are redistributed bytewise (lane l takes bytes l, l+32, l+64, l+96, so
-				// a run of 100 channels spreads over 13 lanes), every lane accumulates private partial
-				// moments, and the partials are added up with a butterfly of shuffles.
+				// Many channels, typically runs that fill a few threads' words: the warp's 1024 clipped
+				// bits are redistributed by nibbles (lane l takes nibbles l, l+32, ..., l+224, so a run of
+				// 100 channels spreads over 25 lanes, four channels each), every lane accumulates private
+				// partial moments, and the partials are added up with a butterfly of shuffles.
 				uint32_t *cw = reinterpret_cast<uint32_t *>(sh.list[warp]);
 				cw[lane] = clipped;
 				__syncwarp();
 				uint8_t const *cb = reinterpret_cast<uint8_t const *>(cw);
-				uint32_t w = static_cast<uint32_t>(cb[lane]) | (static_cast<uint32_t>(cb[lane + 32]) << 8)
-						| (static_cast<uint32_t>(cb[lane + 64]) << 16)
-						| (static_cast<uint32_t>(cb[lane + 96]) << 24);
+				uint32_t w = 0u; // bit 4 m + e <-> channel 4 (lane + 32 m) + e of this warp
+#pragma unroll
+				for (int m = 0; m < 8; ++m) {
+					int const nibble = lane + 32 * m;
+					w |= ((static_cast<uint32_t>(cb[nibble >> 1]) >> (4 * (nibble & 1))) & 0xfu) << (4 * m);
+				}
 				__syncwarp();
 				double ps[NS];
 				double pt[K];
@@ -770,7 +773,7 @@ PolyScreenFitKernel(PolyFitParams const p, PolyConst const pc, int const num_sms
 				while (w != 0u) {
 					int const s = __ffs(w) - 1;
 					w &= w - 1u;
-					int const ch = 1024 * warp + 8 * (lane + 32 * (s >> 3)) + (s & 7);
+					int const ch = 1024 * warp + 4 * (lane + 32 * (s >> 2)) + (s & 3);
 					double const x = static_cast<double>(ch) * pc.h;
 					double const yd = static_cast<double>(sdata[channel_index(ch >> 5, ch & 31)]);
 					double pw[NS];
