@@ -223,7 +223,10 @@ __device__ __forceinline__ double warp_max_upper(double a) {
 /** 1/sqrt(v) to ~1e-13 relative for v in [1e-30, 1e30] (float rsqrt estimate + two Newton steps);
  *  sqrt(v) = v * rsqrt_fast(v) */
 __device__ __forceinline__ double rsqrt_fast(double v) {
-	double r = static_cast<double>(rsqrtf(static_cast<float>(v)));
+	// FP64 hardware estimate (relative error ~2^-20; no float round trip: a conversion costs as much
+	// as the estimate itself)
+	double r;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(v));
 	double const hv = 0.5 * v;
 	r = fma(r, fma(-hv * r, r, 0.5), r);
 	r = fma(r, fma(-hv * r, r, 0.5), r);
@@ -321,7 +324,8 @@ __device__ __forceinline__ void Control(ScreenShared<K, NT> &sh, PolyConst const
 			// what the other three wait for): products of the form a sqrt(N ss) are bounded by
 			// (a^2 N + ss) / 2, and sum |rho| / N <= sqrt(ss / N) reuses the rms computed anyway.
 			double const e64_ss = kTiny40 * 2.0 * (Q + c1 * c1 * N); // >= 2^-40 (Q + 2 c1 sum|y| + c1^2 N)
-			double const ssc = fmax(ss + e64_ss, 0.0);
+			double const ss_up = ss + e64_ss;
+			double const ssc = (ss_up > 0.0) ? ss_up : 0.0; // (NaN -> 0: caught by the tests on q_m below)
 			// what rounding the model and the residual to float can change (|e_i| <= u (A + |rho_i|)):
 			// 2 u (A sum|rho| + ss) + 2 u^2 (N A^2 + ss). sum|rho| <= sqrt(N ss) <= (N kappa + ss / kappa) / 2
 			// for any kappa > 0: the previous fit's rms (tight within a few per cent), A for the first fit
@@ -348,12 +352,13 @@ __device__ __forceinline__ void Control(ScreenShared<K, NT> &sh, PolyConst const
 				double const m2max = mabs * mabs;
 				// var = q - mean^2 in [q_m - m2max, q_p]; sqrt(q_m - m2) >= sqrt(q_m) - m2 / sqrt(q_m)
 				double const sigma = static_cast<double>(clip);
-				double const rms_m = fma(-m2max * (1.0 + kTiny40), r_m, q_m * r_m) * (1.0 - kTiny40);
+				// (the safety factors of rms_m and of the product with sigma are folded into sigma_m / sigma_p)
+				double const rms_m = fma(-m2max * (1.0 + kTiny40), r_m, q_m * r_m);
 				double const rms_p = s_p;
 				// thresholds as make_thresholds (device_common.cuh) forms them; conversions to float
 				// round to nearest and are monotone, the FP64 roundings are covered by the nudges
-				float const thr_m = static_cast<float>(sigma * rms_m * (1.0 - kTiny40));
-				float const thr_p = static_cast<float>(sigma * rms_p * (1.0 + kTiny40));
+				float const thr_m = static_cast<float>(rms_m * (sigma * (1.0 - 3.0 * kTiny40)));
+				float const thr_p = static_cast<float>(rms_p * (sigma * (1.0 + 3.0 * kTiny40)));
 				double const nudge = kTiny40 * (mabs + static_cast<double>(thr_p));
 				lo_m = static_cast<float>(mean_m - static_cast<double>(thr_p) - nudge);
 				lo_p = static_cast<float>(mean_p - static_cast<double>(thr_m) + nudge);
