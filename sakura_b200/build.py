@@ -17,7 +17,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsakura_b200.so")
 
-CUDA_SOURCES = ["capi.cu", "lsqfit_general.cu", "lsqfit_poly.cu", "lsqfit_poly_screen.cu", "statistics.cu",
+CUDA_SOURCES = ["capi.cu", "lsqfit_general.cu", "lsqfit_poly.cu", "lsqfit_poly_screen.cu", "lsqfit_poly_warp.cu", "statistics.cu",
                 "lsq_blocks.cu", "lsqfit_sinusoid.cu", "lsqfit_spline.cu", "calibration.cu", "bool_filters.cu", "interpolation.cu"]
 HOST_SOURCES = ["basis_tables.cc"]
 

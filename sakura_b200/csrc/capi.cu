@@ -521,9 +521,10 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 			p.fallback_rows = c->d_fallback.As<int32_t>();
 		}
 		int launches = 0;
-		cudaError_t e = LaunchPolyFit(p, info.num_sms, stream, &launches);
+		char const *kernel_name = "poly_fast";
+		cudaError_t e = LaunchPolyFit(p, info.num_sms, stream, &launches, &kernel_name);
 		g_launch_count += launches;
-		g_last_kernel = launches > 1 ? "poly_screen" : "poly_fast";
+		g_last_kernel = kernel_name;
 		c->last_handover = launches > 1 ? p.fallback_rows : nullptr;
 		if (e != cudaSuccess) {
 			SetError("LaunchPolyFit", e);

@@ -947,27 +947,56 @@ namespace {
 
 cudaError_t LaunchPolyFitKernel(PolyFitParams const &p, int num_sms, cudaStream_t stream);
 
-bool ScreeningEnabled(int num_fitting_max) {
-	// Screening pays from the third fit on (measured on B200, 4096 channels, order 5: 7.2e7 against
-	// 7.9e7 spectra/s at one fit, 4.85e7 / 5.0e7 at two, 3.94e7 / 3.70e7 at three, 3.05e7 / 2.66e7 at
-	// five).
-	// SAKURA_B200_POLY_SCREEN=0 runs every row through PolyFitKernel, =1 screens whatever the number
-	// of fits (the parity tests compare the two kernels); read per call so that a test can switch
-	// within one process.
+enum PolyKernelChoice : int {
+	kChoiceChannel = 0, kChoiceScreen = 1, kChoiceWarp = 2
+};
+
+PolyKernelChoice ChooseKernel(PolyFitParams const &p) {
+	// SAKURA_B200_POLY_KERNEL = channel | screen | warp forces one kernel (where the shape allows it);
+	// SAKURA_B200_POLY_SCREEN = 0 / 1 is the older switch between the first two. Read per call so that a
+	// test can switch within one process (the parity tests compare the kernels with each other).
+	// Default: the warp-per-spectrum kernel from the second fit on (4096 / 2048 channels), the screening
+	// kernel from the third fit on for 8192 channels, the per-channel kernel otherwise (measured on B200,
+	// 4096 channels, order 5: see profiles/README.md).
+	bool const can_screen = p.fallback_rows != nullptr && PolyScreenSupported(p);
+	bool const can_warp = p.fallback_rows != nullptr && PolyWarpSupported(p);
+	char const *k = getenv("SAKURA_B200_POLY_KERNEL");
+	if (k != nullptr) {
+		if (k[0] == 'c') {
+			return kChoiceChannel;
+		}
+		if (k[0] == 's') {
+			return can_screen ? kChoiceScreen : kChoiceChannel;
+		}
+		if (k[0] == 'w') {
+			return can_warp ? kChoiceWarp : kChoiceChannel;
+		}
+	}
 	char const *e = getenv("SAKURA_B200_POLY_SCREEN");
 	if (e != nullptr && (e[0] == '0' || e[0] == '1')) {
-		return e[0] == '1';
+		return (e[0] == '1' && can_screen) ? kChoiceScreen : kChoiceChannel;
 	}
-	return num_fitting_max >= 3;
+	if (can_warp && p.num_fitting_max >= 2) {
+		return kChoiceWarp;
+	}
+	if (can_screen && p.num_fitting_max >= 3) {
+		return kChoiceScreen;
+	}
+	return kChoiceChannel;
 }
 
 } // namespace
 
-cudaError_t LaunchPolyFit(PolyFitParams const &p_in, int num_sms, cudaStream_t stream, int *launches) {
+cudaError_t LaunchPolyFit(PolyFitParams const &p_in, int num_sms, cudaStream_t stream, int *launches,
+		char const **kernel_name) {
 	PolyFitParams p = p_in;
 	p.row_index = nullptr;
 	p.row_count = nullptr;
-	if (p.fallback_rows != nullptr && ScreeningEnabled(p.num_fitting_max) && PolyScreenSupported(p)) {
+	PolyKernelChoice const choice = ChooseKernel(p);
+	if (kernel_name != nullptr) {
+		*kernel_name = (choice == kChoiceWarp) ? "poly_warp" : (choice == kChoiceScreen) ? "poly_screen" : "poly_fast";
+	}
+	if (choice != kChoiceChannel) {
 		// screened clip iterations first; the rows that kernel gives up (undecidable channel,
 		// degenerate system) are then fitted by the per-channel kernel from its list
 		p.fallback_count = p.fallback_rows;
@@ -976,7 +1005,8 @@ cudaError_t LaunchPolyFit(PolyFitParams const &p_in, int num_sms, cudaStream_t s
 		if (err != cudaSuccess) {
 			return err;
 		}
-		err = LaunchPolyScreenFit(p, num_sms, stream);
+		err = (choice == kChoiceWarp) ? LaunchPolyWarpFit(p, num_sms, stream) :
+				LaunchPolyScreenFit(p, num_sms, stream);
 		*launches += 1;
 		if (err != cudaSuccess) {
 			return err;

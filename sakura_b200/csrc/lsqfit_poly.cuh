@@ -50,11 +50,16 @@ bool PolyFastSupported(size_t n, size_t K, size_t data_stride, size_t mask_strid
  *  (4096 and 8192: every thread owns all of its 32 channel slots). */
 bool PolyFusedCalibrationSupported(size_t n);
 
-cudaError_t LaunchPolyFit(PolyFitParams const &p, int num_sms, cudaStream_t stream, int *launches);
+cudaError_t LaunchPolyFit(PolyFitParams const &p, int num_sms, cudaStream_t stream, int *launches,
+		char const **kernel_name);
 
 /** Screened clip iterations (lsqfit_poly_screen.cu): n = 4096 or 8192 channels, K <= 8. */
 bool PolyScreenSupported(PolyFitParams const &p);
 cudaError_t LaunchPolyScreenFit(PolyFitParams const &p, int num_sms, cudaStream_t stream);
+
+/** One warp per spectrum, no block barrier (lsqfit_poly_warp.cu): n = 2048 or 4096 channels, K <= 8. */
+bool PolyWarpSupported(PolyFitParams const &p);
+cudaError_t LaunchPolyWarpFit(PolyFitParams const &p, int num_sms, cudaStream_t stream);
 
 } // namespace sakura_b200
 
