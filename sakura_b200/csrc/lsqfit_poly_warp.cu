@@ -50,6 +50,7 @@ constexpr double kSlack = 1.0009765625; // 1 + 2^-10
 constexpr double kTiny40 = 9.094947017729282e-13; // 2^-40
 constexpr double kTiny44 = 5.684341886080802e-14; // 2^-44
 constexpr int kScratchBytes = 2048;
+constexpr int kListCap = 960; // u16 entries of the work lists; the last 128 scratch bytes hold the dirty bits
 constexpr int kSegStride = 16; // doubles per row of the segment table (>= kMaxMoments)
 
 enum WarpMode : int {
@@ -307,6 +308,7 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 	unsigned char *scratch = slice + static_cast<size_t>(n) * 4;
 	uint16_t *slist = reinterpret_cast<uint16_t *>(scratch);
 	double *sstage = reinterpret_cast<double *>(scratch);
+	uint32_t *sdirty = reinterpret_cast<uint32_t *>(scratch + 2 * kListCap); // bit g: group g holds a NaN
 	uint32_t *svalid = reinterpret_cast<uint32_t *>(scratch + kScratchBytes);
 	uint64_t *mbar = reinterpret_cast<uint64_t *>(scratch + kScratchBytes + static_cast<size_t>(NB) * 128);
 
@@ -354,13 +356,6 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 			fence_proxy_async();
 			mbar_expect_tx(mbar, static_cast<unsigned>(n) * 4u);
 			bulk_copy_g2s(sdata, grow, static_cast<unsigned>(n) * 4u, mbar);
-			size_t const nrow = row + static_cast<size_t>(gridDim.x) * W;
-			if (nrow < p.num_spectra) {
-				asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
-						:: "l"(p.data + nrow * p.data_stride), "r"(static_cast<unsigned>(n) * 4u) : "memory");
-				asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
-						:: "l"(p.mask + nrow * p.mask_stride), "r"(static_cast<unsigned>(n)) : "memory");
-			}
 		}
 		// ---- mask bytes -> bits, interleaved ownership: segment lane + 32 j = channels 16 (lane + 32 j).. ----
 		uint32_t vseg[NPW]; // valid bits of segments (2 w, 2 w + 1) in the low / high half
@@ -443,7 +438,7 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 				mine += __popc(it);
 			}
 			int const total = __reduce_add_sync(0xffffffffu, mine);
-			if (total > kScratchBytes / 2) {
+			if (total > kListCap) {
 				giveup = true; // (cannot happen below 8 visited channels per segment on average)
 			} else if (total > 0) {
 				int pos = warp_exclusive_scan(mine, lane);
@@ -487,20 +482,6 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 		if (skip) {
 			continue;
 		}
-		// flagged channels -> 0 for the moment pass (so that it needs no mask), -> NaN afterwards
-		auto sanitize = [&](float value) {
-#pragma unroll
-			for (int w = 0; w < NPW; ++w) {
-				uint32_t b = ~vseg[w];
-				while (b != 0u) {
-					int const s = __ffs(b) - 1;
-					b &= b - 1u;
-					sdata[16 * (lane + 32 * (2 * w + (s >> 4))) + (s & 15)] = value;
-				}
-			}
-			__syncwarp();
-		};
-		sanitize(0.0f);
 		// ---- data moments: per 32-channel block sum y u^m (u = 0..31, m < 8) on the FP64 tensor cores,
 		// shifted to the row origin by the lane that takes the block ----------------------------------
 		double tm[K];
@@ -525,10 +506,12 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 					float4 const ya = sd4[8 * blk + 2 * kcol];
 					float4 const yb = sd4[8 * blk + 2 * kcol + 1];
 					float const ye[8] = { ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w };
+					uint32_t const vb = reinterpret_cast<uint8_t const *>(svalid)[4 * blk + kcol];
 					double c0 = 0.0, c1 = 0.0;
 #pragma unroll
 					for (int j = 0; j < 8; ++j) {
-						double const yd = static_cast<double>(ye[j]);
+						// (a select on the bits: a NaN / Inf under the mask must not leak)
+						double const yd = static_cast<double>(keep_if_bit(ye[j], vb, j));
 						qsum = fma(yd, yd, qsum);
 						dmma8x8x4(c0, c1, yd, bp[j]);
 					}
@@ -560,7 +543,7 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 				__syncwarp();
 			}
 		}
-		sanitize(__int_as_float(0x7fc00000));
+		sdirty[lane] = 0u; // (the staging area of the moments is dead: barrier at the end of the last round)
 		// ---- totals: every lane gets S (2K-1), T (K), Q ---------------------------------------------
 		double S[NS], T[K], Q;
 #pragma unroll
@@ -656,25 +639,33 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 					bool clipped = false;
 					float y = 0.0f;
 					int ch = 0;
+					bool mute = false; // a flagged channel far from the model: silenced for the later passes
 					if (idx < total) {
 						ch = 4 * static_cast<int>(slist[idx]) + (lane & 3);
 						y = sdata[ch];
-						if (y == y && ch != n - 1) { // (channel n-1 is never examined: baseline.cc:1078)
-							double const z = static_cast<double>(ch);
-							double acc = fit.cz[K - 1];
+						bool const valid = ((svalid[ch >> 5] >> (ch & 31)) & 1u) != 0u;
+						double const z = static_cast<double>(ch);
+						double acc = fit.cz[K - 1];
 #pragma unroll
-							for (int k = K - 2; k >= 0; --k) {
-								acc = fma(acc, z, fit.cz[k]);
-							}
-							float const r = __fsub_rn(y, static_cast<float>(acc));
+						for (int k = K - 2; k >= 0; --k) {
+							acc = fma(acc, z, fit.cz[k]);
+						}
+						float const r = __fsub_rn(y, static_cast<float>(acc));
+						if (valid && ch != n - 1) { // (channel n-1 is never examined: baseline.cc:1078)
 							if (r > fit.hi_p || r < fit.lo_m) {
 								clipped = true; // outside whatever the exact thresholds are
 							} else if (!(r <= fit.hi_m && r >= fit.lo_p)) {
 								undecided = true; // inside a threshold interval
 							}
+						} else if (!(fabsf(r) < c_in) && y == y) {
+							mute = true;
 						}
 					}
 					uint32_t const cb = __ballot_sync(0xffffffffu, clipped);
+					if (clipped || mute) {
+						sdata[ch] = __int_as_float(0x7fc00000);
+						atomicOr(sdirty + (ch >> 7), 1u << ((ch >> 2) & 31));
+					}
 					if (cb != 0u) {
 						num_clipped += __popc(cb);
 						if (clipped) {
@@ -690,7 +681,6 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 								}
 							}
 							cq = fma(yd, yd, cq);
-							sdata[ch] = __int_as_float(0x7fc00000);
 							atomicAnd(svalid + (ch >> 5), ~(1u << (ch & 31)));
 						}
 					}
@@ -766,6 +756,24 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 			float4 const *grow4 = reinterpret_cast<float4 const *>(grow);
 			float4 *gbest4 = (p.best_fit != nullptr) ?
 					reinterpret_cast<float4 *>(p.best_fit + row * p.data_stride) : nullptr;
+			if (p.residual != nullptr) {
+				// groups that hold a NaN (clipped or silenced channels): their data comes from global memory
+				// again, two groups per step so that the loads overlap
+				uint32_t dirty = (NB == 4) ? sdirty[lane] : ((sdirty[lane >> 1] >> (16 * (lane & 1))) & 0xffffu);
+				while (dirty != 0u) {
+					int const g0 = __ffs(dirty) - 1;
+					dirty &= dirty - 1u;
+					int g1 = g0;
+					if (dirty != 0u) {
+						g1 = __ffs(dirty) - 1;
+						dirty &= dirty - 1u;
+					}
+					float4 const a = __ldg(grow4 + own4 + g0);
+					float4 const b = __ldg(grow4 + own4 + g1);
+					sd4[own4 + g0] = a;
+					sd4[own4 + g1] = b;
+				}
+			}
 #pragma unroll 1
 			for (int j = 0; j < NB; ++j) {
 				double d[K];
@@ -775,10 +783,7 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 					int const g = q ^ l7;
 					int const idx = own4 + 8 * j + g;
 					uint32_t const nib = (vw[j] >> (4 * g)) & 0xfu;
-					float4 y = sd4[idx];
-					if (nib != 0xfu) {
-						y = __ldg(grow4 + idx);
-					}
+					float4 const y = sd4[idx];
 					float const ye[4] = { y.x, y.y, y.z, y.w };
 					float re[4], me[4];
 					double const ub = static_cast<double>(4 * g);
@@ -793,9 +798,11 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 						me[e] = static_cast<float>(acc);
 						float const r = __fsub_rn(ye[e], me[e]);
 						re[e] = r;
-						double const rd = static_cast<double>(keep_if_bit(r, nib, e));
-						sum += rd;
-						sq = fma(rd, rd, sq);
+						// statistics over the valid channels: predicated, so that whatever sits under the
+						// mask (NaN, Inf) cannot leak
+						double const rd = static_cast<double>(r);
+						asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %3;\n\t"
+								"@p fma.rn.f64 %1, %3, %3, %1;\n\t}" : "+d"(sum), "+d"(sq) : "r"(nib & (1u << e)), "d"(rd));
 					}
 					sd4[idx] = make_float4(re[0], re[1], re[2], re[3]);
 					if (gbest4 != nullptr) {
