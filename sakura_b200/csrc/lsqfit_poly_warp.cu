@@ -71,7 +71,8 @@ __host__ __device__ constexpr size_t TableBytes() {
 }
 
 __device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a, double b) {
-	asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+	// (not volatile: a pure function of its operands, so that independent products can be interleaved)
+	asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
 			: "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
@@ -284,8 +285,9 @@ __device__ __forceinline__ void ControlWarp(double const (&S)[2 * K - 1], double
 // 16 mask bytes -> 16 bits (any non-zero byte is "true"), bit b <-> byte b
 __device__ __forceinline__ uint32_t MaskBits16(uint4 const m) {
 	auto nib = [](uint32_t w) {
-		uint32_t const t = __vcmpne4(w, 0u) & 0x01010101u;
-		return (t * 0x01020408u) >> 24;
+		// bit 7 of every non-zero byte, then the four flags gathered into the top nibble by a product
+		uint32_t const t = (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;
+		return (t * 0x00204081u) >> 28;
 	};
 	return nib(m.x) | (nib(m.y) << 4) | (nib(m.z) << 8) | (nib(m.w) << 12);
 }
@@ -314,10 +316,11 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 
 	// DMMA B fragments of the data-moment pass: B_j[k][m] = (8 k + j)^m, k = lane % 4, m = lane / 4
 	if (warp == 0) {
-#pragma unroll
+#pragma unroll 1
 		for (int j = 0; j < 8; ++j) {
 			double const u = static_cast<double>(8 * (lane & 3) + j);
 			double v = 1.0;
+#pragma unroll 1
 			for (int m = 0; m < (lane >> 2); ++m) {
 				v *= u;
 			}
@@ -346,6 +349,7 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 	}
 	float4 *sd4 = reinterpret_cast<float4 *>(sdata);
 	int const own4 = lane * (8 * NB); // first float4 group of the lane's consecutive channels
+	float4 const *own_sw = sd4 + own4;
 
 	for (size_t row = static_cast<size_t>(blockIdx.x) * W + warp; row < p.num_spectra;
 			row += static_cast<size_t>(gridDim.x) * W) {
@@ -405,46 +409,44 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 		}
 		bool const direct = (2 * count < n);
 		if (!skip) {
-			uint32_t items[NPW];
+			uint16_t const *sv16 = reinterpret_cast<uint16_t const *>(svalid);
+			auto visited = [&](int s, bool &comp) {
+				uint32_t const vb = sv16[lane + 32 * s]; // (this lane's own store above)
+				uint32_t const x = direct ? vb : (~vb & 0xffffu);
+				comp = __popc(x) > 8;
+				return comp ? (~x & 0xffffu) : x;
+			};
 			uint32_t neg = 0u; // bit s: segment s of this lane is visited through its complement
 			int mine = 0;
+#pragma unroll 1
+			for (int s = 0; s < NSEG; ++s) {
+				bool comp;
+				mine += __popc(visited(s, comp));
+				if (__any_sync(0xffffffffu, comp)) {
+					if (comp) {
+						double const *rowp = seg_sums + static_cast<size_t>(lane + 32 * s) * kSegStride;
 #pragma unroll
-			for (int w = 0; w < NPW; ++w) {
-				uint32_t it = 0u;
-#pragma unroll
-				for (int hgh = 0; hgh < 2; ++hgh) {
-					int const s = 2 * w + hgh;
-					uint32_t const vb = (vseg[w] >> (16 * hgh)) & 0xffffu;
-					uint32_t const x = direct ? vb : (~vb & 0xffffu);
-					int const c = __popc(x);
-					bool const comp = c > 8;
-					if (__any_sync(0xffffffffu, comp)) {
-						if (comp) {
-							double const *rowp = seg_sums + static_cast<size_t>(lane + 32 * s) * kSegStride;
-#pragma unroll
-							for (int k = 0; k < NS; k += 2) {
-								double2 const v = __ldg(reinterpret_cast<double2 const *>(rowp + k));
-								ps[k] += v.x;
-								if (k + 1 < NS) {
-									ps[k + 1] += v.y;
-								}
+						for (int k = 0; k < NS; k += 2) {
+							double2 const v = __ldg(reinterpret_cast<double2 const *>(rowp + k));
+							ps[k] += v.x;
+							if (k + 1 < NS) {
+								ps[k + 1] += v.y;
 							}
-							neg |= 1u << s;
 						}
+						neg |= 1u << s;
 					}
-					it |= (comp ? (~x & 0xffffu) : x) << (16 * hgh);
 				}
-				items[w] = it;
-				mine += __popc(it);
 			}
 			int const total = __reduce_add_sync(0xffffffffu, mine);
 			if (total > kListCap) {
 				giveup = true; // (cannot happen below 8 visited channels per segment on average)
 			} else if (total > 0) {
 				int pos = warp_exclusive_scan(mine, lane);
-#pragma unroll
+#pragma unroll 1
 				for (int w = 0; w < NPW; ++w) {
-					uint32_t b = items[w];
+					bool c0, c1;
+					uint32_t b = visited(2 * w, c0);
+					b |= visited(2 * w + 1, c1) << 16;
 					while (b != 0u) {
 						int const s = __ffs(b) - 1;
 						b &= b - 1u;
@@ -500,22 +502,32 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 			int const kcol = lane & 3;
 #pragma unroll 1
 			for (int r = 0; r < NB; ++r) {
+				// four independent sequences of eight dependent products each, interleaved
+				float ye[4][8];
+				uint32_t vb[4];
 #pragma unroll
 				for (int q = 0; q < 4; ++q) {
 					int const blk = 32 * r + 8 * q + mrow;
 					float4 const ya = sd4[8 * blk + 2 * kcol];
 					float4 const yb = sd4[8 * blk + 2 * kcol + 1];
-					float const ye[8] = { ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w };
-					uint32_t const vb = reinterpret_cast<uint8_t const *>(svalid)[4 * blk + kcol];
-					double c0 = 0.0, c1 = 0.0;
+					ye[q][0] = ya.x, ye[q][1] = ya.y, ye[q][2] = ya.z, ye[q][3] = ya.w;
+					ye[q][4] = yb.x, ye[q][5] = yb.y, ye[q][6] = yb.z, ye[q][7] = yb.w;
+					vb[q] = reinterpret_cast<uint8_t const *>(svalid)[4 * blk + kcol];
+				}
+				double c0[4] = { 0.0, 0.0, 0.0, 0.0 }, c1[4] = { 0.0, 0.0, 0.0, 0.0 };
 #pragma unroll
-					for (int j = 0; j < 8; ++j) {
+				for (int j = 0; j < 8; ++j) {
+#pragma unroll
+					for (int q = 0; q < 4; ++q) {
 						// (a select on the bits: a NaN / Inf under the mask must not leak)
-						double const yd = static_cast<double>(keep_if_bit(ye[j], vb, j));
+						double const yd = static_cast<double>(keep_if_bit(ye[q][j], vb[q], j));
 						qsum = fma(yd, yd, qsum);
-						dmma8x8x4(c0, c1, yd, bp[j]);
+						dmma8x8x4(c0[q], c1[q], yd, bp[j]);
 					}
-					reinterpret_cast<double2 *>(sstage)[((8 * q + mrow) * 8 + 2 * kcol) >> 1] = make_double2(c0, c1);
+				}
+#pragma unroll
+				for (int q = 0; q < 4; ++q) {
+					reinterpret_cast<double2 *>(sstage)[((8 * q + mrow) * 8 + 2 * kcol) >> 1] = make_double2(c0[q], c1[q]);
 				}
 				__syncwarp();
 				{
@@ -589,10 +601,11 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 				float2 const d0 = make_float2(n0, n0);
 				float2 const d1 = make_float2(n1, n1);
 				float2 const d2 = make_float2(n2, n2);
-				uint32_t sj = 0u;
+				uint32_t sj = 0u; // bit q: the group visited at step q
+				float4 const *blk4 = own_sw + 8 * j;
 #pragma unroll
 				for (int q = 0; q < 8; ++q) {
-					float4 const y = sd4[own4 + 8 * j + (q ^ l7)];
+					float4 const y = blk4[q ^ l7];
 					float2 const t01 = __ffma2_rn(d2, u01[q], d1);
 					float2 const t23 = __ffma2_rn(d2, u23[q], d1);
 					float2 const p01 = __ffma2_rn(t01, u01[q], d0);
@@ -602,7 +615,7 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 					// a NaN (flagged or clipped channel) is ignored by the maximum
 					float const m = fmaxf(fmaxf(fmaxf(fabsf(r01.x), fabsf(r01.y)), fabsf(r23.x)), fabsf(r23.y));
 					if (m >= c_in) {
-						sj |= 1u << (q ^ l7);
+						sj |= 1u << q;
 					}
 				}
 				susp |= sj << (8 * j);
@@ -619,7 +632,7 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 					while (b != 0u) {
 						int const s = __ffs(b) - 1;
 						b &= b - 1u;
-						slist[pos] = static_cast<uint16_t>(8 * NB * lane + s);
+						slist[pos] = static_cast<uint16_t>(8 * NB * lane + (s ^ l7)); // (step -> group of the block)
 						++pos;
 					}
 				}
