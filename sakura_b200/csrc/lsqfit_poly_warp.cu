@@ -730,6 +730,30 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 			}
 			continue;
 		}
+		// ---- groups that hold a NaN (clipped or silenced channels) get their data from global memory again:
+		// asynchronous 16-byte copies, in flight while the final mask is expanded and written; the next
+		// row's lines are requested into L2 now (not earlier: they would be evicted again before use) ----
+		__syncwarp();
+		if (p.residual != nullptr && !failed) {
+			uint32_t dirty = (NB == 4) ? sdirty[lane] : ((sdirty[lane >> 1] >> (16 * (lane & 1))) & 0xffffu);
+			float4 const *grow4 = reinterpret_cast<float4 const *>(grow);
+			while (dirty != 0u) {
+				int const g = __ffs(dirty) - 1;
+				dirty &= dirty - 1u;
+				asm volatile("cp.async.ca.shared.global [%0], [%1], 16;"
+						:: "r"(smem_u32(sd4 + own4 + g)), "l"(grow4 + own4 + g) : "memory");
+			}
+			asm volatile("cp.async.commit_group;" ::: "memory");
+		}
+		if (lane == 0) {
+			size_t const nrow = row + static_cast<size_t>(gridDim.x) * W;
+			if (nrow < p.num_spectra) {
+				asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+						:: "l"(p.data + nrow * p.data_stride), "r"(static_cast<unsigned>(n) * 4u) : "memory");
+				asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+						:: "l"(p.mask + nrow * p.mask_stride), "r"(static_cast<unsigned>(n)) : "memory");
+			}
+		}
 		// ---- final mask: 32 NB consecutive bytes per lane ---------------------------------------------
 		uint32_t vw[NB];
 		{
@@ -766,27 +790,9 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 		// again (their lines are still in L2) ----------------------------------------------------------
 		double sum = 0.0, sq = 0.0;
 		{
-			float4 const *grow4 = reinterpret_cast<float4 const *>(grow);
 			float4 *gbest4 = (p.best_fit != nullptr) ?
 					reinterpret_cast<float4 *>(p.best_fit + row * p.data_stride) : nullptr;
-			if (p.residual != nullptr) {
-				// groups that hold a NaN (clipped or silenced channels): their data comes from global memory
-				// again, two groups per step so that the loads overlap
-				uint32_t dirty = (NB == 4) ? sdirty[lane] : ((sdirty[lane >> 1] >> (16 * (lane & 1))) & 0xffffu);
-				while (dirty != 0u) {
-					int const g0 = __ffs(dirty) - 1;
-					dirty &= dirty - 1u;
-					int g1 = g0;
-					if (dirty != 0u) {
-						g1 = __ffs(dirty) - 1;
-						dirty &= dirty - 1u;
-					}
-					float4 const a = __ldg(grow4 + own4 + g0);
-					float4 const b = __ldg(grow4 + own4 + g1);
-					sd4[own4 + g0] = a;
-					sd4[own4 + g1] = b;
-				}
-			}
+			asm volatile("cp.async.wait_all;" ::: "memory"); // (own copies into own groups: no warp barrier needed)
 #pragma unroll 1
 			for (int j = 0; j < NB; ++j) {
 				double d[K];
