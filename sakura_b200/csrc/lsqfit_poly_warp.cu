@@ -349,7 +349,12 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 	}
 	float4 *sd4 = reinterpret_cast<float4 *>(sdata);
 	int const own4 = lane * (8 * NB); // first float4 group of the lane's consecutive channels
-	float4 const *own_sw = sd4 + own4;
+	// shared-memory addresses of the eight groups of the lane's first block in visiting order
+	uint32_t qaddr[8];
+#pragma unroll
+	for (int q = 0; q < 8; ++q) {
+		qaddr[q] = smem_u32(sd4 + own4 + (q ^ l7));
+	}
 
 	for (size_t row = static_cast<size_t>(blockIdx.x) * W + warp; row < p.num_spectra;
 			row += static_cast<size_t>(gridDim.x) * W) {
@@ -602,10 +607,12 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 				float2 const d1 = make_float2(n1, n1);
 				float2 const d2 = make_float2(n2, n2);
 				uint32_t sj = 0u; // bit q: the group visited at step q
-				float4 const *blk4 = own_sw + 8 * j;
 #pragma unroll
 				for (int q = 0; q < 8; ++q) {
-					float4 const y = blk4[q ^ l7];
+					float4 y;
+					// (volatile: the row changes between passes -- clipped channels become NaN)
+					asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(y.x), "=f"(y.y), "=f"(y.z), "=f"(y.w)
+							: "r"(qaddr[q] + 128u * static_cast<unsigned>(j)));
 					float2 const t01 = __ffma2_rn(d2, u01[q], d1);
 					float2 const t23 = __ffma2_rn(d2, u23[q], d1);
 					float2 const p01 = __ffma2_rn(t01, u01[q], d0);
@@ -790,6 +797,9 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 		// again (their lines are still in L2) ----------------------------------------------------------
 		double sum = 0.0, sq = 0.0;
 		{
+			// four independent accumulator pairs (one per channel of a group): the additions of a single
+			// pair would be one dependent chain of 8-cycle operations through the whole row
+			double s4[4] = { 0.0, 0.0, 0.0, 0.0 }, q4[4] = { 0.0, 0.0, 0.0, 0.0 };
 			float4 *gbest4 = (p.best_fit != nullptr) ?
 					reinterpret_cast<float4 *>(p.best_fit + row * p.data_stride) : nullptr;
 			asm volatile("cp.async.wait_all;" ::: "memory"); // (own copies into own groups: no warp barrier needed)
@@ -808,7 +818,7 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 					double const ub = static_cast<double>(4 * g);
 #pragma unroll
 					for (int e = 0; e < 4; ++e) {
-						double const u = ub + static_cast<double>(e);
+						double const u = (e == 0) ? ub : ub + static_cast<double>(e);
 						double acc = d[K - 1];
 #pragma unroll
 						for (int k = K - 2; k >= 0; --k) {
@@ -817,11 +827,11 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 						me[e] = static_cast<float>(acc);
 						float const r = __fsub_rn(ye[e], me[e]);
 						re[e] = r;
-						// statistics over the valid channels: predicated, so that whatever sits under the
-						// mask (NaN, Inf) cannot leak
-						double const rd = static_cast<double>(r);
-						asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %2, 0;\n\t@p add.rn.f64 %0, %0, %3;\n\t"
-								"@p fma.rn.f64 %1, %3, %3, %1;\n\t}" : "+d"(sum), "+d"(sq) : "r"(nib & (1u << e)), "d"(rd));
+						// statistics over the valid channels: a select on the float (whatever sits under the
+						// mask -- NaN, Inf -- cannot leak), then unconditional FP64 accumulation
+						double const rd = static_cast<double>(((nib >> e) & 1u) != 0u ? r : 0.0f);
+						s4[e] += rd;
+						q4[e] = fma(rd, rd, q4[e]);
 					}
 					sd4[idx] = make_float4(re[0], re[1], re[2], re[3]);
 					if (gbest4 != nullptr) {
@@ -829,6 +839,8 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 					}
 				}
 			}
+			sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+			sq = (q4[0] + q4[1]) + (q4[2] + q4[3]);
 		}
 		if (p.residual != nullptr) {
 			fence_proxy_async();
