@@ -632,6 +632,10 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 			int const mine = __popc(susp);
 			int const total = __reduce_add_sync(0xffffffffu, mine);
 			int num_clipped = 0;
+			if (total > kListCap) {
+				giveup = true; // (more than 94 % of the groups suspect: the per-channel kernel takes the row)
+				break;
+			}
 			if (total > 0) {
 				{
 					int pos = warp_exclusive_scan(mine, lane);

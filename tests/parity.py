@@ -134,3 +134,24 @@ def spline_truth_residual(data_row, final_mask_row, boundary_row, npiece):
     c, *_ = np.linalg.lstsq(phi[sel], data_row[sel].astype(np.float64), rcond=None)
     model = (phi @ c).astype(np.float32)
     return (data_row.astype(np.float32) - model).astype(np.float64)
+
+
+class forced_kernel:
+    """SAKURA_B200_POLY_KERNEL = channel | screen | warp for the polynomial fits inside the block
+    (True / False = screen / channel)."""
+
+    def __init__(self, which):
+        self.which = which if isinstance(which, str) else ("screen" if which else "channel")
+
+    def __enter__(self):
+        import os
+        self.old = os.environ.get("SAKURA_B200_POLY_KERNEL")
+        os.environ["SAKURA_B200_POLY_KERNEL"] = self.which
+        return self
+
+    def __exit__(self, *exc):
+        import os
+        if self.old is None:
+            del os.environ["SAKURA_B200_POLY_KERNEL"]
+        else:
+            os.environ["SAKURA_B200_POLY_KERNEL"] = self.old

@@ -3,6 +3,8 @@ fused into its load is identical to calibrating, NaN/Inf-flagging and fitting in
 import numpy as np
 import pytest
 
+from parity import forced_kernel
+
 from sakura_b200 import synth
 from sakura_b200.capi import STATUS_OK, aligned_copy
 
@@ -101,7 +103,9 @@ def test_fused_calibration_equals_sequence(lib, dev, oracle, n, order, kernel):
     assert lib.last_kernel_name() == kernel
     cal = dev.calibrate(s, d, r)
     m2 = m & torch.isfinite(cal)
-    seq = dev.polynomial(ctx, order, cal, m2, 3.0, 4, want_best_fit=True)
+    # (bit-for-bit: the sequence must run the kernel family the fused call ran)
+    with forced_kernel({"poly_screen": "screen"}.get(kernel, "channel")):
+        seq = dev.polynomial(ctx, order, cal, m2, 3.0, 4, want_best_fit=True)
     torch.cuda.synchronize()
     for k in ("status", "lsqfit_status", "final_mask", "rms", "coeff", "residual", "best_fit"):
         a, b = fused[k].cpu().numpy(), seq[k].cpu().numpy()

@@ -45,7 +45,7 @@ def test_full_size_properties(lib, oracle, rows, n, nfit):
     data, mask = bench.generate_on_device(torch, rows, n, seed=7, device=dev)
     st, ctx = lib.create_polynomial_context(5, n)
     out = device_fit(lib, ctx, torch, data, mask, 5, 3.0, nfit)
-    assert lib.last_kernel_name() == ("poly_screen" if n in (4096, 8192) and nfit >= 3 else "poly_fast")
+    assert lib.last_kernel_name() == "poly_warp"
     assert int((out["status"] != 0).sum()) == 0
     fm = out["final_mask"]
     assert not bool((fm & ~mask).any())  # clipping only removes channels

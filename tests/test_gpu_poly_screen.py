@@ -1,4 +1,5 @@
-"""The screening kernel (csrc/lsqfit_poly_screen.cu) against the per-channel kernel
+"""The screening kernel (csrc/lsqfit_poly_screen.cu) and the warp-per-spectrum kernel
+(csrc/lsqfit_poly_warp.cu) against the per-channel kernel
 (csrc/lsqfit_poly.cu) and the oracle: a row the screening kernel finishes must carry exactly the
 clip decisions of the per-channel evaluation; rows it cannot decide are handed over."""
 import os
@@ -8,27 +9,27 @@ import pytest
 
 from sakura_b200 import synth
 from sakura_b200.capi import STATUS_OK
-from parity import compare_fit
+from parity import compare_fit, forced_kernel
 
 pytestmark = pytest.mark.gpu
 
 
-def fit(lib, order, data, mask, clip, nfit, screen, **want):
+KERNEL_NAME = {"screen": "poly_screen", "warp": "poly_warp", "channel": "poly_fast"}
+
+
+def fit(lib, order, data, mask, clip, nfit, which, **want):
+    """`which`: "screen" / "warp" / "channel" (True / False = screen / channel)."""
     st, ctx = lib.create_polynomial_context(order, data.shape[-1])
     assert st == STATUS_OK
-    old = os.environ.get("SAKURA_B200_POLY_SCREEN")
-    os.environ["SAKURA_B200_POLY_SCREEN"] = "1" if screen else "0"
-    try:
+    with forced_kernel(which):
         g = lib.lsqfit_polynomial_batch(ctx, order, data, mask, clip, nfit, **want)
         kernel = lib.last_kernel_name()
         handed = lib.last_handover_count(ctx)
-    finally:
-        if old is None:
-            del os.environ["SAKURA_B200_POLY_SCREEN"]
-        else:
-            os.environ["SAKURA_B200_POLY_SCREEN"] = old
     lib.destroy_context(ctx)
     return g, kernel, handed
+
+
+FAST = ["screen", "warp"]
 
 
 def assert_same(a, b, data, loose=False):
@@ -61,54 +62,62 @@ def assert_same(a, b, data, loose=False):
     assert np.all(np.abs(ca - cb) <= (1e-3 if loose else 1e-7) * np.abs(cb) + (1e-4 if loose else 1e-12) * scale)
 
 
-@pytest.mark.parametrize("n,order,nfit", [(4096, 5, 5), (4096, 5, 3), (4096, 5, 2), (4096, 5, 1),
-                                           (4096, 0, 4), (4096, 1, 4), (4096, 3, 6), (4096, 7, 3),
-                                           (8192, 5, 5), (8192, 2, 3)])
-def test_screen_equals_per_channel_kernel(lib, oracle, n, order, nfit):
+@pytest.mark.parametrize("which,n,order,nfit",
+                         [("screen", n, o, f) for n, o, f in [(4096, 5, 5), (4096, 5, 3), (4096, 5, 2), (4096, 5, 1),
+                                                              (4096, 0, 4), (4096, 1, 4), (4096, 3, 6), (4096, 7, 3),
+                                                              (8192, 5, 5), (8192, 2, 3)]]
+                         + [("warp", n, o, f) for n, o, f in [(4096, 5, 5), (4096, 5, 3), (4096, 5, 2), (4096, 5, 1),
+                                                              (4096, 0, 4), (4096, 1, 4), (4096, 2, 7), (4096, 3, 6),
+                                                              (4096, 4, 5), (4096, 6, 4), (4096, 7, 3),
+                                                              (2048, 5, 5), (2048, 2, 3), (2048, 7, 4), (2048, 0, 2)]])
+def test_screen_equals_per_channel_kernel(lib, oracle, which, n, order, nfit):
     rows = 768
     data, mask = synth.make_spectra(rows, n, seed=100 + order + nfit)
     synth.add_edge_case_rows(data, mask, order + 1)
-    s, kernel, handed = fit(lib, order, data, mask, 3.0, nfit, True, want_best_fit=True)
-    assert kernel == "poly_screen"
-    p, kernel, _ = fit(lib, order, data, mask, 3.0, nfit, False, want_best_fit=True)
+    s, kernel, handed = fit(lib, order, data, mask, 3.0, nfit, which, want_best_fit=True)
+    assert kernel == KERNEL_NAME[which]
+    p, kernel, _ = fit(lib, order, data, mask, 3.0, nfit, "channel", want_best_fit=True)
     assert kernel == "poly_fast"
     assert_same(s, p, data, loose=order >= 6)
     # the edge-case rows (constant data, exactly K valid channels, ...) are handed over by design;
     # ordinary rows almost never are
     # (orders 6 and 7: the monomial coefficients are large, the FP64 slack terms of the bounds grow
     # with their squares and more rows are handed over)
-    assert 0 <= handed <= 16 + rows // (10 if order >= 6 else 50), handed
+    assert 0 <= handed <= 16 + rows // (5 if order >= 6 else 50), handed
     if order <= 5:
         o = oracle.lsqfit_polynomial_batch(order, data, mask, 3.0, nfit, want_best_fit=True)
         reported = compare_fit(s, o, data, 3.0, poly_rescale_n=n)
         assert reported == [], reported
 
 
+@pytest.mark.parametrize("which", FAST)
 @pytest.mark.parametrize("scale,offset", [(1.0, 1000.0), (1e-6, 0.0), (1e6, 3e7), (1e-20, 0.0), (1.0, 1e6)])
-def test_screen_scales_and_offsets(lib, scale, offset):
+def test_screen_scales_and_offsets(lib, which, scale, offset):
     """Large offsets widen the float-rounding band (more hand-overs, same results); tiny scales
     push the thresholds below the underflow guard (every row handed over)."""
     data, mask = synth.make_spectra(256, 4096, seed=77)
     data = (data * np.float32(scale) + np.float32(offset)).astype(np.float32)
-    s, kernel, handed = fit(lib, 5, data, mask, 3.0, 5, True)
-    assert kernel == "poly_screen"
-    p, _, _ = fit(lib, 5, data, mask, 3.0, 5, False)
+    s, kernel, handed = fit(lib, 5, data, mask, 3.0, 5, which)
+    assert kernel == KERNEL_NAME[which]
+    p, _, _ = fit(lib, 5, data, mask, 3.0, 5, "channel")
     assert_same(s, p, data)
     if scale == 1e-20:
         assert handed == 256
 
 
+@pytest.mark.parametrize("which", FAST)
 @pytest.mark.parametrize("clip", [0.5, 1.5, 2.5, 6.0])
-def test_screen_clip_levels(lib, clip):
+def test_screen_clip_levels(lib, which, clip):
     """Low thresholds clip a large part of the row per pass (long clipped lists, several rounds
     per warp); many iterations exercise the stale passes."""
     data, mask = synth.make_spectra(128, 4096, seed=int(clip * 10))
-    s, _, handed = fit(lib, 4, data, mask, clip, 12, True)
-    p, _, _ = fit(lib, 4, data, mask, clip, 12, False)
+    s, _, handed = fit(lib, 4, data, mask, clip, 12, which)
+    p, _, _ = fit(lib, 4, data, mask, clip, 12, "channel")
     assert_same(s, p, data)
 
 
-def test_screen_dense_flags_and_runs(lib):
+@pytest.mark.parametrize("which", FAST)
+def test_screen_dense_flags_and_runs(lib, which):
     """Rows with most channels flagged (direct power sums instead of the complement), long
     flagged runs, rows that run out of channels while clipping."""
     rng = np.random.default_rng(5)
@@ -118,14 +127,17 @@ def test_screen_dense_flags_and_runs(lib):
         a = int(rng.integers(0, 3000))
         mask[r, a:a + int(rng.integers(300, 1000))] = False
     mask[128:160] &= rng.random((32, 4096)) < 0.004   # ~16 valid channels: clipping exhausts them
-    s, _, handed = fit(lib, 5, data, mask, 3.0, 6, True, want_best_fit=True)
-    p, _, _ = fit(lib, 5, data, mask, 3.0, 6, False, want_best_fit=True)
+    s, _, handed = fit(lib, 5, data, mask, 3.0, 6, which, want_best_fit=True)
+    p, _, _ = fit(lib, 5, data, mask, 3.0, 6, "channel", want_best_fit=True)
     assert_same(s, p, data)
     assert (s["status"] != 0).sum() == (p["status"] != 0).sum()
 
 
-@pytest.mark.parametrize("rows,n,nfit,clip", [(1 << 17, 4096, 5, 3.0), (1 << 16, 4096, 9, 2.5), (1 << 15, 8192, 6, 3.0)])
-def test_screen_large_device_batches(lib, rows, n, nfit, clip):
+@pytest.mark.parametrize("which,rows,n,nfit,clip", [("screen", 1 << 17, 4096, 5, 3.0), ("screen", 1 << 16, 4096, 9, 2.5),
+                                                    ("screen", 1 << 15, 8192, 6, 3.0), ("warp", 1 << 17, 4096, 5, 3.0),
+                                                    ("warp", 1 << 16, 4096, 9, 2.5), ("warp", 1 << 17, 2048, 6, 3.0),
+                                                    ("warp", 1 << 16, 4096, 2, 3.5)])
+def test_screen_large_device_batches(lib, which, rows, n, nfit, clip):
     """Device-resident batches: identical clip decisions with and without screening on every row,
     bit-identical results from run to run (fixed reduction orders, no atomics in the data path)."""
     import torch
@@ -135,21 +147,14 @@ def test_screen_large_device_batches(lib, rows, n, nfit, clip):
     data, mask = bench.generate_on_device(torch, rows, n, seed=rows + nfit, device=torch.device("cuda", 0))
     st, ctx = lib.create_polynomial_context(5, n)
     assert st == STATUS_OK
-    old = os.environ.get("SAKURA_B200_POLY_SCREEN")
-    try:
-        os.environ["SAKURA_B200_POLY_SCREEN"] = "1"
+    with forced_kernel(which):
         a = dev.polynomial(ctx, 5, data, mask, clip, nfit)
-        assert lib.last_kernel_name() == "poly_screen"
+        assert lib.last_kernel_name() == KERNEL_NAME[which]
         handed = lib.last_handover_count(ctx)
         b = dev.polynomial(ctx, 5, data, mask, clip, nfit)
-        os.environ["SAKURA_B200_POLY_SCREEN"] = "0"
+    with forced_kernel("channel"):
         c = dev.polynomial(ctx, 5, data, mask, clip, nfit)
         assert lib.last_kernel_name() == "poly_fast"
-    finally:
-        if old is None:
-            del os.environ["SAKURA_B200_POLY_SCREEN"]
-        else:
-            os.environ["SAKURA_B200_POLY_SCREEN"] = old
     lib.destroy_context(ctx)
     assert 0 <= handed <= rows // 200, handed
     for key in ("final_mask", "status", "lsqfit_status", "rms", "coeff", "residual"):
@@ -160,7 +165,8 @@ def test_screen_large_device_batches(lib, rows, n, nfit, clip):
     assert rel <= 1e-6, rel
 
 
-def test_screen_non_finite_and_degenerate_rows(lib):
+@pytest.mark.parametrize("which", FAST)
+def test_screen_non_finite_and_degenerate_rows(lib, which):
     """NaN / Inf in a valid channel, constant rows, rows of zeros, huge and denormal values: the
     screening kernel must hand such rows over (or decide them identically); whatever the
     per-channel kernel produces for them is what comes out."""
@@ -177,9 +183,9 @@ def test_screen_non_finite_and_degenerate_rows(lib):
     data[15] *= np.float32(1e-42)
     data[17, ::2] = 0.0                       # half of the row exactly on the model
     data[19] = np.arange(4096, dtype=np.float32)  # exactly polynomial: residual is rounding noise
-    s, kernel, handed = fit(lib, 5, data, mask, 3.0, 5, True, want_best_fit=True)
-    assert kernel == "poly_screen"
-    p, _, _ = fit(lib, 5, data, mask, 3.0, 5, False, want_best_fit=True)
+    s, kernel, handed = fit(lib, 5, data, mask, 3.0, 5, which, want_best_fit=True)
+    assert kernel == KERNEL_NAME[which]
+    p, _, _ = fit(lib, 5, data, mask, 3.0, 5, "channel", want_best_fit=True)
     assert np.array_equal(s["status"], p["status"])
     assert np.array_equal(s["lsqfit_status"], p["lsqfit_status"])
     assert np.array_equal(s["final_mask"], p["final_mask"])

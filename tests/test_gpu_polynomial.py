@@ -32,7 +32,7 @@ def test_config_c1_1024x4096_poly5_3fits(lib, oracle):
     data, mask = synth.make_spectra(1024, 4096)
     names = synth.add_edge_case_rows(data, mask, 6)
     g, o, kernel = run_both(lib, oracle, 5, data, mask, 3.0, 3, want_best_fit=True)
-    assert kernel == "poly_screen"  # screening from three fits on
+    assert kernel == "poly_warp"  # the warp-per-spectrum kernel from two fits on
     reported = compare_fit(g, o, data, 3.0, poly_rescale_n=4096)
     assert reported == [], reported
     assert g["status"][names["K_minus_1"]] == STATUS_NG
@@ -53,7 +53,7 @@ def test_orders_fast_path(lib, oracle, order):
     data, mask = synth.make_spectra(96, 2048, seed=10 + order)
     synth.add_edge_case_rows(data, mask, order + 1)
     g, o, kernel = run_both(lib, oracle, order, data, mask, 3.0, 4, want_best_fit=True)
-    assert kernel == "poly_fast"
+    assert kernel == "poly_warp"
     # cond(G) grows ~30x per order in the monomial basis (1.5e7 at order 5, ~1e10 at order 7):
     # the O(eps) differences in G (power sums / downdates vs the reference's sums) move the
     # model by cond*eps on rows with flagged gaps, so the band is widened for orders 6 and 7
@@ -69,7 +69,7 @@ def test_channel_counts(lib, oracle, n):
     data, mask = synth.make_spectra(8, n, seed=n)
     if n % 32 == 0:
         g, o, kernel = run_both(lib, oracle, order, data, mask, 3.0, 3)
-        assert kernel == ("poly_screen" if n in (4096, 8192) else "poly_fast" if n <= 8192 else "general")
+        assert kernel == ("poly_warp" if n in (2048, 4096) else "poly_screen" if n == 8192 else "poly_fast" if n <= 8192 else "general")
         compare_fit(g, o, data, 3.0, poly_rescale_n=n)
     else:
         st, ctx = lib.create_polynomial_context(order, n)
