@@ -136,6 +136,12 @@ class Oracle:
             _ptr(res["rms"]), _ptr(res["status"]), _ptr(res["lsqfit_status"]), nthreads)
         if rc != 0:
             raise RuntimeError("oracle: context creation failed")
+        # the same fit of one row with another iteration count (tests/parity.py: threshold of the
+        # iteration at which a clip decision diverged)
+        res["refit"] = lambda row, nfit: self.lsqfit_polynomial_batch(
+            order, data[row], mask[row], clip_threshold_sigma, nfit, num_coeff=num_coeff,
+            lsqfit_type=lsqfit_type, context_order=context_order, want_coeff=False)
+        res["num_fitting_max"] = num_fitting_max
         return res
 
     def lsqfit_cubicspline_batch(self, num_pieces: int, data, mask, clip_threshold_sigma: float,
@@ -154,6 +160,10 @@ class Oracle:
             _ptr(res["boundary"]), _ptr(res["status"]), _ptr(res["lsqfit_status"]), nthreads)
         if rc != 0:
             raise RuntimeError("oracle: context creation failed")
+        res["refit"] = lambda row, nfit: self.lsqfit_cubicspline_batch(
+            num_pieces, data[row], mask[row], clip_threshold_sigma, nfit, context_npiece=context_npiece,
+            want_coeff=False)
+        res["num_fitting_max"] = num_fitting_max
         return res
 
     def lsqfit_sinusoid_batch(self, nwave: Sequence[int], data, mask, clip_threshold_sigma: float,
@@ -174,6 +184,10 @@ class Oracle:
             _ptr(res["rms"]), _ptr(res["status"]), _ptr(res["lsqfit_status"]), nthreads)
         if rc != 0:
             raise RuntimeError("oracle: context creation failed")
+        res["refit"] = lambda row, nfit: self.lsqfit_sinusoid_batch(
+            nwave, data[row], mask[row], clip_threshold_sigma, nfit, num_coeff=num_coeff,
+            context_nwave=context_nwave, want_coeff=False)
+        res["num_fitting_max"] = num_fitting_max
         return res
 
     def calibrate_batch(self, scaling, data, reference, in_place: bool = False):

@@ -261,6 +261,15 @@ cudaError_t LaunchInterpolate(InterpolateParams const &p, int num_sms, cudaStrea
 		}
 		size_t const smem = (p.num_base + 1) * kTableThreads * sizeof(IntervalEntry)
 				+ kTableThreads * (sizeof(double) + sizeof(int));
+		// 15 base points need 50 688 bytes: above the 48 KiB a kernel gets without opting in (set on every
+		// launch: the attribute is per device and a process may drive several)
+		cudaError_t const attr = cudaFuncSetAttribute(InterpolateYTableKernel,
+				cudaFuncAttributeMaxDynamicSharedMemorySize,
+				static_cast<int>((kTableMaxBase + 1) * kTableThreads * sizeof(IntervalEntry)
+						+ kTableThreads * (sizeof(double) + sizeof(int))));
+		if (attr != cudaSuccess) {
+			return attr;
+		}
 		InterpolateYTableKernel<<<dim3(static_cast<unsigned>(tbx), static_cast<unsigned>(tby)), kTableThreads,
 				smem, stream>>>(p);
 		return cudaGetLastError();

@@ -20,26 +20,47 @@ def residual_tolerance(ref_residual, data):
 
 
 def check_mask_parity(g, o, data, clip, good):
-    """Returns the list of (row, channel) mismatches; asserts each is a near-threshold channel."""
+    """Returns the list of final_mask mismatches as (row, channel, iteration, residual, threshold).
+    north_star: a mismatch is tolerated only where the residual lay within 1e-5 relative of the clip
+    threshold AT THE ITERATION WHERE THE DECISIONS DIVERGED. That iteration's residual and threshold
+    are recomputed on the oracle side: the oracle refits the row with 1, 2, ... fits (with j fits it
+    returns the residual and rms of fit j, whose thresholds clip_sigma * rms drive clip j) and the
+    channel must sit on the threshold of one of them. Every mismatch is printed."""
     gm = g["final_mask"][good]
     om = o["final_mask"][good]
     bad = np.argwhere(gm != om)
     reported = []
     rows = np.nonzero(good)[0]
+    refit = o.get("refit")
+    nfit = int(o.get("num_fitting_max", 0))
     for r, ch in bad:
-        rr = rows[r]
-        resid = float(o["residual"][rr, ch]) if o.get("residual") is not None else np.nan
-        thr = clip * float(o["rms"][rr])
-        reported.append((int(rr), int(ch), resid, thr))
-        # the divergence happened at some iteration's threshold; the final threshold is within
-        # a few per cent of it, so use a loose band here and print the channel
-        assert abs(abs(resid) - thr) <= 0.2 * thr, f"mask mismatch far from threshold: {reported[-1]}"
+        rr = int(rows[r])
+        best = None
+        if refit is not None:
+            for j in range(1, max(nfit, 2)):
+                oj = refit(rr, j)
+                if oj["status"][0] != OK:
+                    break
+                resid = float(oj["residual"][0, ch])
+                thr = clip * float(oj["rms"][0])
+                rel = abs(abs(resid) - thr) / thr if thr > 0 else np.inf
+                if best is None or rel < best[0]:
+                    best = (rel, j, resid, thr)
+        else:  # (no refit available: the final threshold is the only one there is)
+            resid = float(o["residual"][rr, ch]) if o.get("residual") is not None else np.nan
+            thr = clip * float(o["rms"][rr])
+            best = (abs(abs(resid) - thr) / thr, nfit, resid, thr)
+        entry = (rr, int(ch), best[1], best[2], best[3])
+        reported.append(entry)
+        print(f"final_mask mismatch: row {rr} channel {int(ch)} iteration {best[1]} residual {best[2]!r} "
+              f"threshold {best[3]!r} relative distance {best[0]:.3e}")
+        assert best[0] <= 1e-5, f"mask mismatch not on a clip threshold (1e-5 relative): {entry}"
     assert len(bad) <= max(2, int(1e-6 * gm.size)), f"{len(bad)} final_mask mismatches: {reported[:10]}"
     return reported
 
 
 def compare_fit(g, o, data, clip, poly_rescale_n=None, coeff_rtol=1e-5, coeff_atol=1e-6,
-                check_coeff=True, resid_atol=0.0):
+                check_coeff=True, resid_atol=0.0, allow_threshold_flips=False):
     """`resid_atol` widens the residual/best_fit band for ill-conditioned bases (cubic splines:
     two builds of the reference itself differ by 3.8e-6 there)."""
     assert g["call_status"] == OK
@@ -47,8 +68,10 @@ def compare_fit(g, o, data, clip, poly_rescale_n=None, coeff_rtol=1e-5, coeff_at
     assert np.array_equal(g["lsqfit_status"], o["lsqfit_status"])
     good = o["status"] == OK
     reported = check_mask_parity(g, o, data, clip, good)
+    # no test input sits on a threshold by construction: a flip, even a tolerated one, is a finding
+    assert allow_threshold_flips or reported == [], reported
     exact_rows = good.copy()
-    for r, _, _, _ in reported:
+    for r, *_ in reported:
         exact_rows[r] = False  # a flipped channel legitimately perturbs that row's fit
     # rows that failed keep their outputs untouched (NaN-prefilled by the bindings)
     failed = ~good

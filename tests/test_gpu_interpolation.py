@@ -42,6 +42,20 @@ def test_random_masked_problems_against_oracle(lib, oracle, base_desc, interp_de
                 assert np.array_equal(g.view(np.uint32), o.view(np.uint32)), (nb, na, method, axis)
 
 
+@pytest.mark.parametrize("nb", [12, 13, 14, 15, 16, 17])
+def test_y_axis_table_kernel_boundary(lib, oracle, nb):
+    """The per-array interval table of the Y-axis kernel is used up to 15 base points, where it needs
+    more than 48 KiB of shared memory (opt-in attribute); 16 and 17 go through the bisection kernel."""
+    rng = np.random.default_rng(100 + nb)
+    xb, yb, mb, xi = random_problem(rng, nb, 300, 257, False, False, 0.9)
+    for method in (NEAREST, LINEAR):
+        g, gm, sg = lib.interpolate("y", method, xb, yb, mb, xi)
+        o, om, so = oracle.interpolate("y", method, xb, yb, mb, xi)
+        assert sg == so == 0, lib.last_error()
+        assert np.array_equal(gm, om)
+        assert np.array_equal(g.view(np.uint32), o.view(np.uint32))
+
+
 def test_argument_rules(lib):
     L = lib.lib
     xb = aligned_copy(np.array([0.0, 1.0]))

@@ -92,7 +92,7 @@ def test_screen_equals_per_channel_kernel(lib, oracle, which, n, order, nfit):
 
 @pytest.mark.parametrize("which", FAST)
 @pytest.mark.parametrize("scale,offset", [(1.0, 1000.0), (1e-6, 0.0), (1e6, 3e7), (1e-20, 0.0), (1.0, 1e6)])
-def test_screen_scales_and_offsets(lib, which, scale, offset):
+def test_screen_scales_and_offsets(lib, oracle, which, scale, offset):
     """Large offsets widen the float-rounding band (more hand-overs, same results); tiny scales
     push the thresholds below the underflow guard (every row handed over)."""
     data, mask = synth.make_spectra(256, 4096, seed=77)
@@ -101,23 +101,50 @@ def test_screen_scales_and_offsets(lib, which, scale, offset):
     assert kernel == KERNEL_NAME[which]
     p, _, _ = fit(lib, 5, data, mask, 3.0, 5, "channel")
     assert_same(s, p, data)
+    # ... and both against the reference itself (status, final_mask bit-exact; the value gates scale with
+    # the data: 1e-5 relative, one float ulp of the model)
+    o = oracle.lsqfit_polynomial_batch(5, data, mask, 3.0, 5)
+    for got in (s, p):
+        assert np.array_equal(got["status"], o["status"])
+        assert np.array_equal(got["lsqfit_status"], o["lsqfit_status"])
+        assert np.array_equal(got["final_mask"], o["final_mask"]), int((got["final_mask"] != o["final_mask"]).sum())
+        good = o["status"] == 0
+        # (1e-6 relative; with an offset of 1e6 one float ulp of the data is 0.06 sigma and the float model
+        # of a few channels per row rounds the other way: the ulp-of-data floor of tests/parity.py)
+        floor = 2.4e-7 * np.abs(data[good]).max(axis=1)
+        assert np.all(np.abs(got["rms"][good].astype(np.float64) - o["rms"][good]) <= 1e-6 * o["rms"][good] + floor)
+        model = np.abs(data[good].astype(np.float64) - o["residual"][good])
+        tol = 1e-5 * np.abs(o["residual"][good].astype(np.float64)) + 2.4e-7 * model
+        assert np.all(np.abs(got["residual"][good].astype(np.float64) - o["residual"][good]) <= tol)
     if scale == 1e-20:
         assert handed == 256
 
 
 @pytest.mark.parametrize("which", FAST)
 @pytest.mark.parametrize("clip", [0.5, 1.5, 2.5, 6.0])
-def test_screen_clip_levels(lib, which, clip):
+def test_screen_clip_levels(lib, oracle, which, clip):
     """Low thresholds clip a large part of the row per pass (long clipped lists, several rounds
     per warp); many iterations exercise the stale passes."""
     data, mask = synth.make_spectra(128, 4096, seed=int(clip * 10))
     s, _, handed = fit(lib, 4, data, mask, clip, 12, which)
     p, _, _ = fit(lib, 4, data, mask, clip, 12, "channel")
     assert_same(s, p, data)
+    # ... and against the reference. At clip 0.5 a pass removes 60 % of the channels that are left: after
+    # six passes a row is down to a dozen channels, the quartic interpolates them and the "residual" is the
+    # rounding noise of the model, so what 0.5 x rms(noise) clips is no longer a property of the data. The
+    # reference comparison therefore stops after four fits there (~230 channels left); the kernels are
+    # compared with each other over all twelve above.
+    nfit_ref = 4 if clip < 1.0 else 12
+    if nfit_ref != 12:
+        s, _, _ = fit(lib, 4, data, mask, clip, nfit_ref, which)
+        p, _, _ = fit(lib, 4, data, mask, clip, nfit_ref, "channel")
+    o = oracle.lsqfit_polynomial_batch(4, data, mask, clip, nfit_ref)
+    compare_fit(s, o, data, clip, poly_rescale_n=4096)
+    compare_fit(p, o, data, clip, poly_rescale_n=4096)
 
 
 @pytest.mark.parametrize("which", FAST)
-def test_screen_dense_flags_and_runs(lib, which):
+def test_screen_dense_flags_and_runs(lib, oracle, which):
     """Rows with most channels flagged (direct power sums instead of the complement), long
     flagged runs, rows that run out of channels while clipping."""
     rng = np.random.default_rng(5)
@@ -131,6 +158,9 @@ def test_screen_dense_flags_and_runs(lib, which):
     p, _, _ = fit(lib, 5, data, mask, 3.0, 6, "channel", want_best_fit=True)
     assert_same(s, p, data)
     assert (s["status"] != 0).sum() == (p["status"] != 0).sum()
+    o = oracle.lsqfit_polynomial_batch(5, data, mask, 3.0, 6, want_best_fit=True)
+    compare_fit(s, o, data, 3.0, poly_rescale_n=4096)
+    compare_fit(p, o, data, 3.0, poly_rescale_n=4096)
 
 
 @pytest.mark.parametrize("which,rows,n,nfit,clip", [("screen", 1 << 17, 4096, 5, 3.0), ("screen", 1 << 16, 4096, 9, 2.5),
@@ -166,7 +196,7 @@ def test_screen_large_device_batches(lib, which, rows, n, nfit, clip):
 
 
 @pytest.mark.parametrize("which", FAST)
-def test_screen_non_finite_and_degenerate_rows(lib, which):
+def test_screen_non_finite_and_degenerate_rows(lib, oracle, which):
     """NaN / Inf in a valid channel, constant rows, rows of zeros, huge and denormal values: the
     screening kernel must hand such rows over (or decide them identically); whatever the
     per-channel kernel produces for them is what comes out."""
@@ -196,3 +226,21 @@ def test_screen_non_finite_and_degenerate_rows(lib, which):
         with np.errstate(over="ignore"):
             assert np.array_equal(np.nan_to_num(a).view(np.uint8), np.nan_to_num(b).view(np.uint8)), key
     assert handed >= len(special) - 1
+    # the reference itself on the same rows: statuses and clip decisions bit-exact, NaN where it has NaN
+    # (a NaN / Inf in a valid channel poisons the normal equations: Eigen's full-pivot LU then decides what
+    # comes out, the per-channel kernel restates that LU)
+    o = oracle.lsqfit_polynomial_batch(5, data, mask, 3.0, 5, want_best_fit=True)
+    for got in (s, p):
+        assert np.array_equal(got["status"], o["status"]), (got["status"][special], o["status"][special])
+        assert np.array_equal(got["lsqfit_status"], o["lsqfit_status"])
+        assert np.array_equal(got["final_mask"], o["final_mask"]), np.argwhere(got["final_mask"] != o["final_mask"])[:8]
+        for key in ("rms", "residual", "best_fit"):
+            assert np.array_equal(np.isnan(got[key]), np.isnan(o[key])), key
+    ordinary = np.ones(data.shape[0], dtype=bool)
+    ordinary[special + [17]] = False
+    sub = lambda d: {k: (v[ordinary] if isinstance(v, np.ndarray) else v) for k, v in d.items()}
+    so = sub(o)
+    so.pop("refit")
+    gs = sub(s)
+    gs["call_status"] = 0
+    compare_fit(gs, so, data[ordinary], 3.0, poly_rescale_n=4096)
