@@ -12,12 +12,13 @@ import os
 import shutil
 import subprocess
 import sys
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsakura_b200.so")
 
-CUDA_SOURCES = ["capi.cu", "lsqfit_general.cu", "lsqfit_poly.cu", "lsqfit_poly_screen.cu", "lsqfit_poly_warp.cu", "statistics.cu",
+CUDA_SOURCES = ["capi_core.cu", "capi_fit.cu", "capi_filters.cu", "capi_stats.cu", "lsqfit_general.cu", "lsqfit_poly.cu", "lsqfit_poly_screen.cu", "lsqfit_poly_warp.cu", "statistics.cu",
                 "lsq_blocks.cu", "lsqfit_sinusoid.cu", "lsqfit_spline.cu", "calibration.cu", "bool_filters.cu", "interpolation.cu"]
 HOST_SOURCES = ["basis_tables.cc"]
 
@@ -72,8 +73,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(" ".join(cmd))
         subprocess.run(cmd, check=True)
         objs.append(obj)
-    for src in CUDA_SOURCES:
+    def compile_cuda(src: str) -> str:
         obj = os.path.join(objdir, src + ".o")
+        # a source whose object is newer than every source file (headers included) is not recompiled
+        newest = max(headers_mtime, os.path.getmtime(os.path.join(CSRC, src)))
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) >= newest:
+            return obj
         cmd = [nvcc, "-ccbin", cxx] + NVCC_FLAGS + ["-Xptxas", "-v", "-c",
                                                     os.path.join(CSRC, src), "-o", obj]
         if verbose:
@@ -86,7 +91,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
             raise RuntimeError("nvcc failed on " + src)
         if verbose:
             sys.stderr.write(res.stderr)
-        objs.append(obj)
+        return obj
+
+    headers_mtime = max([os.path.getmtime(os.path.abspath(__file__))]
+                        + [os.path.getmtime(os.path.join(root, name))
+                           for root in (CSRC, os.path.join(HERE, "..", "include")) for name in os.listdir(root)
+                           if name.endswith((".h", ".cuh"))])
+    with ThreadPoolExecutor(max_workers=min(len(CUDA_SOURCES), os.cpu_count() or 4)) as pool:
+        objs += list(pool.map(compile_cuda, CUDA_SOURCES))
     tmp = LIB + ".tmp"
     cmd = [nvcc, "-ccbin", cxx, "-gencode", "arch=compute_100a,code=sm_100a", "-shared",
            "-cudart", "static", "-o", tmp] + objs

@@ -1,0 +1,977 @@
+// C ABI of libsakura_b200.so, part 2: the least-squares fit entry points (host-pointer batches with the
+// copy/compute pipeline, device-array batches, the reference's single-row signatures, Subtract*).
+#include "capi_internal.cuh"
+
+using namespace sakura_b200;
+using namespace sakura_b200::capi;
+
+namespace {
+
+// Host-pointer batch: stage through device buffers owned by the context.
+struct HostFitArgs {
+	float const *data;
+	bool const *mask;
+	double *coeff;
+	float *best_fit;
+	float *residual;
+	bool *final_mask;
+	float *rms;
+	int32_t *status;
+	int32_t *lsq;
+	size_t *boundary;
+};
+
+sakura_Status RunHostBatchSerial(Context *c, FitCall f, HostFitArgs const &h);
+
+/** Row-strided copy; a single 1-D copy when both sides are tightly packed (faster on the
+ *  copy engines than the pitched form). */
+cudaError_t CopyRows(void *dst, size_t dpitch, void const *src, size_t spitch, size_t width,
+		size_t rows, cudaMemcpyKind kind, cudaStream_t stream) {
+	if (dpitch == width && spitch == width) {
+		return cudaMemcpyAsync(dst, src, width * rows, kind, stream);
+	}
+	return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, stream);
+}
+
+// Pipelined variant for the polynomial hot path: the batch is cut into chunks that cycle
+// through kPipelineSlots (stream, device buffers) slots, so that the host->device copy of
+// chunk i+1, the kernel of chunk i and the device->host copy of chunk i-1 overlap on the
+// copy engines and the SMs. With pinned host buffers every copy is truly asynchronous.
+sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
+	if (f.num_spectra == 0) {
+		return sakura_Status_kOK;
+	}
+	size_t const n = f.num_data;
+	size_t const R = f.num_spectra;
+	size_t const dstride = RoundUp(n, 32);
+	bool const fast = (f.type == kFitPolynomial || (f.type == kFitChebyshev && f.K <= 6))
+			&& PolyFastSupported(n, f.K, dstride, dstride,
+			nullptr, nullptr, nullptr, nullptr, nullptr);
+	// chunk size of the pipeline in MiB of data (tuning knob; default from measurements on B200)
+	static size_t const chunk_mib = []() -> size_t {
+		char const *e = getenv("SAKURA_B200_CHUNK_MIB");
+		long const v = (e != nullptr) ? atol(e) : 0;
+		return (v >= 1 && v <= 4096) ? static_cast<size_t>(v) : 96;
+	}();
+	size_t chunk_rows = (chunk_mib << 20) / (dstride * sizeof(float));
+	if (chunk_rows < 1) {
+		chunk_rows = 1;
+	}
+	if (!fast || R <= chunk_rows) {
+		return RunHostBatchSerial(c, f, h);
+	}
+	DeviceInfo info;
+	sakura_Status st = CurrentDevice(&info);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	if (c->device >= 0 && c->device != info.device) {
+		ReleaseDeviceState(c);
+	}
+	c->device = info.device;
+	if (c->slots == nullptr) {
+		c->slots = new PipelineSlot[kPipelineSlots];
+	}
+	size_t const hds = f.data_stride, hms = f.mask_stride;
+	size_t const num_chunks = (R + chunk_rows - 1) / chunk_rows;
+	for (int s = 0; s < kPipelineSlots; ++s) {
+		PipelineSlot &sl = c->slots[s];
+		if (sl.stream == nullptr) {
+			CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
+			CUDA_TRY(cudaStreamCreateWithFlags(&sl.down, cudaStreamNonBlocking));
+			CUDA_TRY(cudaEventCreateWithFlags(&sl.flags_ready, cudaEventDisableTiming));
+			CUDA_TRY(cudaEventCreateWithFlags(&sl.down_done, cudaEventDisableTiming));
+		}
+		CUDA_TRY(sl.data.Reserve(chunk_rows * dstride * sizeof(float)));
+		CUDA_TRY(sl.mask.Reserve(chunk_rows * dstride));
+		CUDA_TRY(sl.final_mask.Reserve(chunk_rows * dstride));
+		CUDA_TRY(sl.small.Reserve(chunk_rows * (sizeof(float) + 3 * sizeof(int32_t))));
+		if (h.coeff != nullptr) {
+			CUDA_TRY(sl.coeff.Reserve(chunk_rows * f.coeff_stride * sizeof(double)));
+		}
+		if (h.best_fit != nullptr) {
+			CUDA_TRY(sl.best_fit.Reserve(chunk_rows * dstride * sizeof(float)));
+		}
+		if (h.residual != nullptr) {
+			CUDA_TRY(sl.residual.Reserve(chunk_rows * dstride * sizeof(float)));
+		}
+		CUDA_TRY(sl.handover.Reserve((chunk_rows + 1) * sizeof(int32_t)));
+		sl.h_flags.resize(chunk_rows);
+		sl.rows = 0;
+	}
+	auto finish = [&](PipelineSlot &sl) -> sakura_Status {
+		// the kernel of this slot's chunk is done and its per-row flags are on the host
+		CUDA_TRY(cudaEventSynchronize(sl.flags_ready));
+		size_t const r0 = sl.row0, rows = sl.rows;
+		float *d_rms = sl.small.As<float>();
+		bool all_published = true;
+		for (size_t r = 0; r < rows; ++r) {
+			if ((sl.h_flags[r] & 3) != 3) {
+				all_published = false;
+				break;
+			}
+		}
+		if (all_published) {
+			if (h.coeff != nullptr) {
+				CUDA_TRY(cudaMemcpyAsync(h.coeff + r0 * f.coeff_stride, sl.coeff.ptr,
+						rows * f.coeff_stride * sizeof(double), cudaMemcpyDeviceToHost, sl.down));
+			}
+			if (h.best_fit != nullptr) {
+				CUDA_TRY(CopyRows(h.best_fit + r0 * hds, hds * sizeof(float), sl.best_fit.ptr,
+						dstride * sizeof(float), n * sizeof(float), rows, cudaMemcpyDeviceToHost,
+						sl.down));
+			}
+			if (h.residual != nullptr) {
+				CUDA_TRY(CopyRows(h.residual + r0 * hds, hds * sizeof(float), sl.residual.ptr,
+						dstride * sizeof(float), n * sizeof(float), rows, cudaMemcpyDeviceToHost,
+						sl.down));
+			}
+			CUDA_TRY(CopyRows(h.final_mask + r0 * hms, hms, sl.final_mask.ptr, dstride, n, rows,
+					cudaMemcpyDeviceToHost, sl.down));
+			CUDA_TRY(cudaMemcpyAsync(h.rms + r0, d_rms, rows * sizeof(float), cudaMemcpyDeviceToHost,
+					sl.down));
+		} else {
+			for (size_t r = 0; r < rows; ++r) {
+				int const fl = sl.h_flags[r];
+				if (fl & 1) {
+					if (h.coeff != nullptr) {
+						CUDA_TRY(cudaMemcpyAsync(h.coeff + (r0 + r) * f.coeff_stride,
+								sl.coeff.As<double>() + r * f.coeff_stride,
+								f.coeff_stride * sizeof(double), cudaMemcpyDeviceToHost, sl.down));
+					}
+					if (h.best_fit != nullptr) {
+						CUDA_TRY(cudaMemcpyAsync(h.best_fit + (r0 + r) * hds,
+								sl.best_fit.As<float>() + r * dstride, n * sizeof(float),
+								cudaMemcpyDeviceToHost, sl.down));
+					}
+					if (h.residual != nullptr) {
+						CUDA_TRY(cudaMemcpyAsync(h.residual + (r0 + r) * hds,
+								sl.residual.As<float>() + r * dstride, n * sizeof(float),
+								cudaMemcpyDeviceToHost, sl.down));
+					}
+					CUDA_TRY(cudaMemcpyAsync(h.rms + r0 + r, d_rms + r, sizeof(float),
+							cudaMemcpyDeviceToHost, sl.down));
+				}
+				if (fl & 2) {
+					CUDA_TRY(cudaMemcpyAsync(h.final_mask + (r0 + r) * hms,
+							sl.final_mask.As<uint8_t>() + r * dstride, n, cudaMemcpyDeviceToHost,
+							sl.down));
+				}
+			}
+		}
+		CUDA_TRY(cudaEventRecord(sl.down_done, sl.down));
+		sl.rows = 0;
+		return sakura_Status_kOK;
+	};
+	for (size_t ci = 0; ci < num_chunks; ++ci) {
+		PipelineSlot &sl = c->slots[ci % kPipelineSlots];
+		if (sl.rows != 0) {
+			st = finish(sl);
+			if (st != sakura_Status_kOK) {
+				return st;
+			}
+		}
+		size_t const r0 = ci * chunk_rows;
+		size_t const rows = (r0 + chunk_rows <= R) ? chunk_rows : (R - r0);
+		sl.row0 = r0;
+		sl.rows = rows;
+		float *d_rms = sl.small.As<float>();
+		int32_t *d_status = reinterpret_cast<int32_t *>(d_rms + chunk_rows);
+		int32_t *d_lsq = d_status + chunk_rows;
+		int32_t *d_flags = d_lsq + chunk_rows;
+		CUDA_TRY(CopyRows(sl.data.ptr, dstride * sizeof(float), h.data + r0 * hds,
+				hds * sizeof(float), n * sizeof(float), rows, cudaMemcpyHostToDevice, sl.stream));
+		CUDA_TRY(CopyRows(sl.mask.ptr, dstride, h.mask + r0 * hms, hms, n, rows,
+				cudaMemcpyHostToDevice, sl.stream));
+		// the kernel overwrites this slot's result buffers: wait for their previous download
+		CUDA_TRY(cudaStreamWaitEvent(sl.stream, sl.down_done, 0));
+		CUDA_TRY(cudaMemsetAsync(d_flags, 0, rows * sizeof(int32_t), sl.stream));
+		FitCall fc = f;
+		fc.num_spectra = rows;
+		fc.data = sl.data.As<float>();
+		fc.mask = sl.mask.As<uint8_t>();
+		fc.data_stride = dstride;
+		fc.mask_stride = dstride;
+		fc.coeff = h.coeff ? sl.coeff.As<double>() : nullptr;
+		fc.best_fit = h.best_fit ? sl.best_fit.As<float>() : nullptr;
+		fc.residual = h.residual ? sl.residual.As<float>() : nullptr;
+		fc.final_mask = sl.final_mask.As<uint8_t>();
+		fc.rms = d_rms;
+		fc.status = d_status;
+		fc.lsq = d_lsq;
+		fc.flags = d_flags;
+		fc.boundary = nullptr;
+		fc.handover = sl.handover.As<int32_t>();
+		st = LaunchFit(c, fc, sl.stream);
+		if (st != sakura_Status_kOK) {
+			return st;
+		}
+		CUDA_TRY(cudaMemcpyAsync(h.status + r0, d_status, rows * sizeof(int32_t),
+				cudaMemcpyDeviceToHost, sl.stream));
+		CUDA_TRY(cudaMemcpyAsync(h.lsq + r0, d_lsq, rows * sizeof(int32_t), cudaMemcpyDeviceToHost,
+				sl.stream));
+		CUDA_TRY(cudaMemcpyAsync(sl.h_flags.data(), d_flags, rows * sizeof(int32_t),
+				cudaMemcpyDeviceToHost, sl.stream));
+		CUDA_TRY(cudaEventRecord(sl.flags_ready, sl.stream));
+		CUDA_TRY(cudaStreamWaitEvent(sl.down, sl.flags_ready, 0));
+	}
+	for (size_t k = 0; k < static_cast<size_t>(kPipelineSlots); ++k) {
+		PipelineSlot &sl = c->slots[(num_chunks + k) % kPipelineSlots];
+		if (sl.rows != 0) {
+			st = finish(sl);
+			if (st != sakura_Status_kOK) {
+				return st;
+			}
+		}
+	}
+	for (int s = 0; s < kPipelineSlots; ++s) {
+		CUDA_TRY(cudaStreamSynchronize(c->slots[s].stream));
+		CUDA_TRY(cudaStreamSynchronize(c->slots[s].down));
+	}
+	return sakura_Status_kOK;
+}
+
+sakura_Status RunHostBatchSerial(Context *c, FitCall f, HostFitArgs const &h) {
+	if (f.num_spectra == 0) {
+		return sakura_Status_kOK;
+	}
+	cudaStream_t const stream = 0;
+	size_t const n = f.num_data;
+	size_t const R = f.num_spectra;
+	size_t const dstride = RoundUp(n, 32);
+	size_t const hds = f.data_stride, hms = f.mask_stride;
+	size_t const nb = f.npiece + 1;
+	bool const spline = (f.type == kFitCubicSpline);
+
+	CUDA_TRY(c->s_data.Reserve(R * dstride * sizeof(float)));
+	CUDA_TRY(c->s_mask.Reserve(R * dstride));
+	CUDA_TRY(c->s_final_mask.Reserve(R * dstride));
+	CUDA_TRY(c->s_rms.Reserve(R * sizeof(float)));
+	CUDA_TRY(c->s_status.Reserve(R * sizeof(int32_t)));
+	CUDA_TRY(c->s_lsq.Reserve(R * sizeof(int32_t)));
+	CUDA_TRY(c->s_flags.Reserve(R * sizeof(int32_t)));
+	if (h.coeff != nullptr) {
+		CUDA_TRY(c->s_coeff.Reserve(R * f.coeff_stride * sizeof(double)));
+	}
+	if (h.best_fit != nullptr) {
+		CUDA_TRY(c->s_best_fit.Reserve(R * dstride * sizeof(float)));
+	}
+	if (h.residual != nullptr) {
+		CUDA_TRY(c->s_residual.Reserve(R * dstride * sizeof(float)));
+	}
+	if (spline) {
+		CUDA_TRY(c->s_boundary.Reserve(R * nb * sizeof(unsigned long long)));
+	}
+	CUDA_TRY(cudaMemcpy2DAsync(c->s_data.ptr, dstride * sizeof(float), h.data, hds * sizeof(float),
+			n * sizeof(float), R, cudaMemcpyHostToDevice, stream));
+	CUDA_TRY(cudaMemcpy2DAsync(c->s_mask.ptr, dstride, h.mask, hms, n, R, cudaMemcpyHostToDevice,
+			stream));
+	CUDA_TRY(cudaMemsetAsync(c->s_flags.ptr, 0, R * sizeof(int32_t), stream));
+
+	f.data = c->s_data.As<float>();
+	f.mask = c->s_mask.As<uint8_t>();
+	f.data_stride = dstride;
+	f.mask_stride = dstride;
+	f.coeff = h.coeff ? c->s_coeff.As<double>() : nullptr;
+	f.best_fit = h.best_fit ? c->s_best_fit.As<float>() : nullptr;
+	f.residual = h.residual ? c->s_residual.As<float>() : nullptr;
+	f.final_mask = c->s_final_mask.As<uint8_t>();
+	f.rms = c->s_rms.As<float>();
+	f.status = c->s_status.As<int32_t>();
+	f.lsq = c->s_lsq.As<int32_t>();
+	f.flags = c->s_flags.As<int32_t>();
+	f.boundary = spline ? c->s_boundary.As<unsigned long long>() : nullptr;
+
+	sakura_Status st = LaunchFit(c, f, stream);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	if (c->h_flags == nullptr) {
+		c->h_flags = new std::vector<int32_t>();
+	}
+	std::vector<int32_t> &flags = *c->h_flags;
+	flags.resize(R);
+	CUDA_TRY(cudaMemcpyAsync(h.status, f.status, R * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+	CUDA_TRY(cudaMemcpyAsync(h.lsq, f.lsq, R * sizeof(int32_t), cudaMemcpyDeviceToHost, stream));
+	CUDA_TRY(cudaMemcpyAsync(flags.data(), f.flags, R * sizeof(int32_t), cudaMemcpyDeviceToHost,
+			stream));
+	CUDA_TRY(cudaStreamSynchronize(stream));
+
+	// Row flags (set by the kernels): bit0 = results published, bit1 = final_mask written,
+	// bit2 = boundary written.
+	bool all_published = true;
+	for (size_t r = 0; r < R; ++r) {
+		if ((flags[r] & 7) != (spline ? 7 : 3)) {
+			all_published = false;
+			break;
+		}
+	}
+	if (all_published) {
+		if (h.coeff != nullptr) {
+			CUDA_TRY(cudaMemcpyAsync(h.coeff, f.coeff, R * f.coeff_stride * sizeof(double),
+					cudaMemcpyDeviceToHost, stream));
+		}
+		if (h.best_fit != nullptr) {
+			CUDA_TRY(cudaMemcpy2DAsync(h.best_fit, hds * sizeof(float), f.best_fit,
+					dstride * sizeof(float), n * sizeof(float), R, cudaMemcpyDeviceToHost, stream));
+		}
+		if (h.residual != nullptr) {
+			CUDA_TRY(cudaMemcpy2DAsync(h.residual, hds * sizeof(float), f.residual,
+					dstride * sizeof(float), n * sizeof(float), R, cudaMemcpyDeviceToHost, stream));
+		}
+		CUDA_TRY(cudaMemcpy2DAsync(h.final_mask, hms, f.final_mask, dstride, n, R,
+				cudaMemcpyDeviceToHost, stream));
+		CUDA_TRY(cudaMemcpyAsync(h.rms, f.rms, R * sizeof(float), cudaMemcpyDeviceToHost, stream));
+		if (spline) {
+			CUDA_TRY(cudaMemcpyAsync(h.boundary, f.boundary, R * nb * sizeof(unsigned long long),
+					cudaMemcpyDeviceToHost, stream));
+		}
+	} else {
+		// Some rows failed or wrote nothing: copy row by row exactly what the reference
+		// would have written.
+		for (size_t r = 0; r < R; ++r) {
+			int const fl = flags[r];
+			if (fl & 1) {
+				if (h.coeff != nullptr) {
+					CUDA_TRY(cudaMemcpyAsync(h.coeff + r * f.coeff_stride, f.coeff + r * f.coeff_stride,
+							f.coeff_stride * sizeof(double), cudaMemcpyDeviceToHost, stream));
+				}
+				if (h.best_fit != nullptr) {
+					CUDA_TRY(cudaMemcpyAsync(h.best_fit + r * hds, f.best_fit + r * dstride,
+							n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+				}
+				if (h.residual != nullptr) {
+					CUDA_TRY(cudaMemcpyAsync(h.residual + r * hds, f.residual + r * dstride,
+							n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+				}
+				CUDA_TRY(cudaMemcpyAsync(h.rms + r, f.rms + r, sizeof(float), cudaMemcpyDeviceToHost,
+						stream));
+			}
+			if (fl & 2) {
+				CUDA_TRY(cudaMemcpyAsync(h.final_mask + r * hms, f.final_mask + r * dstride, n,
+						cudaMemcpyDeviceToHost, stream));
+			}
+			if (spline && (fl & 4)) {
+				CUDA_TRY(cudaMemcpyAsync(h.boundary + r * nb, f.boundary + r * nb,
+						nb * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+			}
+		}
+	}
+	CUDA_TRY(cudaStreamSynchronize(stream));
+	return sakura_Status_kOK;
+}
+
+bool UniqueAscending(size_t n, size_t const *a) {
+	for (size_t i = 1; i < n; ++i) {
+		if (a[i - 1] >= a[i]) {
+			return false;
+		}
+	}
+	return true;
+}
+
+void FillIdentity(int16_t *use_idx) {
+	for (int i = 0; i < kMaxBases; ++i) {
+		use_idx[i] = static_cast<int16_t>(i);
+	}
+}
+
+// baseline.cc:1239-1254; entries past the ones the wave list defines continue with
+// the next unused columns (the reference leaves them unspecified).
+void FillSinusoidIndex(size_t num_nwave, size_t const *nwave, size_t num_bases, int16_t *use_idx) {
+	size_t iuse = 0, i = 0;
+	bool used[kMaxBases + 2];
+	memset(used, 0, sizeof(used));
+	if (nwave[0] == 0) {
+		use_idx[iuse++] = 0;
+		used[0] = true;
+		++i;
+	}
+	for (; i < num_nwave; ++i) {
+		use_idx[iuse++] = static_cast<int16_t>(2 * nwave[i] - 1);
+		use_idx[iuse++] = static_cast<int16_t>(2 * nwave[i]);
+		used[2 * nwave[i] - 1] = true;
+		used[2 * nwave[i]] = true;
+	}
+	for (size_t col = 0; col < num_bases && iuse < static_cast<size_t>(kMaxBases); ++col) {
+		if (!used[col]) {
+			use_idx[iuse++] = static_cast<int16_t>(col);
+		}
+	}
+	for (; iuse < static_cast<size_t>(kMaxBases); ++iuse) {
+		use_idx[iuse] = 0;
+	}
+}
+
+template<typename PtrCheck>
+sakura_Status CheckPolynomial(Context const *c, uint16_t order, size_t num_spectra, size_t num_data,
+		void const *data, size_t data_stride, void const *mask, size_t mask_stride, float clip,
+		size_t num_coeff, void const *coeff, void const *best_fit, void const *residual,
+		void const *final_mask, void const *rms, PtrCheck rows_ok) {
+	CHECK_ARGS(ValidContext(c));
+	CHECK_ARGS(c->type == kFitPolynomial || c->type == kFitChebyshev); // baseline.cc:1699-1701
+	CHECK_ARGS(order <= c->param); // :1702
+	CHECK_ARGS(num_data == c->num_data); // :1703
+	CHECK_ARGS(data != nullptr && mask != nullptr);
+	CHECK_ARGS(num_spectra <= 1 || (data_stride >= num_data && mask_stride >= num_data));
+	CHECK_ARGS(rows_ok(data, data_stride * sizeof(float)));
+	CHECK_ARGS(rows_ok(mask, mask_stride));
+	CHECK_ARGS(0.0f < clip); // :1708
+	if (coeff != nullptr) {
+		CHECK_ARGS(num_coeff == static_cast<size_t>(order) + 1); // :1710-1712
+		CHECK_ARGS(rows_ok(coeff, kAlignment));
+	}
+	if (best_fit != nullptr) {
+		CHECK_ARGS(rows_ok(best_fit, data_stride * sizeof(float)));
+	}
+	if (residual != nullptr) {
+		CHECK_ARGS(rows_ok(residual, data_stride * sizeof(float)));
+	}
+	CHECK_ARGS(final_mask != nullptr);
+	CHECK_ARGS(rows_ok(final_mask, mask_stride));
+	CHECK_ARGS(rms != nullptr);
+	// num_coeff selects the number of fitted bases (baseline.cc:1301-1302); it must address
+	// columns that exist in the context table.
+	CHECK_ARGS(num_coeff <= c->num_bases);
+	CHECK_ARGS(num_coeff <= num_data);
+	return sakura_Status_kOK;
+}
+
+} // namespace
+
+// ---------------------------------------------------------------- polynomial
+
+sakura_Status sakura_LSQFitPolynomialFloatBatch(struct sakura_LSQFitContextFloat const *context,
+		uint16_t order, size_t num_spectra, size_t num_data, float const data[], size_t data_stride,
+		bool const mask[], size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max,
+		size_t num_coeff, double coeff[], float best_fit[], float residual[], bool final_mask[],
+		float rms[], int32_t status[], int32_t lsqfit_status[]) noexcept {
+	CHECK_ARGS(status != nullptr && lsqfit_status != nullptr);
+	auto rows_ok = [&](void const *p, size_t stride_bytes) {
+		return RowsAligned(p, stride_bytes, num_spectra);
+	};
+	sakura_Status st = CheckPolynomial(context, order, num_spectra, num_data, data, data_stride, mask,
+			mask_stride, clip_threshold_sigma, num_coeff, coeff, best_fit, residual, final_mask, rms,
+			rows_ok);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	Context *c = const_cast<Context *>(context);
+	FitCall f;
+	memset(&f, 0, sizeof(f));
+	f.type = c->type;
+	f.num_spectra = num_spectra;
+	f.num_data = num_data;
+	f.data_stride = data_stride;
+	f.mask_stride = mask_stride;
+	f.clip = clip_threshold_sigma;
+	f.nfit = num_fitting_max;
+	f.K = num_coeff;
+	f.coeff_stride = num_coeff;
+	FillIdentity(f.use_idx);
+	HostFitArgs h = { data, mask, coeff, best_fit, residual, final_mask, rms, status, lsqfit_status,
+			nullptr };
+	return RunHostBatch(c, f, h);
+}
+
+namespace {
+sakura_Status PolynomialBatchDevice(struct sakura_LSQFitContextFloat const *context, uint16_t order,
+		size_t num_spectra, size_t num_data, float const d_data[], size_t data_stride,
+		bool const d_mask[], size_t mask_stride, float clip_threshold_sigma,
+		uint16_t num_fitting_max, size_t num_coeff, double d_coeff[], float d_best_fit[],
+		float d_residual[], bool d_final_mask[], float d_rms[], int32_t d_status[],
+		int32_t d_lsqfit_status[], void *cuda_stream, CalibrationSpec const *cal) {
+	CHECK_ARGS(d_status != nullptr && d_lsqfit_status != nullptr);
+	auto rows_ok = [&](void const *p, size_t stride_bytes) {
+		return DeviceRowsAligned(p, stride_bytes, num_spectra);
+	};
+	sakura_Status st = CheckPolynomial(context, order, num_spectra, num_data, d_data, data_stride,
+			d_mask, mask_stride, clip_threshold_sigma, num_coeff, d_coeff, d_best_fit, d_residual,
+			d_final_mask, d_rms, rows_ok);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	CHECK_ARGS(static_cast<void const *>(d_best_fit) != static_cast<void const *>(d_data)
+			&& static_cast<void const *>(d_residual) != static_cast<void const *>(d_data));
+	Context *c = const_cast<Context *>(context);
+	FitCall f;
+	memset(&f, 0, sizeof(f));
+	f.type = c->type;
+	f.num_spectra = num_spectra;
+	f.num_data = num_data;
+	f.data_stride = data_stride;
+	f.mask_stride = mask_stride;
+	f.clip = clip_threshold_sigma;
+	f.nfit = num_fitting_max;
+	f.K = num_coeff;
+	f.coeff_stride = num_coeff;
+	FillIdentity(f.use_idx);
+	f.data = d_data;
+	f.mask = reinterpret_cast<uint8_t const *>(d_mask);
+	f.coeff = d_coeff;
+	f.best_fit = d_best_fit;
+	f.residual = d_residual;
+	f.final_mask = reinterpret_cast<uint8_t *>(d_final_mask);
+	f.rms = d_rms;
+	f.status = d_status;
+	f.lsq = d_lsqfit_status;
+	f.flags = nullptr;
+	if (cal != nullptr) {
+		f.cal = *cal;
+	}
+	return LaunchFit(c, f, static_cast<cudaStream_t>(cuda_stream));
+}
+} // namespace
+
+sakura_Status sakura_LSQFitPolynomialFloatBatchDevice(
+		struct sakura_LSQFitContextFloat const *context, uint16_t order, size_t num_spectra,
+		size_t num_data, float const d_data[], size_t data_stride, bool const d_mask[],
+		size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max, size_t num_coeff,
+		double d_coeff[], float d_best_fit[], float d_residual[], bool d_final_mask[], float d_rms[],
+		int32_t d_status[], int32_t d_lsqfit_status[], void *cuda_stream) noexcept {
+	return PolynomialBatchDevice(context, order, num_spectra, num_data, d_data, data_stride, d_mask,
+			mask_stride, clip_threshold_sigma, num_fitting_max, num_coeff, d_coeff, d_best_fit,
+			d_residual, d_final_mask, d_rms, d_status, d_lsqfit_status, cuda_stream, nullptr);
+}
+
+sakura_Status sakura_CalibrateAndLSQFitPolynomialFloatBatchDevice(
+		struct sakura_LSQFitContextFloat const *context, uint16_t order, size_t num_spectra,
+		size_t num_data, float const d_scaling_factor[], size_t scaling_stride,
+		float const_scaling_factor, float const d_data[], size_t data_stride,
+		float const d_reference[], size_t reference_stride, bool flag_nan_or_inf,
+		bool const d_mask[], size_t mask_stride, float clip_threshold_sigma,
+		uint16_t num_fitting_max, size_t num_coeff, double d_coeff[], float d_best_fit[],
+		float d_residual[], bool d_final_mask[], float d_rms[], int32_t d_status[],
+		int32_t d_lsqfit_status[], void *cuda_stream) noexcept {
+	sakura_Status const st = CheckCalibration(num_spectra, num_data, d_scaling_factor,
+			scaling_stride, d_data, data_stride, d_reference, reference_stride);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	CalibrationSpec cal;
+	memset(&cal, 0, sizeof(cal));
+	cal.reference = d_reference;
+	cal.reference_stride = reference_stride;
+	cal.scaling = d_scaling_factor;
+	cal.scaling_stride = scaling_stride;
+	cal.const_scaling = const_scaling_factor;
+	cal.flag_nonfinite = flag_nan_or_inf ? 1 : 0;
+	return PolynomialBatchDevice(context, order, num_spectra, num_data, d_data, data_stride, d_mask,
+			mask_stride, clip_threshold_sigma, num_fitting_max, num_coeff, d_coeff, d_best_fit,
+			d_residual, d_final_mask, d_rms, d_status, d_lsqfit_status, cuda_stream, &cal);
+}
+
+sakura_Status sakura_LSQFitPolynomialFloat(struct sakura_LSQFitContextFloat const *context,
+		uint16_t order, size_t num_data, float const data[], bool const mask[],
+		float clip_threshold_sigma, uint16_t num_fitting_max, size_t num_coeff, double coeff[],
+		float best_fit[], float residual[], bool final_mask[], float *rms,
+		sakura_LSQFitStatus *lsqfit_status) noexcept {
+	CHECK_ARGS(lsqfit_status != nullptr);
+	*lsqfit_status = sakura_LSQFitStatus_kNG; // baseline.cc:1696
+	int32_t st_row = sakura_Status_kNG, lsq_row = sakura_LSQFitStatus_kNG;
+	sakura_Status st = sakura_LSQFitPolynomialFloatBatch(context, order, 1, num_data, data, num_data,
+			mask, num_data, clip_threshold_sigma, num_fitting_max, num_coeff, coeff, best_fit,
+			residual, final_mask, rms, &st_row, &lsq_row);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	*lsqfit_status = static_cast<sakura_LSQFitStatus>(lsq_row);
+	return static_cast<sakura_Status>(st_row);
+}
+
+// ---------------------------------------------------------------- cubic spline
+
+namespace {
+template<typename PtrCheck>
+sakura_Status CheckSpline(Context const *c, size_t num_pieces, size_t num_spectra, size_t num_data,
+		void const *data, size_t data_stride, void const *mask, size_t mask_stride, float clip,
+		void const *coeff, void const *best_fit, void const *residual, void const *final_mask,
+		void const *rms, void const *boundary, PtrCheck rows_ok) {
+	CHECK_ARGS(ValidContext(c));
+	CHECK_ARGS(c->type == kFitCubicSpline); // baseline.cc:1774
+	CHECK_ARGS(0 < num_pieces);
+	CHECK_ARGS(num_pieces <= c->param);
+	CHECK_ARGS(num_pieces + 3 <= num_data);
+	CHECK_ARGS(num_data == c->num_data);
+	CHECK_ARGS(data != nullptr && mask != nullptr);
+	CHECK_ARGS(num_spectra <= 1 || (data_stride >= num_data && mask_stride >= num_data));
+	CHECK_ARGS(rows_ok(data, data_stride * sizeof(float)));
+	CHECK_ARGS(rows_ok(mask, mask_stride));
+	CHECK_ARGS(0.0f < clip);
+	if (coeff != nullptr) {
+		CHECK_ARGS(rows_ok(coeff, num_pieces * 4 * sizeof(double)));
+	}
+	if (best_fit != nullptr) {
+		CHECK_ARGS(rows_ok(best_fit, data_stride * sizeof(float)));
+	}
+	if (residual != nullptr) {
+		CHECK_ARGS(rows_ok(residual, data_stride * sizeof(float)));
+	}
+	CHECK_ARGS(final_mask != nullptr);
+	CHECK_ARGS(rows_ok(final_mask, mask_stride));
+	CHECK_ARGS(rms != nullptr);
+	CHECK_ARGS(boundary != nullptr);
+	CHECK_ARGS(rows_ok(boundary, kAlignment));
+	return sakura_Status_kOK;
+}
+
+void SetupSplineCall(Context *c, FitCall *f, size_t num_pieces, size_t num_spectra, size_t num_data,
+		size_t data_stride, size_t mask_stride, float clip, uint16_t nfit) {
+	memset(f, 0, sizeof(*f));
+	f->type = kFitCubicSpline;
+	f->num_spectra = num_spectra;
+	f->num_data = num_data;
+	f->data_stride = data_stride;
+	f->mask_stride = mask_stride;
+	f->clip = clip;
+	f->nfit = nfit;
+	f->K = num_pieces + 3;
+	f->npiece = num_pieces;
+	f->coeff_stride = num_pieces * 4;
+	FillIdentity(f->use_idx);
+	(void) c;
+}
+} // namespace
+
+sakura_Status sakura_LSQFitCubicSplineFloatBatch(struct sakura_LSQFitContextFloat const *context,
+		size_t num_pieces, size_t num_spectra, size_t num_data, float const data[], size_t data_stride,
+		bool const mask[], size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max,
+		double coeff[], float best_fit[], float residual[], bool final_mask[], float rms[],
+		size_t boundary[], int32_t status[], int32_t lsqfit_status[]) noexcept {
+	CHECK_ARGS(status != nullptr && lsqfit_status != nullptr);
+	sakura_Status st = CheckSpline(context, num_pieces, num_spectra, num_data, data, data_stride,
+			mask, mask_stride, clip_threshold_sigma, coeff, best_fit, residual, final_mask, rms,
+			boundary, [&](void const *p, size_t sb) {
+				return RowsAligned(p, sb, num_spectra);
+			});
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	Context *c = const_cast<Context *>(context);
+	FitCall f;
+	SetupSplineCall(c, &f, num_pieces, num_spectra, num_data, data_stride, mask_stride,
+			clip_threshold_sigma, num_fitting_max);
+	HostFitArgs h = { data, mask, coeff, best_fit, residual, final_mask, rms, status, lsqfit_status,
+			boundary };
+	return RunHostBatch(c, f, h);
+}
+
+sakura_Status sakura_LSQFitCubicSplineFloatBatchDevice(
+		struct sakura_LSQFitContextFloat const *context, size_t num_pieces, size_t num_spectra,
+		size_t num_data, float const d_data[], size_t data_stride, bool const d_mask[],
+		size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max, double d_coeff[],
+		float d_best_fit[], float d_residual[], bool d_final_mask[], float d_rms[], size_t d_boundary[],
+		int32_t d_status[], int32_t d_lsqfit_status[], void *cuda_stream) noexcept {
+	CHECK_ARGS(d_status != nullptr && d_lsqfit_status != nullptr);
+	sakura_Status st = CheckSpline(context, num_pieces, num_spectra, num_data, d_data, data_stride,
+			d_mask, mask_stride, clip_threshold_sigma, d_coeff, d_best_fit, d_residual, d_final_mask,
+			d_rms, d_boundary, [&](void const *p, size_t sb) {
+				return DeviceRowsAligned(p, sb, num_spectra);
+			});
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	CHECK_ARGS(static_cast<void const *>(d_best_fit) != static_cast<void const *>(d_data)
+			&& static_cast<void const *>(d_residual) != static_cast<void const *>(d_data));
+	Context *c = const_cast<Context *>(context);
+	FitCall f;
+	SetupSplineCall(c, &f, num_pieces, num_spectra, num_data, data_stride, mask_stride,
+			clip_threshold_sigma, num_fitting_max);
+	f.data = d_data;
+	f.mask = reinterpret_cast<uint8_t const *>(d_mask);
+	f.coeff = d_coeff;
+	f.best_fit = d_best_fit;
+	f.residual = d_residual;
+	f.final_mask = reinterpret_cast<uint8_t *>(d_final_mask);
+	f.rms = d_rms;
+	f.status = d_status;
+	f.lsq = d_lsqfit_status;
+	f.boundary = reinterpret_cast<unsigned long long *>(d_boundary);
+	return LaunchFit(c, f, static_cast<cudaStream_t>(cuda_stream));
+}
+
+sakura_Status sakura_LSQFitCubicSplineFloat(struct sakura_LSQFitContextFloat const *context,
+		size_t num_pieces, size_t num_data, float const data[], bool const mask[],
+		float clip_threshold_sigma, uint16_t num_fitting_max, double coeff[][4], float best_fit[],
+		float residual[], bool final_mask[], float *rms, size_t boundary[],
+		sakura_LSQFitStatus *lsqfit_status) noexcept {
+	CHECK_ARGS(lsqfit_status != nullptr);
+	*lsqfit_status = sakura_LSQFitStatus_kNG; // baseline.cc:1771
+	int32_t st_row = sakura_Status_kNG, lsq_row = sakura_LSQFitStatus_kNG;
+	sakura_Status st = sakura_LSQFitCubicSplineFloatBatch(context, num_pieces, 1, num_data, data,
+			num_data, mask, num_data, clip_threshold_sigma, num_fitting_max,
+			reinterpret_cast<double *>(coeff), best_fit, residual, final_mask, rms, boundary, &st_row,
+			&lsq_row);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	*lsqfit_status = static_cast<sakura_LSQFitStatus>(lsq_row);
+	return static_cast<sakura_Status>(st_row);
+}
+
+// ---------------------------------------------------------------- sinusoid
+
+namespace {
+template<typename PtrCheck>
+sakura_Status CheckSinusoid(Context const *c, size_t num_nwave, size_t const *nwave,
+		size_t num_spectra, size_t num_data, void const *data, size_t data_stride, void const *mask,
+		size_t mask_stride, float clip, size_t num_coeff, void const *coeff, void const *best_fit,
+		void const *residual, void const *final_mask, void const *rms, PtrCheck rows_ok) {
+	CHECK_ARGS(ValidContext(c));
+	CHECK_ARGS(c->type == kFitSinusoid); // baseline.cc:1848
+	CHECK_ARGS(0 < num_nwave);
+	CHECK_ARGS(nwave != nullptr);
+	CHECK_ARGS(UniqueAscending(num_nwave, nwave));
+	CHECK_ARGS(nwave[num_nwave - 1] <= c->param);
+	CHECK_ARGS(num_data == c->num_data);
+	CHECK_ARGS(data != nullptr && mask != nullptr);
+	CHECK_ARGS(num_spectra <= 1 || (data_stride >= num_data && mask_stride >= num_data));
+	CHECK_ARGS(rows_ok(data, data_stride * sizeof(float)));
+	CHECK_ARGS(rows_ok(mask, mask_stride));
+	CHECK_ARGS(0.0f < clip);
+	size_t const needed = (nwave[0] == 0) ? (2 * num_nwave - 1) : (2 * num_nwave);
+	CHECK_ARGS(needed <= num_coeff); // baseline.cc:1859-1861
+	CHECK_ARGS(num_coeff <= c->num_bases); // :1862
+	if (coeff != nullptr) {
+		CHECK_ARGS(rows_ok(coeff, kAlignment));
+	}
+	if (best_fit != nullptr) {
+		CHECK_ARGS(rows_ok(best_fit, data_stride * sizeof(float)));
+	}
+	if (residual != nullptr) {
+		CHECK_ARGS(rows_ok(residual, data_stride * sizeof(float)));
+	}
+	CHECK_ARGS(final_mask != nullptr);
+	CHECK_ARGS(rows_ok(final_mask, mask_stride));
+	CHECK_ARGS(rms != nullptr);
+	return sakura_Status_kOK;
+}
+
+void SetupSinusoidCall(Context *c, FitCall *f, size_t num_nwave, size_t const *nwave,
+		size_t num_spectra, size_t num_data, size_t data_stride, size_t mask_stride, float clip,
+		uint16_t nfit, size_t num_coeff) {
+	memset(f, 0, sizeof(*f));
+	f->type = kFitSinusoid;
+	f->num_spectra = num_spectra;
+	f->num_data = num_data;
+	f->data_stride = data_stride;
+	f->mask_stride = mask_stride;
+	f->clip = clip;
+	f->nfit = nfit;
+	f->K = num_coeff;
+	f->coeff_stride = num_coeff;
+	FillSinusoidIndex(num_nwave, nwave, c->num_bases, f->use_idx);
+}
+} // namespace
+
+sakura_Status sakura_LSQFitSinusoidFloatBatch(struct sakura_LSQFitContextFloat const *context,
+		size_t num_nwave, size_t const nwave[], size_t num_spectra, size_t num_data,
+		float const data[], size_t data_stride, bool const mask[], size_t mask_stride,
+		float clip_threshold_sigma, uint16_t num_fitting_max, size_t num_coeff, double coeff[],
+		float best_fit[], float residual[], bool final_mask[], float rms[], int32_t status[],
+		int32_t lsqfit_status[]) noexcept {
+	CHECK_ARGS(status != nullptr && lsqfit_status != nullptr);
+	sakura_Status st = CheckSinusoid(context, num_nwave, nwave, num_spectra, num_data, data,
+			data_stride, mask, mask_stride, clip_threshold_sigma, num_coeff, coeff, best_fit,
+			residual, final_mask, rms, [&](void const *p, size_t sb) {
+				return RowsAligned(p, sb, num_spectra);
+			});
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	Context *c = const_cast<Context *>(context);
+	FitCall f;
+	SetupSinusoidCall(c, &f, num_nwave, nwave, num_spectra, num_data, data_stride, mask_stride,
+			clip_threshold_sigma, num_fitting_max, num_coeff);
+	HostFitArgs h = { data, mask, coeff, best_fit, residual, final_mask, rms, status, lsqfit_status,
+			nullptr };
+	return RunHostBatch(c, f, h);
+}
+
+sakura_Status sakura_LSQFitSinusoidFloatBatchDevice(struct sakura_LSQFitContextFloat const *context,
+		size_t num_nwave, size_t const nwave[], size_t num_spectra, size_t num_data,
+		float const d_data[], size_t data_stride, bool const d_mask[], size_t mask_stride,
+		float clip_threshold_sigma, uint16_t num_fitting_max, size_t num_coeff, double d_coeff[],
+		float d_best_fit[], float d_residual[], bool d_final_mask[], float d_rms[],
+		int32_t d_status[], int32_t d_lsqfit_status[], void *cuda_stream) noexcept {
+	CHECK_ARGS(d_status != nullptr && d_lsqfit_status != nullptr);
+	sakura_Status st = CheckSinusoid(context, num_nwave, nwave, num_spectra, num_data, d_data,
+			data_stride, d_mask, mask_stride, clip_threshold_sigma, num_coeff, d_coeff, d_best_fit,
+			d_residual, d_final_mask, d_rms, [&](void const *p, size_t sb) {
+				return DeviceRowsAligned(p, sb, num_spectra);
+			});
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	CHECK_ARGS(static_cast<void const *>(d_best_fit) != static_cast<void const *>(d_data)
+			&& static_cast<void const *>(d_residual) != static_cast<void const *>(d_data));
+	Context *c = const_cast<Context *>(context);
+	FitCall f;
+	SetupSinusoidCall(c, &f, num_nwave, nwave, num_spectra, num_data, data_stride, mask_stride,
+			clip_threshold_sigma, num_fitting_max, num_coeff);
+	f.data = d_data;
+	f.mask = reinterpret_cast<uint8_t const *>(d_mask);
+	f.coeff = d_coeff;
+	f.best_fit = d_best_fit;
+	f.residual = d_residual;
+	f.final_mask = reinterpret_cast<uint8_t *>(d_final_mask);
+	f.rms = d_rms;
+	f.status = d_status;
+	f.lsq = d_lsqfit_status;
+	return LaunchFit(c, f, static_cast<cudaStream_t>(cuda_stream));
+}
+
+sakura_Status sakura_LSQFitSinusoidFloat(struct sakura_LSQFitContextFloat const *context,
+		size_t num_nwave, size_t const nwave[], size_t num_data, float const data[],
+		bool const mask[], float clip_threshold_sigma, uint16_t num_fitting_max, size_t num_coeff,
+		double coeff[], float best_fit[], float residual[], bool final_mask[], float *rms,
+		sakura_LSQFitStatus *lsqfit_status) noexcept {
+	CHECK_ARGS(lsqfit_status != nullptr);
+	*lsqfit_status = sakura_LSQFitStatus_kNG; // baseline.cc:1845
+	int32_t st_row = sakura_Status_kNG, lsq_row = sakura_LSQFitStatus_kNG;
+	sakura_Status st = sakura_LSQFitSinusoidFloatBatch(context, num_nwave, nwave, 1, num_data, data,
+			num_data, mask, num_data, clip_threshold_sigma, num_fitting_max, num_coeff, coeff,
+			best_fit, residual, final_mask, rms, &st_row, &lsq_row);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	*lsqfit_status = static_cast<sakura_LSQFitStatus>(lsq_row);
+	return static_cast<sakura_Status>(st_row);
+}
+
+// ---------------------------------------------------------------- Subtract*
+
+namespace {
+sakura_Status RunSubtract(Context *c, int type, size_t num_data, float const *data, size_t K,
+		size_t npiece, std::vector<double> const &coeff_apply, size_t const *boundary,
+		int16_t const *use_idx, float *out) {
+	DeviceInfo info;
+	sakura_Status st = CurrentDevice(&info);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	cudaStream_t const stream = 0;
+	st = BindDevice(c, info, stream);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	size_t const n = num_data;
+	CUDA_TRY(c->s_data.Reserve(n * sizeof(float)));
+	CUDA_TRY(c->s_residual.Reserve(n * sizeof(float)));
+	CUDA_TRY(c->s_coeff.Reserve(coeff_apply.size() * sizeof(double)));
+	CUDA_TRY(cudaMemcpyAsync(c->s_data.ptr, data, n * sizeof(float), cudaMemcpyHostToDevice, stream));
+	CUDA_TRY(cudaMemcpyAsync(c->s_coeff.ptr, coeff_apply.data(), coeff_apply.size() * sizeof(double),
+			cudaMemcpyHostToDevice, stream));
+	SubtractParams p;
+	memset(&p, 0, sizeof(p));
+	p.fit_type = type;
+	p.num_spectra = 1;
+	p.n = static_cast<int>(n);
+	p.nb_ctx = static_cast<int>(c->num_bases);
+	p.K = static_cast<int>(K);
+	p.npiece = static_cast<int>(npiece);
+	p.basis = c->d_basis.As<double>();
+	p.data = c->s_data.As<float>();
+	p.data_stride = n;
+	p.coeff = c->s_coeff.As<double>();
+	p.coeff_stride = coeff_apply.size();
+	p.out = c->s_residual.As<float>();
+	if (type == kFitCubicSpline) {
+		CUDA_TRY(c->s_boundary.Reserve((npiece + 1) * sizeof(unsigned long long)));
+		CUDA_TRY(cudaMemcpyAsync(c->s_boundary.ptr, boundary, (npiece + 1) * sizeof(size_t),
+				cudaMemcpyHostToDevice, stream));
+		p.boundary = c->s_boundary.As<unsigned long long>();
+	}
+	memcpy(p.use_idx, use_idx, sizeof(p.use_idx));
+	cudaError_t e = LaunchSubtract(p, 1, stream);
+	g_launch_count += 1;
+	g_last_kernel = "subtract";
+	if (e != cudaSuccess) {
+		SetError("LaunchSubtract", e);
+		return sakura_Status_kUnknownError;
+	}
+	CUDA_TRY(cudaMemcpyAsync(out, p.out, n * sizeof(float), cudaMemcpyDeviceToHost, stream));
+	CUDA_TRY(cudaStreamSynchronize(stream));
+	return sakura_Status_kOK;
+}
+} // namespace
+
+sakura_Status sakura_SubtractPolynomialFloat(struct sakura_LSQFitContextFloat const *context,
+		size_t num_data, float const data[], size_t num_coeff, double const coeff[], float out[])
+				noexcept {
+	CHECK_ARGS(ValidContext(context));
+	int const type = context->type;
+	CHECK_ARGS(type == kFitPolynomial || type == kFitChebyshev);
+	CHECK_ARGS(num_data == context->num_data);
+	CHECK_ARGS(data != nullptr && IsAligned(data));
+	CHECK_ARGS(0 < num_coeff);
+	CHECK_ARGS(num_coeff <= context->num_bases);
+	CHECK_ARGS(coeff != nullptr && IsAligned(coeff));
+	CHECK_ARGS(out != nullptr && IsAligned(out));
+	std::vector<double> apply(coeff, coeff + num_coeff);
+	if (type == kFitPolynomial) { // baseline.cc:1444-1451
+		double const max_x = static_cast<double>(num_data - 1);
+		double factor = 1.0;
+		for (size_t i = 0; i < num_coeff; ++i) {
+			apply[i] *= factor;
+			factor *= max_x;
+		}
+	}
+	int16_t use_idx[kMaxBases];
+	FillIdentity(use_idx);
+	return RunSubtract(const_cast<Context *>(context), type, num_data, data, num_coeff, 0, apply,
+			nullptr, use_idx, out);
+}
+
+sakura_Status sakura_SubtractCubicSplineFloat(struct sakura_LSQFitContextFloat const *context,
+		size_t num_data, float const data[], size_t num_pieces, double const coeff[][4],
+		size_t const boundary[], float out[]) noexcept {
+	CHECK_ARGS(ValidContext(context));
+	CHECK_ARGS(context->type == kFitCubicSpline);
+	CHECK_ARGS(0 < num_pieces);
+	CHECK_ARGS(num_pieces <= context->param);
+	CHECK_ARGS(num_data == context->num_data);
+	CHECK_ARGS(data != nullptr && IsAligned(data));
+	CHECK_ARGS(coeff != nullptr && IsAligned(coeff));
+	CHECK_ARGS(boundary != nullptr && IsAligned(boundary));
+	CHECK_ARGS(boundary[0] == 0);
+	CHECK_ARGS(boundary[num_pieces] == num_data);
+	CHECK_ARGS(out != nullptr && IsAligned(out));
+	std::vector<double> apply(num_pieces * 4);
+	double const max_x = static_cast<double>(num_data - 1);
+	for (size_t i = 0; i < num_pieces; ++i) { // baseline.cc:1490-1498
+		double factor = 1.0;
+		for (size_t j = 0; j < 4; ++j) {
+			apply[4 * i + j] = coeff[i][j] * factor;
+			factor *= max_x;
+		}
+	}
+	int16_t use_idx[kMaxBases];
+	FillIdentity(use_idx);
+	return RunSubtract(const_cast<Context *>(context), kFitCubicSpline, num_data, data, 4,
+			num_pieces, apply, boundary, use_idx, out);
+}
+
+sakura_Status sakura_SubtractSinusoidFloat(struct sakura_LSQFitContextFloat const *context,
+		size_t num_data, float const data[], size_t num_nwave, size_t const nwave[],
+		size_t num_coeff, double const coeff[], float out[]) noexcept {
+	CHECK_ARGS(ValidContext(context));
+	CHECK_ARGS(context->type == kFitSinusoid);
+	CHECK_ARGS(num_data == context->num_data);
+	CHECK_ARGS(data != nullptr && IsAligned(data));
+	CHECK_ARGS(0 < num_nwave);
+	CHECK_ARGS(nwave != nullptr);
+	CHECK_ARGS(UniqueAscending(num_nwave, nwave));
+	CHECK_ARGS(nwave[num_nwave - 1] <= context->param);
+	size_t const needed = (nwave[0] == 0) ? (2 * num_nwave - 1) : (2 * num_nwave);
+	CHECK_ARGS(needed <= num_coeff);
+	CHECK_ARGS(num_coeff <= context->num_bases);
+	CHECK_ARGS(coeff != nullptr && IsAligned(coeff));
+	CHECK_ARGS(out != nullptr && IsAligned(out));
+	std::vector<double> apply(coeff, coeff + num_coeff);
+	int16_t use_idx[kMaxBases];
+	FillSinusoidIndex(num_nwave, nwave, context->num_bases, use_idx);
+	return RunSubtract(const_cast<Context *>(context), kFitSinusoid, num_data, data, num_coeff, 0,
+			apply, nullptr, use_idx, out);
+}
+

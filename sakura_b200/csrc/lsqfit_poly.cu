@@ -346,7 +346,7 @@ __device__ __forceinline__ bool UpdateAndSolve(Shared<K, NT> &sh, PolyConst cons
 // FULL: n == 4 * NT * kSlotGroups (4096 channels at 128 threads, 8192 at 256), every thread owns
 // all 32 channel slots and the per-group bounds checks disappear.
 // CAL: position-switch calibration (and NaN/Inf flagging) applied while the row is loaded; only
-// instantiated together with FULL, other shapes calibrate in a pre-pass (capi.cu).
+// instantiated together with FULL, other shapes calibrate in a pre-pass (capi_core.cu).
 template<int K, int NT, bool FULL, bool CAL>
 __global__ void __launch_bounds__(NT, (NT == 64 ? (K >= 7 ? 8 : 12) : NT == 128 ? (K >= 7 ? 4 : kMinBlocks128) :
 		(K >= 7 ? 2 : kMinBlocks256)))
