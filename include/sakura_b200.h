@@ -254,6 +254,43 @@ sakura_Status sakura_LSQFitSinusoidFloatBatchDevice(
 		float d_rms[], int32_t d_status[], int32_t d_lsqfit_status[], void *cuda_stream)
 				SAKURA_B200_NOEXCEPT;
 
+/* ---- NEW: one call, several GPUs ---------------------------------------------------
+ *
+ * The host-pointer batch calls above drive the CURRENT device. The ...MultiDevice variants take the
+ * same arguments plus a device list and split the rows into one contiguous block per device
+ * (block g = rows [R*g/G, R*(g+1)/G)): what the reference's callers do with worker threads
+ * (bench/e2eReduce/src/main.cc:290, 520-608 fans blocks of rows out to a thread pool) happens inside
+ * the library, with one host thread, one replica of the context and one copy/compute pipeline per
+ * GPU. Rows are independent: there is no exchange between the devices.
+ *   num_devices == 0 or device_ids == NULL : every visible CUDA device (the first num_devices of
+ *                                            them when num_devices > 0);
+ *   otherwise device_ids[0..num_devices)   : distinct CUDA device ordinals (kInvalidArgument if not).
+ * Results, per-row status semantics and argument rules are those of the ...Batch call; the calling
+ * thread's current device is restored. Page-locked host buffers (cudaHostAlloc / cudaHostRegister,
+ * portable) are needed for the copies of the devices to overlap. */
+sakura_Status sakura_LSQFitPolynomialFloatBatchMultiDevice(
+		struct sakura_LSQFitContextFloat const *context, uint16_t order, size_t num_spectra,
+		size_t num_data, float const data[], size_t data_stride, bool const mask[],
+		size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max,
+		size_t num_coeff, double coeff[], float best_fit[], float residual[],
+		bool final_mask[], float rms[], int32_t status[], int32_t lsqfit_status[],
+		size_t num_devices, int const device_ids[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_LSQFitCubicSplineFloatBatchMultiDevice(
+		struct sakura_LSQFitContextFloat const *context, size_t num_pieces, size_t num_spectra,
+		size_t num_data, float const data[], size_t data_stride, bool const mask[],
+		size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max,
+		double coeff[/*num_spectra*num_pieces*4*/], float best_fit[], float residual[],
+		bool final_mask[], float rms[], size_t boundary[/*num_spectra*(num_pieces+1)*/],
+		int32_t status[], int32_t lsqfit_status[], size_t num_devices, int const device_ids[])
+				SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_LSQFitSinusoidFloatBatchMultiDevice(
+		struct sakura_LSQFitContextFloat const *context, size_t num_nwave,
+		size_t const nwave[], size_t num_spectra, size_t num_data, float const data[],
+		size_t data_stride, bool const mask[], size_t mask_stride, float clip_threshold_sigma,
+		uint16_t num_fitting_max, size_t num_coeff, double coeff[], float best_fit[],
+		float residual[], bool final_mask[], float rms[], int32_t status[],
+		int32_t lsqfit_status[], size_t num_devices, int const device_ids[]) SAKURA_B200_NOEXCEPT;
+
 /* ---- position-switch calibration ---------------------------
  * result = scaling_factor * (data - reference) / reference in float: subtract, multiply, true
  * divide (normalization.cc:128-139). */
@@ -456,6 +493,12 @@ int64_t sakura_b200_GetLastHandOverCount(struct sakura_LSQFitContextFloat const 
 char const *sakura_b200_GetLastErrorMessage(void) SAKURA_B200_NOEXCEPT;
 /** "sakura_b200 <version> (sm_100a)". */
 char const *sakura_b200_GetVersionString(void) SAKURA_B200_NOEXCEPT;
+/** Tuning of the host-pointer batch paths (process-wide; a value outside its range keeps the current
+ *  setting): `chunk_mib` in [1, 4096] = MiB of spectra per chunk of the copy/compute pipeline
+ *  (default 96, environment SAKURA_B200_CHUNK_MIB); `packed_kib` in [0, 2^20] = batches that stage
+ *  less than this many KiB use one pinned arena with a single upload and download (default 2048,
+ *  environment SAKURA_B200_PACKED_KIB; 0 disables that path). Results do not depend on either. */
+void sakura_b200_SetHostPipelineTuning(int64_t chunk_mib, int64_t packed_kib) SAKURA_B200_NOEXCEPT;
 
 #ifdef __cplusplus
 }

@@ -141,6 +141,10 @@ class SakuraLib:
                                                       vp, vp, vp, vp, vp, i32p, i32p]
         L.sakura_LSQFitSinusoidFloatBatchDevice.argtypes = \
             L.sakura_LSQFitSinusoidFloatBatch.argtypes + [vp]
+        for kind in ("Polynomial", "CubicSpline", "Sinusoid"):
+            fn = getattr(L, f"sakura_LSQFit{kind}FloatBatchMultiDevice")
+            fn.argtypes = getattr(L, f"sakura_LSQFit{kind}FloatBatch").argtypes + [sz, vp]
+            fn.restype = C.c_int
         L.sakura_ComputeStatisticsFloatBatch.argtypes = [sz, sz, vp, sz, vp, sz, vp]
         L.sakura_ComputeStatisticsFloatBatchDevice.argtypes = [sz, sz, vp, sz, vp, sz, vp, vp]
         L.sakura_CalibrateDataWithArrayScalingFloat.argtypes = [sz, vp, vp, vp, vp]
@@ -199,6 +203,8 @@ class SakuraLib:
         L.sakura_b200_GetLastKernelName.restype = C.c_char_p
         L.sakura_b200_GetLastErrorMessage.restype = C.c_char_p
         L.sakura_b200_GetVersionString.restype = C.c_char_p
+        L.sakura_b200_SetHostPipelineTuning.argtypes = [C.c_int64, C.c_int64]
+        L.sakura_b200_SetHostPipelineTuning.restype = None
 
     # ------------------------------------------------------------------ contexts
     def create_polynomial_context(self, order: int, num_data: int,
@@ -237,10 +243,27 @@ class SakuraLib:
         """Rows the screening kernel handed to the per-channel kernel in the last fit on `ctx`."""
         return int(self.lib.sakura_b200_GetLastHandOverCount(ctx))
 
+    def set_host_pipeline_tuning(self, chunk_mib: int = -1, packed_kib: int = -1) -> None:
+        """sakura_b200_SetHostPipelineTuning; -1 keeps a setting."""
+        self.lib.sakura_b200_SetHostPipelineTuning(chunk_mib, packed_kib)
+
     def last_error(self) -> str:
         return self.lib.sakura_b200_GetLastErrorMessage().decode()
 
     # ------------------------------------------------------------------ batched fits (host arrays)
+    def _batch_call(self, kind: str, devices, args):
+        """`devices` None: sakura_LSQFit<kind>FloatBatch on the current device; "all" or a sequence of
+        CUDA device ordinals: sakura_LSQFit<kind>FloatBatchMultiDevice (rows split over the devices)."""
+        if devices is None:
+            return getattr(self.lib, f"sakura_LSQFit{kind}FloatBatch")(*args)
+        fn = getattr(self.lib, f"sakura_LSQFit{kind}FloatBatchMultiDevice")
+        if isinstance(devices, str):
+            if devices != "all":
+                raise ValueError("devices must be None, 'all' or a sequence of device ordinals")
+            return fn(*args, 0, None)
+        ids = (C.c_int * len(devices))(*[int(d) for d in devices])
+        return fn(*args, len(devices), C.cast(ids, C.c_void_p))
+
     @staticmethod
     def _prep_rows(data, mask):
         data = np.asarray(data)
@@ -257,8 +280,9 @@ class SakuraLib:
     def lsqfit_polynomial_batch(self, ctx, order: int, data, mask, clip_threshold_sigma: float,
                                 num_fitting_max: int, num_coeff: Optional[int] = None,
                                 want_coeff: bool = True, want_best_fit: bool = False,
-                                want_residual: bool = True, out: Optional[dict] = None) -> dict:
-        """Rows of `data`/`mask` ([R, n]) through sakura_LSQFitPolynomialFloatBatch."""
+                                want_residual: bool = True, out: Optional[dict] = None,
+                                devices=None) -> dict:
+        """Rows of `data`/`mask` ([R, n]) through sakura_LSQFitPolynomialFloatBatch[MultiDevice]."""
         data, mask = self._prep_rows(data, mask)
         R, n = data.shape
         K = order + 1 if num_coeff is None else num_coeff
@@ -275,15 +299,16 @@ class SakuraLib:
                 if res[k] is not None:
                     res[k][...] = np.nan
             res["final_mask"][...] = False
-        res["call_status"] = self.lib.sakura_LSQFitPolynomialFloatBatch(
+        res["call_status"] = self._batch_call("Polynomial", devices, (
             ctx, order, R, n, _ptr(data), n, _ptr(mask), n, clip_threshold_sigma, num_fitting_max, K,
             _ptr(res["coeff"]), _ptr(res["best_fit"]), _ptr(res["residual"]), _ptr(res["final_mask"]),
-            _ptr(res["rms"]), _ptr(res["status"]), _ptr(res["lsqfit_status"]))
+            _ptr(res["rms"]), _ptr(res["status"]), _ptr(res["lsqfit_status"])))
         return res
 
     def lsqfit_cubicspline_batch(self, ctx, num_pieces: int, data, mask, clip_threshold_sigma: float,
                                  num_fitting_max: int, want_coeff: bool = True,
-                                 want_best_fit: bool = False, want_residual: bool = True) -> dict:
+                                 want_best_fit: bool = False, want_residual: bool = True,
+                                 devices=None) -> dict:
         data, mask = self._prep_rows(data, mask)
         R, n = data.shape
         res = {
@@ -301,16 +326,16 @@ class SakuraLib:
                 res[k][...] = np.nan
         res["final_mask"][...] = False
         res["boundary"][...] = np.iinfo(np.uint64).max
-        res["call_status"] = self.lib.sakura_LSQFitCubicSplineFloatBatch(
+        res["call_status"] = self._batch_call("CubicSpline", devices, (
             ctx, num_pieces, R, n, _ptr(data), n, _ptr(mask), n, clip_threshold_sigma, num_fitting_max,
             _ptr(res["coeff"]), _ptr(res["best_fit"]), _ptr(res["residual"]), _ptr(res["final_mask"]),
-            _ptr(res["rms"]), _ptr(res["boundary"]), _ptr(res["status"]), _ptr(res["lsqfit_status"]))
+            _ptr(res["rms"]), _ptr(res["boundary"]), _ptr(res["status"]), _ptr(res["lsqfit_status"])))
         return res
 
     def lsqfit_sinusoid_batch(self, ctx, nwave: Sequence[int], data, mask, clip_threshold_sigma: float,
                               num_fitting_max: int, num_coeff: Optional[int] = None,
                               want_coeff: bool = True, want_best_fit: bool = False,
-                              want_residual: bool = True) -> dict:
+                              want_residual: bool = True, devices=None) -> dict:
         data, mask = self._prep_rows(data, mask)
         R, n = data.shape
         nw = aligned_copy(np.asarray(nwave, dtype=np.uint64))
@@ -329,11 +354,11 @@ class SakuraLib:
             if res[k] is not None:
                 res[k][...] = np.nan
         res["final_mask"][...] = False
-        res["call_status"] = self.lib.sakura_LSQFitSinusoidFloatBatch(
+        res["call_status"] = self._batch_call("Sinusoid", devices, (
             ctx, len(nw), _ptr(nw), R, n, _ptr(data), n, _ptr(mask), n, clip_threshold_sigma,
             num_fitting_max, num_coeff, _ptr(res["coeff"]), _ptr(res["best_fit"]),
             _ptr(res["residual"]), _ptr(res["final_mask"]), _ptr(res["rms"]), _ptr(res["status"]),
-            _ptr(res["lsqfit_status"]))
+            _ptr(res["lsqfit_status"])))
         return res
 
     # ------------------------------------------------------------------ calibration

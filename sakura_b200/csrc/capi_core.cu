@@ -108,6 +108,16 @@ void ReleaseDeviceState(Context *c) {
 				c->slots[s].Release();
 			}
 		}
+		c->d_pack.Release();
+		if (c->h_pack != nullptr) {
+			cudaFreeHost(c->h_pack);
+			c->h_pack = nullptr;
+			c->h_pack_cap = 0;
+		}
+		if (c->pack_stream != nullptr) {
+			cudaStreamDestroy(c->pack_stream);
+			c->pack_stream = nullptr;
+		}
 		if (prev != c->device) {
 			cudaSetDevice(prev);
 		}
@@ -141,6 +151,10 @@ sakura_Status CreateContext(int type, uint16_t param, size_t num_data, Context *
 	c->h_flags = nullptr;
 	c->last_handover = nullptr;
 	c->slots = nullptr;
+	c->h_pack = nullptr;
+	c->h_pack_cap = 0;
+	c->pack_stream = nullptr;
+	c->replicas = nullptr;
 	c->h_ext = nullptr;
 	c->ext_cols = 0;
 	c->h_basis = static_cast<double *>(g_allocator(sizeof(double) * num_bases * num_data));
@@ -659,6 +673,13 @@ sakura_Status sakura_CreateLSQFitContextSinusoidFloat(uint16_t nwave, size_t num
 sakura_Status sakura_DestroyLSQFitContextFloat(struct sakura_LSQFitContextFloat *context) noexcept {
 	CHECK_ARGS(context != nullptr);
 	CHECK_ARGS(context->magic == kContextMagic);
+	if (context->replicas != nullptr) {
+		for (auto &r : *context->replicas) {
+			sakura_DestroyLSQFitContextFloat(r.second);
+		}
+		delete context->replicas;
+		context->replicas = nullptr;
+	}
 	ReleaseDeviceState(context);
 	delete context->h_flags;
 	delete context->h_ext;

@@ -2,6 +2,8 @@
 // copy/compute pipeline, device-array batches, the reference's single-row signatures, Subtract*).
 #include "capi_internal.cuh"
 
+#include <thread>
+
 using namespace sakura_b200;
 using namespace sakura_b200::capi;
 
@@ -21,7 +23,12 @@ struct HostFitArgs {
 	size_t *boundary;
 };
 
-sakura_Status RunHostBatchSerial(Context *c, FitCall f, HostFitArgs const &h);
+// Row flags (set by the kernels): bit0 = results published, bit1 = final_mask written,
+// bit2 = boundary written (cubic splines). A row copies back exactly what the reference would have
+// written.
+inline int AllPublished(int type) {
+	return type == kFitCubicSpline ? 7 : 3;
+}
 
 /** Row-strided copy; a single 1-D copy when both sides are tightly packed (faster on the
  *  copy engines than the pitched form). */
@@ -33,47 +40,49 @@ cudaError_t CopyRows(void *dst, size_t dpitch, void const *src, size_t spitch, s
 	return cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, rows, kind, stream);
 }
 
-// Pipelined variant for the polynomial hot path: the batch is cut into chunks that cycle
-// through kPipelineSlots (stream, device buffers) slots, so that the host->device copy of
-// chunk i+1, the kernel of chunk i and the device->host copy of chunk i-1 overlap on the
-// copy engines and the SMs. With pinned host buffers every copy is truly asynchronous.
-sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
-	if (f.num_spectra == 0) {
-		return sakura_Status_kOK;
+// Tuning knobs of the host-buffer paths: defaults from measurements on B200, overridden by the
+// environment at load time or by sakura_b200_SetHostPipelineTuning at any time.
+size_t EnvSize(char const *name, long lo, long hi, size_t fallback) {
+	char const *e = getenv(name);
+	if (e == nullptr) {
+		return fallback;
 	}
+	long const v = atol(e);
+	return (v >= lo && v <= hi) ? static_cast<size_t>(v) : fallback;
+}
+
+// chunk size of the pipeline in MiB of data
+std::atomic<size_t> g_chunk_mib(EnvSize("SAKURA_B200_CHUNK_MIB", 1, 4096, 96));
+// batches whose staged size is below this many KiB go through the single-arena path
+std::atomic<size_t> g_packed_kib(EnvSize("SAKURA_B200_PACKED_KIB", 0, 1 << 20, 2048));
+
+size_t ChunkMiB() {
+	return g_chunk_mib.load();
+}
+
+size_t PackedLimitBytes() {
+	return g_packed_kib.load() << 10;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pipelined variant: the batch is cut into chunks that cycle through kPipelineSlots (stream, device
+// buffers) slots, so that the host->device copy of chunk i+1, the kernel of chunk i and the
+// device->host copy of chunk i-1 overlap on the copy engines and the SMs. With pinned host buffers
+// every copy is truly asynchronous. The polynomial fast path brings a hand-over list per slot, so its
+// kernels may overlap freely; every other kernel uses scratch of the context and is ordered after
+// the previous chunk's kernel by an event (the uploads still run ahead).
+// ---------------------------------------------------------------------------------------------
+sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, size_t chunk_rows,
+		bool fast) {
 	size_t const n = f.num_data;
 	size_t const R = f.num_spectra;
 	size_t const dstride = RoundUp(n, 32);
-	bool const fast = (f.type == kFitPolynomial || (f.type == kFitChebyshev && f.K <= 6))
-			&& PolyFastSupported(n, f.K, dstride, dstride,
-			nullptr, nullptr, nullptr, nullptr, nullptr);
-	// chunk size of the pipeline in MiB of data (tuning knob; default from measurements on B200)
-	static size_t const chunk_mib = []() -> size_t {
-		char const *e = getenv("SAKURA_B200_CHUNK_MIB");
-		long const v = (e != nullptr) ? atol(e) : 0;
-		return (v >= 1 && v <= 4096) ? static_cast<size_t>(v) : 96;
-	}();
-	size_t chunk_rows = (chunk_mib << 20) / (dstride * sizeof(float));
-	if (chunk_rows < 1) {
-		chunk_rows = 1;
-	}
-	if (!fast || R <= chunk_rows) {
-		return RunHostBatchSerial(c, f, h);
-	}
-	DeviceInfo info;
-	sakura_Status st = CurrentDevice(&info);
-	if (st != sakura_Status_kOK) {
-		return st;
-	}
-	if (c->device >= 0 && c->device != info.device) {
-		ReleaseDeviceState(c);
-	}
-	c->device = info.device;
-	if (c->slots == nullptr) {
-		c->slots = new PipelineSlot[kPipelineSlots];
-	}
 	size_t const hds = f.data_stride, hms = f.mask_stride;
+	size_t const nb = f.npiece + 1;
+	bool const spline = (f.type == kFitCubicSpline);
+	int const published = AllPublished(f.type);
 	size_t const num_chunks = (R + chunk_rows - 1) / chunk_rows;
+	sakura_Status st = sakura_Status_kOK;
 	for (int s = 0; s < kPipelineSlots; ++s) {
 		PipelineSlot &sl = c->slots[s];
 		if (sl.stream == nullptr) {
@@ -95,6 +104,9 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 		if (h.residual != nullptr) {
 			CUDA_TRY(sl.residual.Reserve(chunk_rows * dstride * sizeof(float)));
 		}
+		if (spline) {
+			CUDA_TRY(sl.boundary.Reserve(chunk_rows * nb * sizeof(unsigned long long)));
+		}
 		CUDA_TRY(sl.handover.Reserve((chunk_rows + 1) * sizeof(int32_t)));
 		sl.h_flags.resize(chunk_rows);
 		sl.rows = 0;
@@ -106,7 +118,7 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 		float *d_rms = sl.small.As<float>();
 		bool all_published = true;
 		for (size_t r = 0; r < rows; ++r) {
-			if ((sl.h_flags[r] & 3) != 3) {
+			if ((sl.h_flags[r] & 7) != published) {
 				all_published = false;
 				break;
 			}
@@ -130,6 +142,10 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 					cudaMemcpyDeviceToHost, sl.down));
 			CUDA_TRY(cudaMemcpyAsync(h.rms + r0, d_rms, rows * sizeof(float), cudaMemcpyDeviceToHost,
 					sl.down));
+			if (spline) {
+				CUDA_TRY(cudaMemcpyAsync(h.boundary + r0 * nb, sl.boundary.ptr,
+						rows * nb * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl.down));
+			}
 		} else {
 			for (size_t r = 0; r < rows; ++r) {
 				int const fl = sl.h_flags[r];
@@ -157,12 +173,18 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 							sl.final_mask.As<uint8_t>() + r * dstride, n, cudaMemcpyDeviceToHost,
 							sl.down));
 				}
+				if (spline && (fl & 4)) {
+					CUDA_TRY(cudaMemcpyAsync(h.boundary + (r0 + r) * nb,
+							sl.boundary.As<unsigned long long>() + r * nb,
+							nb * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl.down));
+				}
 			}
 		}
 		CUDA_TRY(cudaEventRecord(sl.down_done, sl.down));
 		sl.rows = 0;
 		return sakura_Status_kOK;
 	};
+	PipelineSlot *previous = nullptr;
 	for (size_t ci = 0; ci < num_chunks; ++ci) {
 		PipelineSlot &sl = c->slots[ci % kPipelineSlots];
 		if (sl.rows != 0) {
@@ -185,6 +207,10 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 				cudaMemcpyHostToDevice, sl.stream));
 		// the kernel overwrites this slot's result buffers: wait for their previous download
 		CUDA_TRY(cudaStreamWaitEvent(sl.stream, sl.down_done, 0));
+		if (!fast && previous != nullptr) {
+			// scratch of the context is shared by the chunks: kernels one after the other
+			CUDA_TRY(cudaStreamWaitEvent(sl.stream, previous->flags_ready, 0));
+		}
 		CUDA_TRY(cudaMemsetAsync(d_flags, 0, rows * sizeof(int32_t), sl.stream));
 		FitCall fc = f;
 		fc.num_spectra = rows;
@@ -200,8 +226,8 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 		fc.status = d_status;
 		fc.lsq = d_lsq;
 		fc.flags = d_flags;
-		fc.boundary = nullptr;
-		fc.handover = sl.handover.As<int32_t>();
+		fc.boundary = spline ? sl.boundary.As<unsigned long long>() : nullptr;
+		fc.handover = fast ? sl.handover.As<int32_t>() : nullptr;
 		st = LaunchFit(c, fc, sl.stream);
 		if (st != sakura_Status_kOK) {
 			return st;
@@ -214,6 +240,7 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 				cudaMemcpyDeviceToHost, sl.stream));
 		CUDA_TRY(cudaEventRecord(sl.flags_ready, sl.stream));
 		CUDA_TRY(cudaStreamWaitEvent(sl.down, sl.flags_ready, 0));
+		previous = &sl;
 	}
 	for (size_t k = 0; k < static_cast<size_t>(kPipelineSlots); ++k) {
 		PipelineSlot &sl = c->slots[(num_chunks + k) % kPipelineSlots];
@@ -230,6 +257,183 @@ sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
 	}
 	return sakura_Status_kOK;
 }
+
+sakura_Status RunHostBatchPipelined(Context *c, FitCall const &f, HostFitArgs const &h,
+		size_t chunk_rows, bool fast, DeviceInfo const &info) {
+	if (c->device >= 0 && c->device != info.device) {
+		ReleaseDeviceState(c);
+	}
+	c->device = info.device;
+	if (c->slots == nullptr) {
+		c->slots = new PipelineSlot[kPipelineSlots];
+	}
+	sakura_Status const st = PipelineBody(c, f, h, chunk_rows, fast);
+	if (st != sakura_Status_kOK) {
+		// copies into the caller's buffers may still be in flight on the slot streams: drain them
+		// before the caller sees the error, and leave no slot marked busy for the next call
+		for (int s = 0; s < kPipelineSlots; ++s) {
+			PipelineSlot &sl = c->slots[s];
+			if (sl.stream != nullptr) {
+				(void) cudaStreamSynchronize(sl.stream);
+			}
+			if (sl.down != nullptr) {
+				(void) cudaStreamSynchronize(sl.down);
+			}
+			sl.rows = 0;
+		}
+		(void) cudaGetLastError();
+	}
+	return st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Small batches (the reference's single-row signatures are batches of one): everything a call moves
+// lives in ONE device arena mirrored by ONE pinned host arena,
+//     [ data | mask | flags ]  ->  one host->device copy (flags = 0)
+//     [ flags | status | lsqfit_status | rms | coeff | boundary | final_mask | residual | best_fit ]
+//                              <-  one device->host copy,
+// on a stream of the context's own: two copies, the kernel(s) and one synchronisation per call
+// instead of two synchronisations and ten copies out of pageable memory.
+// ---------------------------------------------------------------------------------------------
+sakura_Status RunHostBatchPacked(Context *c, FitCall f, HostFitArgs const &h, DeviceInfo const &info) {
+	size_t const n = f.num_data;
+	size_t const R = f.num_spectra;
+	size_t const dstride = RoundUp(n, 32);
+	size_t const hds = f.data_stride, hms = f.mask_stride;
+	size_t const nb = f.npiece + 1;
+	bool const spline = (f.type == kFitCubicSpline);
+	if (c->device >= 0 && c->device != info.device) {
+		ReleaseDeviceState(c);
+	}
+	c->device = info.device;
+	if (c->pack_stream == nullptr) {
+		CUDA_TRY(cudaStreamCreateWithFlags(&c->pack_stream, cudaStreamNonBlocking));
+	}
+	cudaStream_t const stream = c->pack_stream;
+	size_t off = 0;
+	auto take = [&off](size_t bytes) {
+		size_t const at = off;
+		off = RoundUp(off + bytes, 256);
+		return at;
+	};
+	size_t const o_data = take(R * dstride * sizeof(float));
+	size_t const o_mask = take(R * dstride);
+	size_t const o_flags = take(R * sizeof(int32_t));
+	size_t const o_status = take(R * sizeof(int32_t));
+	size_t const o_lsq = take(R * sizeof(int32_t));
+	size_t const o_rms = take(R * sizeof(float));
+	size_t const o_coeff = take(h.coeff ? R * f.coeff_stride * sizeof(double) : 0);
+	size_t const o_boundary = take(spline ? R * nb * sizeof(unsigned long long) : 0);
+	size_t const o_final = take(R * dstride);
+	size_t const o_resid = take(h.residual ? R * dstride * sizeof(float) : 0);
+	size_t const o_best = take(h.best_fit ? R * dstride * sizeof(float) : 0);
+	size_t const total = off;
+	if (c->h_pack_cap < total) {
+		if (c->h_pack != nullptr) {
+			cudaFreeHost(c->h_pack);
+			c->h_pack = nullptr;
+			c->h_pack_cap = 0;
+		}
+		size_t const want = total + total / 4;
+		CUDA_TRY(cudaHostAlloc(&c->h_pack, want, cudaHostAllocDefault));
+		c->h_pack_cap = want;
+	}
+	CUDA_TRY(c->d_pack.Reserve(total));
+	char *hp = static_cast<char *>(c->h_pack);
+	char *dp = c->d_pack.As<char>();
+	for (size_t r = 0; r < R; ++r) {
+		memcpy(hp + o_data + r * dstride * sizeof(float), h.data + r * hds, n * sizeof(float));
+		memcpy(hp + o_mask + r * dstride, h.mask + r * hms, n);
+	}
+	memset(hp + o_flags, 0, R * sizeof(int32_t));
+	CUDA_TRY(cudaMemcpyAsync(dp, hp, o_flags + R * sizeof(int32_t), cudaMemcpyHostToDevice, stream));
+	f.data = reinterpret_cast<float const *>(dp + o_data);
+	f.mask = reinterpret_cast<uint8_t const *>(dp + o_mask);
+	f.data_stride = dstride;
+	f.mask_stride = dstride;
+	f.coeff = h.coeff ? reinterpret_cast<double *>(dp + o_coeff) : nullptr;
+	f.best_fit = h.best_fit ? reinterpret_cast<float *>(dp + o_best) : nullptr;
+	f.residual = h.residual ? reinterpret_cast<float *>(dp + o_resid) : nullptr;
+	f.final_mask = reinterpret_cast<uint8_t *>(dp + o_final);
+	f.rms = reinterpret_cast<float *>(dp + o_rms);
+	f.status = reinterpret_cast<int32_t *>(dp + o_status);
+	f.lsq = reinterpret_cast<int32_t *>(dp + o_lsq);
+	f.flags = reinterpret_cast<int32_t *>(dp + o_flags);
+	f.boundary = spline ? reinterpret_cast<unsigned long long *>(dp + o_boundary) : nullptr;
+	sakura_Status const st = LaunchFit(c, f, stream);
+	if (st != sakura_Status_kOK) {
+		(void) cudaStreamSynchronize(stream);
+		return st;
+	}
+	CUDA_TRY(cudaMemcpyAsync(hp + o_flags, dp + o_flags, total - o_flags, cudaMemcpyDeviceToHost, stream));
+	CUDA_TRY(cudaStreamSynchronize(stream));
+	int32_t const *flags = reinterpret_cast<int32_t const *>(hp + o_flags);
+	memcpy(h.status, hp + o_status, R * sizeof(int32_t));
+	memcpy(h.lsq, hp + o_lsq, R * sizeof(int32_t));
+	for (size_t r = 0; r < R; ++r) {
+		int const fl = flags[r];
+		if (fl & 1) {
+			if (h.coeff != nullptr) {
+				memcpy(h.coeff + r * f.coeff_stride, hp + o_coeff + r * f.coeff_stride * sizeof(double),
+						f.coeff_stride * sizeof(double));
+			}
+			if (h.best_fit != nullptr) {
+				memcpy(h.best_fit + r * hds, hp + o_best + r * dstride * sizeof(float), n * sizeof(float));
+			}
+			if (h.residual != nullptr) {
+				memcpy(h.residual + r * hds, hp + o_resid + r * dstride * sizeof(float), n * sizeof(float));
+			}
+			memcpy(h.rms + r, hp + o_rms + r * sizeof(float), sizeof(float));
+		}
+		if (fl & 2) {
+			memcpy(h.final_mask + r * hms, hp + o_final + r * dstride, n);
+		}
+		if (spline && (fl & 4)) {
+			memcpy(h.boundary + r * nb, hp + o_boundary + r * nb * sizeof(unsigned long long),
+					nb * sizeof(unsigned long long));
+		}
+	}
+	return sakura_Status_kOK;
+}
+
+sakura_Status RunHostBatchSerial(Context *c, FitCall f, HostFitArgs const &h);
+
+sakura_Status RunHostBatch(Context *c, FitCall f, HostFitArgs const &h) {
+	if (f.num_spectra == 0) {
+		return sakura_Status_kOK;
+	}
+	size_t const n = f.num_data;
+	size_t const R = f.num_spectra;
+	size_t const dstride = RoundUp(n, 32);
+	DeviceInfo info;
+	sakura_Status st = CurrentDevice(&info);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	// staged bytes per row: data, mask, final_mask, residual, best_fit (+ the small per-row outputs)
+	size_t const row_bytes = dstride * (4 + 1 + 1 + (h.residual ? 4 : 0) + (h.best_fit ? 4 : 0))
+			+ f.coeff_stride * sizeof(double) + 64;
+	if (R * row_bytes <= PackedLimitBytes()) {
+		return RunHostBatchPacked(c, f, h, info);
+	}
+	bool const fast = (f.type == kFitPolynomial || (f.type == kFitChebyshev && f.K <= 6))
+			&& PolyFastSupported(n, f.K, dstride, dstride,
+			nullptr, nullptr, nullptr, nullptr, nullptr);
+	size_t chunk_rows = (ChunkMiB() << 20) / (dstride * sizeof(float));
+	if (chunk_rows < 1) {
+		chunk_rows = 1;
+	}
+	if (f.type == kFitSinusoid || (f.type == kFitChebyshev && !fast)) {
+		// the tensor-core kernel fits tiles of kSinRowsPerTile rows, one tile per SM at a time:
+		// whole waves per chunk
+		chunk_rows = RoundUp(chunk_rows, static_cast<size_t>(kSinRowsPerTile) * info.num_sms);
+	}
+	if (R <= chunk_rows) {
+		return RunHostBatchSerial(c, f, h);
+	}
+	return RunHostBatchPipelined(c, f, h, chunk_rows, fast, info);
+}
+
 
 sakura_Status RunHostBatchSerial(Context *c, FitCall f, HostFitArgs const &h) {
 	if (f.num_spectra == 0) {
@@ -361,6 +565,150 @@ sakura_Status RunHostBatchSerial(Context *c, FitCall f, HostFitArgs const &h) {
 	return sakura_Status_kOK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// ...MultiDevice entry points: rows are independent, so a batch in host memory is cut into one
+// contiguous block of rows per device (block g = rows [R g / G, R (g+1) / G), the split of
+// sakura_b200/sharding.py and of the reference's e2e driver, bench/e2eReduce/src/main.cc:520-608,
+// which fans blocks of rows out to worker threads). Every device gets a replica of the context
+// (same type / parameter / channel count; tables built once, kept for the context's lifetime) and a
+// host thread that drives the replica's own copy/compute pipeline; there is no exchange between the
+// devices and no collective.
+// ---------------------------------------------------------------------------------------------
+sakura_Status ResolveDevices(size_t num_devices, int const *device_ids, std::vector<int> *out) {
+	int visible = 0;
+	CUDA_TRY(cudaGetDeviceCount(&visible));
+	if (visible < 1) {
+		SetError("cudaGetDeviceCount", cudaErrorNoDevice);
+		return sakura_Status_kUnknownError;
+	}
+	out->clear();
+	if (num_devices == 0 || device_ids == nullptr) { // every visible device (the first num_devices of them)
+		size_t const take = (num_devices == 0 || num_devices > static_cast<size_t>(visible)) ?
+				static_cast<size_t>(visible) : num_devices;
+		for (size_t g = 0; g < take; ++g) {
+			out->push_back(static_cast<int>(g));
+		}
+		return sakura_Status_kOK;
+	}
+	for (size_t g = 0; g < num_devices; ++g) {
+		CHECK_ARGS(0 <= device_ids[g] && device_ids[g] < visible);
+		for (size_t k = 0; k < g; ++k) {
+			CHECK_ARGS(device_ids[k] != device_ids[g]);
+		}
+		out->push_back(device_ids[g]);
+	}
+	return sakura_Status_kOK;
+}
+
+Context *ReplicaFor(Context *c, int device) {
+	if (c->replicas == nullptr) {
+		c->replicas = new std::vector<std::pair<int, Context *> >();
+	}
+	for (auto &r : *c->replicas) {
+		if (r.first == device) {
+			return r.second;
+		}
+	}
+	Context *replica = nullptr;
+	if (CreateContext(c->type, c->param, c->num_data, &replica) != sakura_Status_kOK) {
+		return nullptr;
+	}
+	c->replicas->push_back(std::make_pair(device, replica));
+	return replica;
+}
+
+sakura_Status RunHostBatchMultiDevice(Context *c, FitCall const &f, HostFitArgs const &h,
+		size_t num_devices, int const *device_ids) {
+	std::vector<int> devices;
+	sakura_Status st = ResolveDevices(num_devices, device_ids, &devices);
+	if (st != sakura_Status_kOK) {
+		return st;
+	}
+	size_t const R = f.num_spectra;
+	if (R == 0) {
+		return sakura_Status_kOK;
+	}
+	size_t G = devices.size();
+	if (G > R) {
+		G = R;
+	}
+	size_t const nb = f.npiece + 1;
+	struct Shard {
+		int device;
+		Context *replica;
+		FitCall f;
+		HostFitArgs h;
+		sakura_Status status;
+		std::string error;
+		char const *kernel;
+	};
+	std::vector<Shard> shards(G);
+	for (size_t g = 0; g < G; ++g) {
+		Shard &s = shards[g];
+		size_t const r0 = R / G * g + (R % G) * g / G;
+		size_t const r1 = R / G * (g + 1) + (R % G) * (g + 1) / G;
+		s.device = devices[g];
+		s.replica = ReplicaFor(c, s.device);
+		if (s.replica == nullptr) {
+			return sakura_Status_kNoMemory;
+		}
+		s.f = f;
+		s.f.num_spectra = r1 - r0;
+		s.h.data = h.data + r0 * f.data_stride;
+		s.h.mask = h.mask + r0 * f.mask_stride;
+		s.h.coeff = h.coeff ? h.coeff + r0 * f.coeff_stride : nullptr;
+		s.h.best_fit = h.best_fit ? h.best_fit + r0 * f.data_stride : nullptr;
+		s.h.residual = h.residual ? h.residual + r0 * f.data_stride : nullptr;
+		s.h.final_mask = h.final_mask + r0 * f.mask_stride;
+		s.h.rms = h.rms + r0;
+		s.h.status = h.status + r0;
+		s.h.lsq = h.lsq + r0;
+		s.h.boundary = h.boundary ? h.boundary + r0 * nb : nullptr;
+		s.status = sakura_Status_kOK;
+		s.kernel = "";
+	}
+	auto work = [](Shard *s) {
+		cudaError_t const e = cudaSetDevice(s->device);
+		if (e != cudaSuccess) {
+			SetError("cudaSetDevice", e);
+			s->status = sakura_Status_kUnknownError;
+		} else {
+			s->status = RunHostBatch(s->replica, s->f, s->h);
+		}
+		if (s->status != sakura_Status_kOK) {
+			s->error = g_last_error;
+		}
+		s->kernel = g_last_kernel;
+	};
+	int previous = -1;
+	(void) cudaGetDevice(&previous);
+	if (G == 1) {
+		work(&shards[0]);
+	} else {
+		std::vector<std::thread> threads;
+		threads.reserve(G - 1);
+		for (size_t g = 1; g < G; ++g) {
+			threads.emplace_back(work, &shards[g]);
+		}
+		work(&shards[0]);
+		for (auto &t : threads) {
+			t.join();
+		}
+	}
+	if (previous >= 0) {
+		(void) cudaSetDevice(previous);
+	}
+	g_last_kernel = shards[0].kernel;
+	for (size_t g = 0; g < G; ++g) {
+		if (shards[g].status != sakura_Status_kOK) {
+			snprintf(g_last_error, sizeof(g_last_error), "device %d: %s", shards[g].device,
+					shards[g].error.c_str());
+			return shards[g].status;
+		}
+	}
+	return sakura_Status_kOK;
+}
+
 bool UniqueAscending(size_t n, size_t const *a) {
 	for (size_t i = 1; i < n; ++i) {
 		if (a[i - 1] >= a[i]) {
@@ -441,11 +789,13 @@ sakura_Status CheckPolynomial(Context const *c, uint16_t order, size_t num_spect
 
 // ---------------------------------------------------------------- polynomial
 
-sakura_Status sakura_LSQFitPolynomialFloatBatch(struct sakura_LSQFitContextFloat const *context,
-		uint16_t order, size_t num_spectra, size_t num_data, float const data[], size_t data_stride,
-		bool const mask[], size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max,
-		size_t num_coeff, double coeff[], float best_fit[], float residual[], bool final_mask[],
-		float rms[], int32_t status[], int32_t lsqfit_status[]) noexcept {
+namespace {
+sakura_Status PolynomialBatchHost(struct sakura_LSQFitContextFloat const *context, uint16_t order,
+		size_t num_spectra, size_t num_data, float const data[], size_t data_stride, bool const mask[],
+		size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max, size_t num_coeff,
+		double coeff[], float best_fit[], float residual[], bool final_mask[], float rms[],
+		int32_t status[], int32_t lsqfit_status[], bool multi_device, size_t num_devices,
+		int const device_ids[]) {
 	CHECK_ARGS(status != nullptr && lsqfit_status != nullptr);
 	auto rows_ok = [&](void const *p, size_t stride_bytes) {
 		return RowsAligned(p, stride_bytes, num_spectra);
@@ -471,7 +821,32 @@ sakura_Status sakura_LSQFitPolynomialFloatBatch(struct sakura_LSQFitContextFloat
 	FillIdentity(f.use_idx);
 	HostFitArgs h = { data, mask, coeff, best_fit, residual, final_mask, rms, status, lsqfit_status,
 			nullptr };
+	if (multi_device) {
+		return RunHostBatchMultiDevice(c, f, h, num_devices, device_ids);
+	}
 	return RunHostBatch(c, f, h);
+}
+} // namespace
+
+sakura_Status sakura_LSQFitPolynomialFloatBatch(struct sakura_LSQFitContextFloat const *context,
+		uint16_t order, size_t num_spectra, size_t num_data, float const data[], size_t data_stride,
+		bool const mask[], size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max,
+		size_t num_coeff, double coeff[], float best_fit[], float residual[], bool final_mask[],
+		float rms[], int32_t status[], int32_t lsqfit_status[]) noexcept {
+	return PolynomialBatchHost(context, order, num_spectra, num_data, data, data_stride, mask,
+			mask_stride, clip_threshold_sigma, num_fitting_max, num_coeff, coeff, best_fit, residual,
+			final_mask, rms, status, lsqfit_status, false, 0, nullptr);
+}
+
+sakura_Status sakura_LSQFitPolynomialFloatBatchMultiDevice(
+		struct sakura_LSQFitContextFloat const *context, uint16_t order, size_t num_spectra,
+		size_t num_data, float const data[], size_t data_stride, bool const mask[], size_t mask_stride,
+		float clip_threshold_sigma, uint16_t num_fitting_max, size_t num_coeff, double coeff[],
+		float best_fit[], float residual[], bool final_mask[], float rms[], int32_t status[],
+		int32_t lsqfit_status[], size_t num_devices, int const device_ids[]) noexcept {
+	return PolynomialBatchHost(context, order, num_spectra, num_data, data, data_stride, mask,
+			mask_stride, clip_threshold_sigma, num_fitting_max, num_coeff, coeff, best_fit, residual,
+			final_mask, rms, status, lsqfit_status, true, num_devices, device_ids);
 }
 
 namespace {
@@ -633,11 +1008,13 @@ void SetupSplineCall(Context *c, FitCall *f, size_t num_pieces, size_t num_spect
 }
 } // namespace
 
-sakura_Status sakura_LSQFitCubicSplineFloatBatch(struct sakura_LSQFitContextFloat const *context,
-		size_t num_pieces, size_t num_spectra, size_t num_data, float const data[], size_t data_stride,
-		bool const mask[], size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max,
-		double coeff[], float best_fit[], float residual[], bool final_mask[], float rms[],
-		size_t boundary[], int32_t status[], int32_t lsqfit_status[]) noexcept {
+namespace {
+sakura_Status CubicSplineBatchHost(struct sakura_LSQFitContextFloat const *context, size_t num_pieces,
+		size_t num_spectra, size_t num_data, float const data[], size_t data_stride, bool const mask[],
+		size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max, double coeff[],
+		float best_fit[], float residual[], bool final_mask[], float rms[], size_t boundary[],
+		int32_t status[], int32_t lsqfit_status[], bool multi_device, size_t num_devices,
+		int const device_ids[]) {
 	CHECK_ARGS(status != nullptr && lsqfit_status != nullptr);
 	sakura_Status st = CheckSpline(context, num_pieces, num_spectra, num_data, data, data_stride,
 			mask, mask_stride, clip_threshold_sigma, coeff, best_fit, residual, final_mask, rms,
@@ -653,7 +1030,32 @@ sakura_Status sakura_LSQFitCubicSplineFloatBatch(struct sakura_LSQFitContextFloa
 			clip_threshold_sigma, num_fitting_max);
 	HostFitArgs h = { data, mask, coeff, best_fit, residual, final_mask, rms, status, lsqfit_status,
 			boundary };
+	if (multi_device) {
+		return RunHostBatchMultiDevice(c, f, h, num_devices, device_ids);
+	}
 	return RunHostBatch(c, f, h);
+}
+} // namespace
+
+sakura_Status sakura_LSQFitCubicSplineFloatBatch(struct sakura_LSQFitContextFloat const *context,
+		size_t num_pieces, size_t num_spectra, size_t num_data, float const data[], size_t data_stride,
+		bool const mask[], size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max,
+		double coeff[], float best_fit[], float residual[], bool final_mask[], float rms[],
+		size_t boundary[], int32_t status[], int32_t lsqfit_status[]) noexcept {
+	return CubicSplineBatchHost(context, num_pieces, num_spectra, num_data, data, data_stride, mask,
+			mask_stride, clip_threshold_sigma, num_fitting_max, coeff, best_fit, residual, final_mask,
+			rms, boundary, status, lsqfit_status, false, 0, nullptr);
+}
+
+sakura_Status sakura_LSQFitCubicSplineFloatBatchMultiDevice(
+		struct sakura_LSQFitContextFloat const *context, size_t num_pieces, size_t num_spectra,
+		size_t num_data, float const data[], size_t data_stride, bool const mask[], size_t mask_stride,
+		float clip_threshold_sigma, uint16_t num_fitting_max, double coeff[], float best_fit[],
+		float residual[], bool final_mask[], float rms[], size_t boundary[], int32_t status[],
+		int32_t lsqfit_status[], size_t num_devices, int const device_ids[]) noexcept {
+	return CubicSplineBatchHost(context, num_pieces, num_spectra, num_data, data, data_stride, mask,
+			mask_stride, clip_threshold_sigma, num_fitting_max, coeff, best_fit, residual, final_mask,
+			rms, boundary, status, lsqfit_status, true, num_devices, device_ids);
 }
 
 sakura_Status sakura_LSQFitCubicSplineFloatBatchDevice(
@@ -764,12 +1166,13 @@ void SetupSinusoidCall(Context *c, FitCall *f, size_t num_nwave, size_t const *n
 }
 } // namespace
 
-sakura_Status sakura_LSQFitSinusoidFloatBatch(struct sakura_LSQFitContextFloat const *context,
-		size_t num_nwave, size_t const nwave[], size_t num_spectra, size_t num_data,
-		float const data[], size_t data_stride, bool const mask[], size_t mask_stride,
-		float clip_threshold_sigma, uint16_t num_fitting_max, size_t num_coeff, double coeff[],
-		float best_fit[], float residual[], bool final_mask[], float rms[], int32_t status[],
-		int32_t lsqfit_status[]) noexcept {
+namespace {
+sakura_Status SinusoidBatchHost(struct sakura_LSQFitContextFloat const *context, size_t num_nwave,
+		size_t const nwave[], size_t num_spectra, size_t num_data, float const data[],
+		size_t data_stride, bool const mask[], size_t mask_stride, float clip_threshold_sigma,
+		uint16_t num_fitting_max, size_t num_coeff, double coeff[], float best_fit[], float residual[],
+		bool final_mask[], float rms[], int32_t status[], int32_t lsqfit_status[], bool multi_device,
+		size_t num_devices, int const device_ids[]) {
 	CHECK_ARGS(status != nullptr && lsqfit_status != nullptr);
 	sakura_Status st = CheckSinusoid(context, num_nwave, nwave, num_spectra, num_data, data,
 			data_stride, mask, mask_stride, clip_threshold_sigma, num_coeff, coeff, best_fit,
@@ -785,7 +1188,33 @@ sakura_Status sakura_LSQFitSinusoidFloatBatch(struct sakura_LSQFitContextFloat c
 			clip_threshold_sigma, num_fitting_max, num_coeff);
 	HostFitArgs h = { data, mask, coeff, best_fit, residual, final_mask, rms, status, lsqfit_status,
 			nullptr };
+	if (multi_device) {
+		return RunHostBatchMultiDevice(c, f, h, num_devices, device_ids);
+	}
 	return RunHostBatch(c, f, h);
+}
+} // namespace
+
+sakura_Status sakura_LSQFitSinusoidFloatBatch(struct sakura_LSQFitContextFloat const *context,
+		size_t num_nwave, size_t const nwave[], size_t num_spectra, size_t num_data,
+		float const data[], size_t data_stride, bool const mask[], size_t mask_stride,
+		float clip_threshold_sigma, uint16_t num_fitting_max, size_t num_coeff, double coeff[],
+		float best_fit[], float residual[], bool final_mask[], float rms[], int32_t status[],
+		int32_t lsqfit_status[]) noexcept {
+	return SinusoidBatchHost(context, num_nwave, nwave, num_spectra, num_data, data, data_stride, mask,
+			mask_stride, clip_threshold_sigma, num_fitting_max, num_coeff, coeff, best_fit, residual,
+			final_mask, rms, status, lsqfit_status, false, 0, nullptr);
+}
+
+sakura_Status sakura_LSQFitSinusoidFloatBatchMultiDevice(
+		struct sakura_LSQFitContextFloat const *context, size_t num_nwave, size_t const nwave[],
+		size_t num_spectra, size_t num_data, float const data[], size_t data_stride, bool const mask[],
+		size_t mask_stride, float clip_threshold_sigma, uint16_t num_fitting_max, size_t num_coeff,
+		double coeff[], float best_fit[], float residual[], bool final_mask[], float rms[],
+		int32_t status[], int32_t lsqfit_status[], size_t num_devices, int const device_ids[]) noexcept {
+	return SinusoidBatchHost(context, num_nwave, nwave, num_spectra, num_data, data, data_stride, mask,
+			mask_stride, clip_threshold_sigma, num_fitting_max, num_coeff, coeff, best_fit, residual,
+			final_mask, rms, status, lsqfit_status, true, num_devices, device_ids);
 }
 
 sakura_Status sakura_LSQFitSinusoidFloatBatchDevice(struct sakura_LSQFitContextFloat const *context,
@@ -975,3 +1404,13 @@ sakura_Status sakura_SubtractSinusoidFloat(struct sakura_LSQFitContextFloat cons
 			apply, nullptr, use_idx, out);
 }
 
+// ---------------------------------------------------------------- tuning
+
+void sakura_b200_SetHostPipelineTuning(int64_t chunk_mib, int64_t packed_kib) noexcept {
+	if (chunk_mib >= 1 && chunk_mib <= 4096) {
+		g_chunk_mib.store(static_cast<size_t>(chunk_mib));
+	}
+	if (packed_kib >= 0 && packed_kib <= (1 << 20)) {
+		g_packed_kib.store(static_cast<size_t>(packed_kib));
+	}
+}

@@ -25,6 +25,7 @@
 #include <mutex>
 #include <new>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace sakura_b200 {
@@ -109,7 +110,7 @@ struct PipelineSlot {
 	cudaStream_t down = nullptr; // bulk result download, so that it never blocks the next upload
 	cudaEvent_t flags_ready = nullptr; // kernel done and per-row flags on the host
 	cudaEvent_t down_done = nullptr; // result buffers of this slot may be overwritten
-	DeviceBuffer data, mask, coeff, best_fit, residual, final_mask, small, handover;
+	DeviceBuffer data, mask, coeff, best_fit, residual, final_mask, small, handover, boundary;
 	std::vector<int32_t> h_flags;
 	size_t row0 = 0;
 	size_t rows = 0; // non-zero while a chunk is in flight in this slot
@@ -122,6 +123,7 @@ struct PipelineSlot {
 		final_mask.Release();
 		small.Release();
 		handover.Release();
+		boundary.Release();
 		if (stream != nullptr) {
 			cudaStreamDestroy(stream);
 			stream = nullptr;
@@ -174,6 +176,14 @@ struct sakura_LSQFitContextFloat {
 	std::vector<int32_t> *h_flags;
 	int32_t const *last_handover; // device counter of the rows the last fit handed to a slower kernel
 	sakura_b200::capi::PipelineSlot *slots; // kPipelineSlots entries, created on first pipelined call
+	// small host batches (the reference's single-row signatures above all): one pinned host arena, one
+	// device arena, one upload and one download per call on a stream of the context's own
+	void *h_pack;
+	size_t h_pack_cap;
+	sakura_b200::capi::DeviceBuffer d_pack;
+	cudaStream_t pack_stream;
+	// ...MultiDevice entry points: one replica of this context per device (created on first use)
+	std::vector<std::pair<int, sakura_LSQFitContextFloat *> > *replicas;
 };
 
 namespace sakura_b200 {
