@@ -155,6 +155,52 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ----------------------------------------------------------------------------- host placement
+def gpu_numa_cpus(torch, index: int):
+    """(NUMA node, CPUs of that node this process may run on) of CUDA device `index`, from sysfs; (None, None)
+    when the box does not say (single node, container without sysfs)."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        addr = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{addr}/numa_node") as fh:
+            node = int(fh.read().strip())
+        if node < 0:
+            return None, None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        return node, (cpus or None)
+    except Exception:
+        return None, None
+
+
+class NearGpu:
+    """Runs the enclosed allocations on the CPUs of the GPU's NUMA node, so that page-locked staging
+    buffers (placed where the allocating thread runs) sit on the memory the GPU's PCIe root port is
+    attached to; the previous affinity is restored on exit (the CPU baseline uses every core)."""
+
+    def __init__(self, torch, index: int):
+        self.node, self.cpus = gpu_numa_cpus(torch, index)
+        self.saved = None
+
+    def __enter__(self):
+        if self.cpus:
+            try:
+                self.saved = os.sched_getaffinity(0)
+                os.sched_setaffinity(0, self.cpus)
+            except OSError:
+                self.saved = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.saved is not None:
+            os.sched_setaffinity(0, self.saved)
+
+
 # ----------------------------------------------------------------------------- synthetic data
 def generate_on_device(torch, rows: int, n: int, seed: int, device, ripple: bool = False):
     """Synthetic spectra of SURVEY 8(d) generated on the GPU (quintic continuum, Gaussian
@@ -243,7 +289,9 @@ def run_reference(args) -> None:
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, rows_per_step=rows),
+        "config": workload_config(args),
+        "sample_spectra_per_step": rows,
+        "values": {"num_fitting_max_%d (configs[1], headline)" % args.nfit: value},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": ora.kind,
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -252,12 +300,16 @@ def run_reference(args) -> None:
     print(json.dumps(line))
 
 
-def workload_config(args, rows_per_step=None) -> dict:
+def workload_config(args) -> dict:
+    """The same dictionary in both arms (the driver compares them): the workload is BASELINE configs[1];
+    how many of its spectra a step of the CPU arm samples is reported outside `config`."""
     return {
         "workload": ("BASELINE configs[1]: ALMA-TP-like spectra x 4096 ch float32 + bool mask, "
                      "sakura_LSQFitPolynomialFloat semantics, polynomial order 5, 5 clip iterations "
-                     "(num_fitting_max=5) at 3 sigma; outputs coeff+residual+final_mask+rms+status"),
-        "spectra_per_gpu": args.rows if rows_per_step is None else rows_per_step,
+                     "(num_fitting_max=5) at 3 sigma; outputs coeff+residual+final_mask+rms+status. The metric "
+                     "string is BASELINE.json's (it says 3 clip iterations); `value` is this 5-iteration "
+                     "config, the 3-iteration figure is `values.num_fitting_max_3`"),
+        "spectra_per_gpu": args.rows,
         "num_data": args.nchan, "order": args.order, "num_fitting_max": args.nfit,
         "clip_threshold_sigma": args.clip,
         "l2": "inputs (20 GiB per step) far exceed the 126 MB L2; no explicit flush needed",
@@ -265,11 +317,12 @@ def workload_config(args, rows_per_step=None) -> dict:
     }
 
 
-def side_configs(lib, torch, device, rows: int = 16384, n: int = 8192, reps: int = 3) -> dict:
-    """BASELINE configs[2] and [3] at reduced row count (same channels, bases, iterations):
-    device-resident spectra/s of the cubic-spline (20 pieces) and sinusoid (nwave 0..20) fits.
-    Not bench lines of their own; reported under "also" so the round's numbers for the
-    tensor-core kernel are in the same JSON."""
+def side_configs(lib, torch, device, host=None, rows: int = 1 << 18, n: int = 8192, reps: int = 2) -> dict:
+    """BASELINE configs[2] and [3] at their full size (262 144 x 8192 ch, 20 pieces / wave numbers 0..20,
+    3 fits): device-resident spectra/s of the cubic-spline and sinusoid fits, and -- through the
+    host-pointer C ABI with pinned host buffers, copies inside the timed region -- their e2e figure on
+    as many rows as the pinned buffers of the headline e2e hold (`host`: dict of pinned tensors).
+    Not bench lines of their own; reported under "also"."""
     out = {}
     data, mask = generate_on_device(torch, rows, n, seed=20240611 + 7, device=device, ripple=True)
     res = torch.empty(rows, n, dtype=torch.float32, device=device)
@@ -280,8 +333,7 @@ def side_configs(lib, torch, device, rows: int = 16384, n: int = 8192, reps: int
     stream = torch.cuda.current_stream(device)
 
     def timeit(fn):
-        for _ in range(2):
-            assert fn() == 0, lib.last_error()
+        assert fn() == 0, lib.last_error()
         torch.cuda.synchronize(device)
         e0 = torch.cuda.Event(enable_timing=True)
         e1 = torch.cuda.Event(enable_timing=True)
@@ -291,6 +343,36 @@ def side_configs(lib, torch, device, rows: int = 16384, n: int = 8192, reps: int
         e1.record(stream)
         torch.cuda.synchronize(device)
         return e0.elapsed_time(e1) / reps
+
+    def host_views(kind, ncoeff_doubles):
+        """Views of the pinned e2e buffers as rows of n channels, filled from the device workload."""
+        if host is None:
+            return None
+        er = min(host["data"].numel() // n, rows)
+        hv = {"rows": er,
+              "data": host["data"].view(-1)[:er * n].view(er, n), "mask": host["mask"].view(-1)[:er * n].view(er, n),
+              "resid": host["resid"].view(-1)[:er * n].view(er, n), "fmask": host["fmask"].view(-1)[:er * n].view(er, n),
+              "rms": torch.empty(er, dtype=torch.float32, pin_memory=True),
+              "status": torch.empty(er, dtype=torch.int32, pin_memory=True),
+              "lsq": torch.empty(er, dtype=torch.int32, pin_memory=True),
+              "coeff": torch.empty(er, ncoeff_doubles, dtype=torch.float64, pin_memory=True)}
+        hv["data"].copy_(data[:er])
+        hv["mask"].copy_(mask[:er])
+        torch.cuda.synchronize(device)
+        return hv
+
+    def time_host(fn, hv, d2h_extra):
+        assert fn() == 0, lib.last_error()
+        torch.cuda.synchronize(device)
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            fn()
+        dt = (time.perf_counter() - t0) / reps
+        er = hv["rows"]
+        same = bool(torch.equal(hv["fmask"], fm[:er].cpu())) and bool(torch.equal(hv["status"], st[:er].cpu()))
+        return {"value": er / dt, "unit": UNIT, "spectra_per_step": er, "ms_per_step": dt * 1e3,
+                "h2d_bytes_per_step": er * n * 5, "d2h_bytes_per_step": er * (n * 5 + d2h_extra),
+                "final_mask_and_status_match_device_path": same}
 
     peak_hbm = measured_peak_gbs()[0]
     # C3: cubic spline, 20 pieces, 3 fits
@@ -304,11 +386,18 @@ def side_configs(lib, torch, device, rows: int = 16384, n: int = 8192, reps: int
         stream.cuda_stream))
     bps = n * 10 + 8 * 4 * npiece + 8 * (npiece + 1) + 8
     out["config_c3_cubic_spline"] = {
-        "workload": f"{rows} x {n} ch, 20 pieces, 3 fits, residual out", "value": rows / (ms * 1e-3),
+        "workload": f"BASELINE configs[2]: {rows} x {n} ch, 20 pieces, 3 fits, residual out", "value": rows / (ms * 1e-3),
         "unit": UNIT, "ms": ms, "kernel": lib.last_kernel_name(), "rows_ok": int((st == 0).sum().item()),
         "roofline": {"bound": "hbm", "bytes_per_spectrum": bps,
                      "achieved": rows * bps / (ms * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s",
                      "frac": rows * bps / (ms * 1e-3) / 1e9 / peak_hbm}}
+    hv = host_views("spline", npiece * 4)
+    if hv is not None:
+        h_bd = torch.empty(hv["rows"], npiece + 1, dtype=torch.int64, pin_memory=True)
+        out["config_c3_cubic_spline"]["e2e"] = time_host(lambda: lib.lib.sakura_LSQFitCubicSplineFloatBatch(
+            ctx, npiece, hv["rows"], n, hv["data"].data_ptr(), n, hv["mask"].data_ptr(), n, 3.0, 3,
+            hv["coeff"].data_ptr(), None, hv["resid"].data_ptr(), hv["fmask"].data_ptr(), hv["rms"].data_ptr(),
+            h_bd.data_ptr(), hv["status"].data_ptr(), hv["lsq"].data_ptr()), hv, 8 * 4 * npiece + 8 * (npiece + 1) + 12)
     lib.destroy_context(ctx)
     # C4: sinusoid, wave numbers 0..20 (41 bases), 3 fits
     s, ctx = lib.create_sinusoid_context(20, n)
@@ -322,24 +411,31 @@ def side_configs(lib, torch, device, rows: int = 16384, n: int = 8192, reps: int
     flop = 2.0 * n * (96 + 48 + 3 * 48)
     sm_mhz = measured_peaks().get("sm_max_mhz", 1965.0)
     peak_tf = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12
+    bps4 = n * 10 + 8 * 41 + 8
     out["config_c4_sinusoid"] = {
-        "workload": f"{rows} x {n} ch, nwave 0..20 (41 bases), 3 fits, residual out",
+        "workload": f"BASELINE configs[3]: {rows} x {n} ch, nwave 0..20 (41 bases), 3 fits, residual out",
         "value": rows / (ms * 1e-3), "unit": UNIT, "ms": ms, "kernel": lib.last_kernel_name(),
         "rows_ok": int((st == 0).sum().item()),
         "roofline": {"bound": "tensor", "flop_per_spectrum": flop,
                      "achieved": rows * flop / (ms * 1e-3) / 1e12, "peak": peak_tf, "unit": "TFLOP/s",
                      "frac": rows * flop / (ms * 1e-3) / 1e12 / peak_tf,
                      "peak_source": "FP64 DMMA/DFMA issue rate measured on this GPU (64 FMA/clk/SM, "
-                                    "tools/microbench.cu; ncu dmma sub-pipe) x 148 SMs x max SM clock"}}
+                                    "tools/microbench.cu; ncu dmma sub-pipe) x 148 SMs x max SM clock",
+                     "hbm_bytes_per_spectrum": bps4,
+                     "hbm_frac": rows * bps4 / (ms * 1e-3) / 1e9 / peak_hbm}}
+    hv = host_views("sinusoid", 41)
+    if hv is not None:
+        out["config_c4_sinusoid"]["e2e"] = time_host(lambda: lib.lib.sakura_LSQFitSinusoidFloatBatch(
+            ctx, 21, nw.ctypes.data, hv["rows"], n, hv["data"].data_ptr(), n, hv["mask"].data_ptr(), n, 3.0, 3, 41,
+            hv["coeff"].data_ptr(), None, hv["resid"].data_ptr(), hv["fmask"].data_ptr(), hv["rms"].data_ptr(),
+            hv["status"].data_ptr(), hv["lsq"].data_ptr()), hv, 8 * 41 + 12)
     lib.destroy_context(ctx)
-    del data, mask, res, fm, co
-    out["config_c5_chain"] = chain_config(lib, torch, device)
     return out
 
 
-def chain_config(lib, torch, device, rows: int = 1 << 17, n: int = 2048, reps: int = 3) -> dict:
+def chain_config(lib, torch, device, rows: int = 1 << 19, n: int = 2048, reps: int = 3) -> dict:
     """BASELINE configs[4] (the e2eReduce chain, bench/e2eReduce/src/main.cc:80-240) on device arrays
-    at reduced row count: linear Tsys interpolation to one row per spectrum, uint8 flags -> mask with
+    at its per-GPU size (4 M spectra over 8 GPUs = 524 288 per rank): linear Tsys interpolation to one row per spectrum, uint8 flags -> mask with
     edge flags, calibration fused into the poly-5 fit (NaN/Inf flags merged, 5 fits), clipping of the
     residual merged into the mask, statistics. One timed pass = all five steps back to back."""
     from sakura_b200.device_api import DeviceFits
@@ -392,7 +488,7 @@ def chain_config(lib, torch, device, rows: int = 1 << 17, n: int = 2048, reps: i
     bps = n * (4 + 1 + 1 + 4) + 48 + 8 + 48  # SURVEY 8(d), C5 fused figure
     return {"workload": f"{rows} x {n} ch: Tsys interpolation + mask builders + calibrate&fit (poly-5, 5 fits) "
                         "+ residual clipping + statistics, device arrays",
-            "value": rows / (ms * 1e-3), "unit": UNIT, "ms": ms, "kernels": kernels, "rows_ok": rows_ok,
+            "value": rows / (ms * 1e-3), "unit": UNIT, "ms": ms, "rows": rows, "kernels": kernels, "rows_ok": rows_ok,
             "roofline": {"bound": "hbm", "bytes_per_spectrum": bps,
                          "achieved": rows * bps / (ms * 1e-3) / 1e9, "peak": measured_peak_gbs()[0],
                          "unit": "GB/s", "frac": rows * bps / (ms * 1e-3) / 1e9 / measured_peak_gbs()[0]}}
@@ -533,33 +629,37 @@ def run_ours(args) -> None:
         finally:
             del os.environ["SAKURA_B200_POLY_SCREEN"]
             del fm_screen
-        try:
-            also.update(side_configs(lib, torch, device))
-        except Exception as exc:  # the headline line must not depend on the side configs
-            also["side_configs_error"] = repr(exc)
 
     # ---- e2e: host buffers through the C ABI, copies inside the timed region --------------
     e2e = None
+    host = None
     if not args.no_e2e:
         er = min(args.e2e_rows, rows)
-        h_data = torch.empty(er, n, dtype=torch.float32, pin_memory=True)
-        h_mask = torch.empty(er, n, dtype=torch.bool, pin_memory=True)
+        # page-locked staging on the NUMA node of this rank's GPU (see NearGpu)
+        with NearGpu(torch, local_rank) as near:
+            h_data = torch.empty(er, n, dtype=torch.float32, pin_memory=True)
+            h_mask = torch.empty(er, n, dtype=torch.bool, pin_memory=True)
+            h_coeff = torch.empty(er, K, dtype=torch.float64, pin_memory=True)
+            h_resid = torch.empty(er, n, dtype=torch.float32, pin_memory=True)
+            h_fmask = torch.empty(er, n, dtype=torch.bool, pin_memory=True)
+            h_rms = torch.empty(er, dtype=torch.float32, pin_memory=True)
+            h_status = torch.empty(er, dtype=torch.int32, pin_memory=True)
+            h_lsq = torch.empty(er, dtype=torch.int32, pin_memory=True)
         h_data.copy_(data[:er])
         h_mask.copy_(mask[:er])
-        h_coeff = torch.empty(er, K, dtype=torch.float64, pin_memory=True)
-        h_resid = torch.empty(er, n, dtype=torch.float32, pin_memory=True)
-        h_fmask = torch.empty(er, n, dtype=torch.bool, pin_memory=True)
-        h_rms = torch.empty(er, dtype=torch.float32, pin_memory=True)
-        h_status = torch.empty(er, dtype=torch.int32, pin_memory=True)
-        h_lsq = torch.empty(er, dtype=torch.int32, pin_memory=True)
+        host = {"data": h_data, "mask": h_mask, "resid": h_resid, "fmask": h_fmask}
         st2, ctx2 = lib.create_polynomial_context(order, n)
         assert st2 == 0
+        import ctypes
+        dev_ids = (ctypes.c_int * 1)(local_rank)
 
         def e2e_step():
-            rc = lib.lib.sakura_LSQFitPolynomialFloatBatch(
+            # the library's own sharding entry point, here with the one GPU this rank owns (a
+            # single-process caller passes every GPU of the box: tools/bench_multidevice.py)
+            rc = lib.lib.sakura_LSQFitPolynomialFloatBatchMultiDevice(
                 ctx2, order, er, n, h_data.data_ptr(), n, h_mask.data_ptr(), n, args.clip, args.nfit,
                 K, h_coeff.data_ptr(), None, h_resid.data_ptr(), h_fmask.data_ptr(), h_rms.data_ptr(),
-                h_status.data_ptr(), h_lsq.data_ptr())
+                h_status.data_ptr(), h_lsq.data_ptr(), 1, ctypes.cast(dev_ids, ctypes.c_void_p))
             if rc != 0:
                 raise RuntimeError(f"e2e fit call failed: {rc} {lib.last_error()}")
 
@@ -578,12 +678,37 @@ def run_ours(args) -> None:
                "h2d_bytes_per_step": er * (n * 4 + n),
                "d2h_bytes_per_step": er * (n * 4 + n + 8 * K + 4 + 4 + 4),
                "spectra_per_step": er, "ms_per_step": dt * 1e3,
-               "api": "sakura_LSQFitPolynomialFloatBatch (pinned host buffers, 4-slot upload | kernel | download pipeline)",
+               "api": "sakura_LSQFitPolynomialFloatBatchMultiDevice (pinned host buffers, per GPU a 4-slot "
+                      "upload | kernel | download pipeline)",
+               "pcie_gbs_per_direction_per_gpu": er * (n * 4 + n) / dt / 1e9,
+               "pinned_buffers_numa_node": near.node,
                "status_match_device_path": bool(np.array_equal(h_status.numpy()[:snap_rows],
                                                                  snap_status[:er])),
                "final_mask_match_device_path": bool(np.array_equal(h_fmask.numpy()[:snap_rows],
                                                                      snap_fmask[:er]))}
         lib.destroy_context(ctx2)
+
+    # ---- the other BASELINE configs (side figures) ------------------------------------------
+    if not args.no_also:
+        if world == 1:
+            try:
+                also.update(side_configs(lib, torch, device, host=host))
+            except Exception as exc:  # the headline line must not depend on the side configs
+                also["side_configs_error"] = repr(exc)
+        try:
+            # configs[4] is defined over 8 GPUs: every rank runs its 524 288-row share
+            c5 = chain_config(lib, torch, device)
+            if dist is not None:
+                t = torch.tensor([c5["ms"]], dtype=torch.float64, device=device)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                c5["ms"] = float(t.item())
+                c5["value"] = world * c5["rows"] / (c5["ms"] * 1e-3)
+                c5["workload"] += f" (x {world} ranks, max over ranks)"
+            also["config_c5_chain"] = c5
+        except Exception as exc:
+            also["config_c5_error"] = repr(exc)
+    host = None
+    if not args.no_e2e:
         del h_data, h_mask, h_resid, h_fmask
 
     # ---- CPU baseline: the reference's own code on this box's host cores ---------------------
@@ -637,6 +762,9 @@ def run_ours(args) -> None:
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args),
+            "values": {"num_fitting_max_%d (configs[1], headline)" % args.nfit: world * rows / (ms_step * 1e-3),
+                       "num_fitting_max_3 (the metric string's iteration count)":
+                           also.get("num_fitting_max_3", {}).get("value")},
             "clocks": clocks,
             "e2e": e2e,
             "gpu_launches": launches,

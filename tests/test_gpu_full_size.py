@@ -92,3 +92,84 @@ def test_full_size_properties(lib, oracle, rows, n, nfit):
     g["best_fit"] = None
     compare_fit(g, o, hd, 3.0, poly_rescale_n=n)
     lib.destroy_context(ctx)
+
+
+def _rms_from_residual(torch, out, rows):
+    """rms of baseline.cc:1200-1207 recomputed with torch from the residual the kernel wrote."""
+    worst = 0.0
+    chunk = 1 << 14
+    for r0 in range(0, rows, chunk):
+        r = out["residual"][r0:r0 + chunk].double()
+        v = out["final_mask"][r0:r0 + chunk]
+        cnt = v.sum(dim=1).double()
+        mean = (r * v).sum(dim=1) / cnt
+        var = ((r * r) * v).sum(dim=1) / cnt - mean * mean
+        rms = var.abs().sqrt()
+        worst = max(worst, ((rms - out["rms"][r0:r0 + chunk].double()).abs() / rms).max().item())
+    return worst
+
+
+@pytest.mark.parametrize("kind", ["spline", "sinusoid"])
+def test_full_size_properties_c3_c4(lib, oracle, kind):
+    """BASELINE configs[2] / configs[3] at full size (262 144 x 8192; 20 pieces / wave numbers 0..20,
+    3 fits) on device arrays: size-independent properties plus the oracle on a sample of rows."""
+    import torch
+    import bench
+    from sakura_b200.device_api import DeviceFits
+    rows, n, nfit, clip = 1 << 18, 8192, 3, 3.0
+    dev = torch.device("cuda", 0)
+    fits = DeviceFits(lib)
+    data, mask = bench.generate_on_device(torch, rows, n, seed=31, device=dev, ripple=True)
+    if kind == "spline":
+        st, ctx = lib.create_cubicspline_context(20, n)
+        fit = lambda d, m, f, **kw: fits.cubicspline(ctx, 20, d, m, clip, f, **kw)
+        expect_kernel = "spline_moments"
+    else:
+        st, ctx = lib.create_sinusoid_context(20, n)
+        waves = list(range(21))
+        fit = lambda d, m, f, **kw: fits.sinusoid(ctx, waves, d, m, clip, f, **kw)
+        expect_kernel = "sinusoid_dmma"
+    assert st == STATUS_OK
+    out = fit(data, mask, nfit)
+    torch.cuda.synchronize()
+    assert out["call_status"] == STATUS_OK, lib.last_error()
+    assert lib.last_kernel_name() == expect_kernel
+    assert int((out["status"] != 0).sum()) == 0
+    fm = out["final_mask"]
+    assert not bool((fm & ~mask).any())
+    assert int((mask & ~fm).sum()) > rows
+    if kind == "spline":
+        b = out["boundary"]
+        assert bool((b[:, 0] == 0).all()) and bool((b[:, -1] == n).all())
+        assert bool((b[:, 1:] > b[:, :-1]).all())
+    assert _rms_from_residual(torch, out, rows) < 1e-6
+    # idempotence: the final mask is a fixed point of one more fit and reproduces the residual
+    # (spline: the piece boundaries follow the mask, so only the rms is compared there)
+    sub = slice(0, 1 << 15)
+    again = fit(data[sub], fm[sub].clone(), 1)
+    torch.cuda.synchronize()
+    assert bool((again["final_mask"] == fm[sub]).all())
+    if kind == "sinusoid":
+        tol = 1e-5 * out["residual"][sub].abs() + 2.4e-7 * (data[sub] - out["residual"][sub]).abs() + 1e-6
+        assert bool(((again["residual"] - out["residual"][sub]).abs() <= tol).all())
+        assert float(((again["rms"] - out["rms"][sub]).abs() / out["rms"][sub]).max()) < 1e-6
+    # run-to-run: bit-identical
+    twice = fit(data[sub], mask[sub], nfit)
+    torch.cuda.synchronize()
+    for key in ("final_mask", "rms", "residual", "coeff", "status"):
+        assert torch.equal(twice[key], out[key][sub]), key
+    # the oracle on a sample of rows
+    take = torch.arange(0, rows, rows // 96, device=dev)[:96]
+    hd, hm = data[take].cpu().numpy(), mask[take].cpu().numpy()
+    g = {k: (v[take].cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
+    g["best_fit"] = None
+    if kind == "spline":
+        o = oracle.lsqfit_cubicspline_batch(20, hd, hm, clip, nfit)
+        g["boundary"] = g["boundary"].astype(np.uint64)
+        assert np.array_equal(g["boundary"], o["boundary"])
+        reported = compare_fit(g, o, hd, clip, check_coeff=False, resid_atol=5e-5)
+    else:
+        o = oracle.lsqfit_sinusoid_batch(list(range(21)), hd, hm, clip, nfit)
+        reported = compare_fit(g, o, hd, clip)
+    assert reported == [], reported
+    lib.destroy_context(ctx)

@@ -21,7 +21,8 @@ KEYS = ("status", "lsqfit_status", "final_mask", "rms", "coeff", "residual", "be
 def assert_bitwise(a, b):
     assert a["call_status"] == STATUS_OK and b["call_status"] == STATUS_OK
     for key in KEYS:
-        if key not in a:
+        if a.get(key) is None:
+            assert b.get(key) is None, key
             continue
         x, y = np.ascontiguousarray(a[key]), np.ascontiguousarray(b[key])
         assert x.shape == y.shape, key
