@@ -674,6 +674,36 @@ def run_ours(args) -> None:
             t = torch.tensor([dt], dtype=torch.float64, device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
+        # copy-only ceiling of the box for the same step: the same bytes up and down on the same pinned
+        # buffers with no kernel, every rank at once (what the host feed allows at this GPU count)
+        d_up = torch.empty(er * n * 5, dtype=torch.uint8, device=device)
+        d_dn = torch.empty(er * n * 5, dtype=torch.uint8, device=device)
+        flat_in = [h_data.view(-1).view(torch.uint8), h_mask.view(-1).view(torch.uint8)]
+        flat_out = [h_resid.view(-1).view(torch.uint8), h_fmask.view(-1).view(torch.uint8)]
+        s_up, s_dn = torch.cuda.Stream(device), torch.cuda.Stream(device)
+
+        def copy_only():
+            with torch.cuda.stream(s_up):
+                d_up[:er * n * 4].copy_(flat_in[0], non_blocking=True)
+                d_up[er * n * 4:].copy_(flat_in[1], non_blocking=True)
+            with torch.cuda.stream(s_dn):
+                flat_out[0].copy_(d_dn[:er * n * 4], non_blocking=True)
+                flat_out[1].copy_(d_dn[er * n * 4:], non_blocking=True)
+            torch.cuda.synchronize(device)
+
+        copy_only()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(2):
+            copy_only()
+        cdt = (time.perf_counter() - t0) / 2
+        if dist is not None:
+            t = torch.tensor([cdt], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            cdt = float(t.item())
+        del d_up, d_dn
+        e2e_step()  # the probe overwrote the result buffers: put the fit's results back
+        torch.cuda.synchronize(device)
         e2e = {"value": world * er / dt, "unit": UNIT,
                "h2d_bytes_per_step": er * (n * 4 + n),
                "d2h_bytes_per_step": er * (n * 4 + n + 8 * K + 4 + 4 + 4),
@@ -681,6 +711,11 @@ def run_ours(args) -> None:
                "api": "sakura_LSQFitPolynomialFloatBatchMultiDevice (pinned host buffers, per GPU a 4-slot "
                       "upload | kernel | download pipeline)",
                "pcie_gbs_per_direction_per_gpu": er * (n * 4 + n) / dt / 1e9,
+               "copy_only_ceiling": {"spectra_per_s": world * er / cdt, "ms_per_step": cdt * 1e3,
+                                     "gbs_per_direction_per_gpu": er * n * 5 / cdt / 1e9,
+                                     "what": "the step's bytes (5 per channel each way) copied up and down "
+                                             "concurrently on every rank, no kernel"},
+               "frac_of_copy_only_ceiling": cdt / dt,
                "pinned_buffers_numa_node": near.node,
                "status_match_device_path": bool(np.array_equal(h_status.numpy()[:snap_rows],
                                                                  snap_status[:er])),
