@@ -5,6 +5,8 @@
 // and fails loudly (status + message on stderr) if no CUDA device is usable.
 #include "capi_internal.cuh"
 
+#include <algorithm>
+
 using namespace sakura_b200;
 using namespace sakura_b200::capi;
 
@@ -125,6 +127,33 @@ void ReleaseDeviceState(Context *c) {
 	c->device = -1;
 }
 
+// Column sums of the extended table over blocks of kSinSumStep channels and over all channels,
+// appended to the table: [steps + 1][ext_ld], the last row the total. The fit kernel gets the sums over
+// a spectrum's VALID channels as "all minus flagged" (a few per cent of the channels) instead of
+// contracting the whole mask with the table. Sums of the table's own doubles, in extended precision.
+void AppendExtSums(std::vector<double> *ext, int cols, size_t num_data) {
+	size_t const ext_ld = static_cast<size_t>(SinusoidExtLd(cols));
+	size_t const chunk_doubles = num_data * kSinExtChunkLd;
+	size_t const steps = (num_data + kSinSumStep - 1) / kSinSumStep;
+	size_t const base = ext->size();
+	ext->resize(base + (steps + 1) * ext_ld, 0.0);
+	std::vector<long double> total(ext_ld, 0.0L);
+	for (size_t s = 0; s < steps; ++s) {
+		size_t const i1 = std::min(num_data, (s + 1) * kSinSumStep);
+		for (size_t col = 0; col < ext_ld; ++col) {
+			long double acc = 0.0L;
+			for (size_t i = s * kSinSumStep; i < i1; ++i) {
+				acc += static_cast<long double>((*ext)[(col / 32) * chunk_doubles + i * kSinExtChunkLd + (col % 32)]);
+			}
+			(*ext)[base + s * ext_ld + col] = static_cast<double>(acc);
+			total[col] += acc;
+		}
+	}
+	for (size_t col = 0; col < ext_ld; ++col) {
+		(*ext)[base + steps * ext_ld + col] = static_cast<double>(total[col]);
+	}
+}
+
 sakura_Status CreateContext(int type, uint16_t param, size_t num_data, Context **out) {
 	size_t const num_bases = ContextBases(type, param);
 	size_t const lsq_max = LsqBases(type, param);
@@ -196,6 +225,7 @@ sakura_Status CreateContext(int type, uint16_t param, size_t num_data, Context *
 							static_cast<double>(t[m]);
 				}
 			}
+			AppendExtSums(c->h_ext, cols, num_data);
 		}
 		break;
 	default:
@@ -220,6 +250,7 @@ sakura_Status CreateContext(int type, uint16_t param, size_t num_data, Context *
 					at(i, 2 * m) = cos(x);
 				}
 			}
+			AppendExtSums(c->h_ext, cols, num_data);
 		}
 		break;
 	}
@@ -415,6 +446,7 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 			sp.table_a = sp.table_p + n * sp.ld_p;
 			sp.ext_p = c->d_ext.As<double>();
 			sp.ext_ld = SinusoidExtLd(c->ext_cols);
+			sp.ext_sums = sp.ext_p + static_cast<size_t>(sp.ext_ld / 32) * n * kSinExtChunkLd;
 			sp.data = f.data;
 			sp.data_stride = f.data_stride;
 			sp.mask = f.mask;

@@ -36,10 +36,20 @@ __host__ __device__ constexpr int LdltDoubles(int Kp) {
 // in rows 0..Kp-1 (rows/columns K..Kp-1 padded with the identity), right-hand side in row Kp.
 // After the factorisation the border row holds D^-1 L^-1 b; then L^T x = z gives x[0..Kp).
 // Returns false (warp-uniform) when a pivot is not safely positive. All 32 lanes must call.
-template<int NT8>
+// PACKED: row i of the lower triangle (and the border row) starts at i (i + 1) / 2 instead of
+// i * LdltLd(Kp): half the shared memory, so that twice as many warps can solve at the same time.
+// (Reads of a diagonal block's upper triangle then run a few entries into the next row: those values
+// never reach a result, as with the stale upper triangle of the unpacked layout.)
+__host__ __device__ constexpr int LdltPackedDoubles(int Kp) {
+	return (Kp + 1) * (Kp + 2) / 2;
+}
+
+template<int NT8, bool PACKED = false>
 __device__ bool WarpLdltSolve(double *A, int K, double *xout, int lane) {
 	constexpr int Kp = 8 * NT8;
-	constexpr int LD = LdltLd(Kp);
+	auto Row = [](int i) {
+		return PACKED ? (i * (i + 1)) / 2 : i * LdltLd(8 * NT8);
+	};
 	constexpr unsigned kFull = 0xffffffffu;
 	int const r8 = lane >> 2;
 	int const c4 = lane & 3;
@@ -54,7 +64,7 @@ __device__ bool WarpLdltSolve(double *A, int K, double *xout, int lane) {
 		double row[8], dinv[8], dneg[8];
 #pragma unroll
 		for (int j = 0; j < 8; ++j) {
-			row[j] = A[(c0 + l8) * LD + c0 + j];
+			row[j] = A[Row(c0 + l8) + c0 + j];
 		}
 #pragma unroll
 		for (int k = 0; k < 8; ++k) {
@@ -76,7 +86,7 @@ __device__ bool WarpLdltSolve(double *A, int K, double *xout, int lane) {
 #pragma unroll
 			for (int j = 0; j < 7; ++j) {
 				if (j < lane) {
-					A[(c0 + lane) * LD + c0 + j] = row[j];
+					A[Row(c0 + lane) + c0 + j] = row[j];
 				}
 			}
 		}
@@ -86,18 +96,18 @@ __device__ bool WarpLdltSolve(double *A, int K, double *xout, int lane) {
 			double w[8];
 #pragma unroll
 			for (int j = 0; j < 8; ++j) {
-				w[j] = A[i * LD + c0 + j];
+				w[j] = A[Row(i) + c0 + j];
 			}
 #pragma unroll
 			for (int j = 1; j < 8; ++j) {
 #pragma unroll
 				for (int t = 0; t < j; ++t) {
-					w[j] = fma(-w[t], A[(c0 + j) * LD + c0 + t], w[j]);
+					w[j] = fma(-w[t], A[Row(c0 + j) + c0 + t], w[j]);
 				}
 			}
 #pragma unroll
 			for (int j = 0; j < 8; ++j) {
-				A[i * LD + c0 + j] = w[j] * dinv[j];
+				A[Row(i) + c0 + j] = w[j] * dinv[j];
 			}
 		}
 		__syncwarp();
@@ -105,37 +115,47 @@ __device__ bool WarpLdltSolve(double *A, int K, double *xout, int lane) {
 		double const nd0 = c4 == 0 ? dneg[0] : (c4 == 1 ? dneg[1] : (c4 == 2 ? dneg[2] : dneg[3]));
 		double const nd1 = c4 == 0 ? dneg[4] : (c4 == 1 ? dneg[5] : (c4 == 2 ? dneg[6] : dneg[7]));
 		for (int I = kb + 1; I < NT8; ++I) {
-			double const *ai = A + (8 * I + r8) * LD + c0 + c4;
+			double const *ai = A + Row(8 * I + r8) + c0 + c4;
 			double const a0 = ai[0] * nd0;
 			double const a1 = ai[4] * nd1;
 			for (int J = kb + 1; J <= I; ++J) {
-				double const *bj = A + (8 * J + r8) * LD + c0 + c4;
-				double *cp = A + (8 * I + r8) * LD + 8 * J + 2 * c4;
+				double const *bj = A + Row(8 * J + r8) + c0 + c4;
+				double *cp = A + Row(8 * I + r8) + 8 * J + 2 * c4;
 				double x0 = cp[0];
 				double x1 = cp[1];
 				dmma(x0, x1, a0, bj[0]);
 				dmma(x0, x1, a1, bj[4]);
-				cp[0] = x0;
-				cp[1] = x1;
+				if (PACKED && J == I) {
+					// the diagonal block's upper triangle does not exist in the packed layout
+					if (2 * c4 <= r8) {
+						cp[0] = x0;
+					}
+					if (2 * c4 + 1 <= r8) {
+						cp[1] = x1;
+					}
+				} else {
+					cp[0] = x0;
+					cp[1] = x1;
+				}
 			}
 		}
 		// border row
 		for (int j = c0 + 8 + lane; j < Kp; j += 32) {
-			double acc = A[Kp * LD + j];
+			double acc = A[Row(Kp) + j];
 #pragma unroll
 			for (int t = 0; t < 8; ++t) {
-				acc = fma(A[Kp * LD + c0 + t] * dneg[t], A[j * LD + c0 + t], acc);
+				acc = fma(A[Row(Kp) + c0 + t] * dneg[t], A[Row(j) + c0 + t], acc);
 			}
-			A[Kp * LD + j] = acc;
+			A[Row(Kp) + j] = acc;
 		}
 		__syncwarp();
 	}
 	// L^T x = z; lane holds x[lane] and x[lane + 32]
-	double xa = (lane < Kp) ? A[Kp * LD + lane] : 0.0;
-	double xb = (Kp > 32 && lane + 32 < Kp) ? A[Kp * LD + lane + 32] : 0.0;
+	double xa = (lane < Kp) ? A[Row(Kp) + lane] : 0.0;
+	double xb = (Kp > 32 && lane + 32 < Kp) ? A[Row(Kp) + lane + 32] : 0.0;
 	for (int k = Kp - 1; k >= 1; --k) {
 		double const xk = (k >= 32) ? __shfl_sync(kFull, xb, k - 32) : __shfl_sync(kFull, xa, k);
-		double const *Lk = A + k * LD;
+		double const *Lk = A + Row(k);
 		if (lane < k) {
 			xa = fma(-Lk[lane], xk, xa);
 		}

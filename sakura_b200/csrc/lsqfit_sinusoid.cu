@@ -86,7 +86,8 @@ __host__ __device__ constexpr int TileDoubles(int Kp) {
 	return 16 * (LdA(Kp) > kSinExtChunkLd ? LdA(Kp) : kSinExtChunkLd);
 }
 __host__ __device__ inline int GwStride(int Kp) {
-	int const a = (Kp + 1) * LdltLd(Kp); // bordered matrix of the solve
+	// bordered matrices of the solve, packed lower triangles: one per warp = two per channel group
+	int const a = (NWARP / NGROUP) * LdltPackedDoubles(Kp);
 	int const b = RB * (Kp > 32 ? Kp : 32); // per-group partial sums of the contractions
 	int const c = 2 * TileDoubles(Kp); // two stages of table tiles per warp pair
 	int const ab = a > b ? a : b;
@@ -308,6 +309,123 @@ __device__ __forceinline__ void ReducePartials(double const (&acc)[MT][NTC][2], 
 	__syncthreads();
 }
 
+// 16 mask bytes -> 16 bits (any non-zero byte is "true"), bit b <-> byte b
+__device__ __forceinline__ unsigned MaskBits16(uint4 const m) {
+	auto nib = [](unsigned w) {
+		return ((__vcmpne4(w, 0u) & 0x80808080u) * 0x00204081u) >> 28;
+	};
+	return nib(m.x) | (nib(m.y) << 4) | (nib(m.z) << 8) | (nib(m.w) << 12);
+}
+
+// Working mask and masked column sums of the extended table of ONE spectrum, by one warp:
+//   trig[e] = sum over valid channels of ext[i][e]
+// The sums over all channels (and over every block of kSinSumStep channels) are constants of the
+// context, so only the FLAGGED channels of a block are visited -- a few per cent of the row -- and
+// subtracted; a block with more flagged than valid channels is summed directly instead. This replaces
+// the contraction mask x ext on the tensor cores (a third of the kernel's FP64 work) by ~3 loads and
+// 3 additions per flagged channel. Column 0 of the table is 1, so trig[0] is the valid-channel count.
+// Lane l accumulates columns l, l + 32, l + 64; fixed order: deterministic.
+__device__ __forceinline__ void ComplementTrigSums(SinusoidFitParams const &p, size_t row, bool live,
+		uint8_t *wm, int *list, double *trig, int lane) {
+	int const n = p.n;
+	int const ext_ld = p.ext_ld;
+	size_t const ext_chunk = static_cast<size_t>(n) * kSinExtChunkLd;
+	int const steps = (n + kSinSumStep - 1) / kSinSumStep;
+	bool const c1 = 32 < ext_ld, c2 = 64 < ext_ld;
+	double acc[3];
+	{
+		double const *tot = p.ext_sums + static_cast<size_t>(steps) * ext_ld + lane;
+		acc[0] = live ? tot[0] : 0.0;
+		acc[1] = (live && c1) ? tot[32] : 0.0;
+		acc[2] = (live && c2) ? tot[64] : 0.0;
+	}
+	uint8_t const *gm = p.mask + (live ? row : 0) * p.mask_stride;
+	uint4 m_next = make_uint4(0u, 0u, 0u, 0u);
+	if (live && 16 * lane < n) {
+		m_next = __ldg(reinterpret_cast<uint4 const *>(gm + 16 * lane));
+	}
+	for (int st = 0; st < steps; ++st) {
+		int const base = st * kSinSumStep + 16 * lane;
+		uint4 const m = m_next;
+		if (live && base + kSinSumStep < n) {
+			m_next = __ldg(reinterpret_cast<uint4 const *>(gm + base + kSinSumStep));
+		}
+		bool const in = base < n;
+		unsigned const valid16 = (live && in) ? MaskBits16(m) : 0u;
+		if (in) {
+			uint4 w;
+			w.x = live ? (__vcmpne4(m.x, 0u) & 0x01010101u) : 0u;
+			w.y = live ? (__vcmpne4(m.y, 0u) & 0x01010101u) : 0u;
+			w.z = live ? (__vcmpne4(m.z, 0u) & 0x01010101u) : 0u;
+			w.w = live ? (__vcmpne4(m.w, 0u) & 0x01010101u) : 0u;
+			*reinterpret_cast<uint4 *>(wm + base) = w;
+		}
+		if (!live) {
+			continue;
+		}
+		unsigned const flag16 = in ? (~valid16 & 0xffffu) : 0u;
+		int const nflag = __reduce_add_sync(kFull, __popc(flag16));
+		if (nflag == 0) {
+			continue;
+		}
+		int const nin = (n - st * kSinSumStep < kSinSumStep) ? n - st * kSinSumStep : kSinSumStep;
+		bool const direct = 2 * nflag > nin; // more flagged than valid channels here: add the valid ones
+		if (direct) {
+			double const *blk = p.ext_sums + static_cast<size_t>(st) * ext_ld + lane;
+			acc[0] -= blk[0];
+			acc[1] -= c1 ? blk[32] : 0.0;
+			acc[2] -= c2 ? blk[64] : 0.0;
+		}
+		unsigned bits = direct ? valid16 : flag16;
+		int const mine = __popc(bits);
+		int incl = mine;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			int const v = __shfl_up_sync(kFull, incl, o);
+			incl += (lane >= o) ? v : 0;
+		}
+		int const total = __shfl_sync(kFull, incl, 31);
+		int at = incl - mine;
+		while (bits != 0u) {
+			list[at++] = base + __ffs(bits) - 1;
+			bits &= bits - 1u;
+		}
+		__syncwarp();
+		double part[3] = { 0.0, 0.0, 0.0 };
+		for (int t = 0; t < total; t += 4) {
+			bool v[4];
+			double e0[4], e1[4], e2[4];
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				v[q] = t + q < total;
+				int const ch = list[v[q] ? t + q : t];
+				double const *er = p.ext_p + static_cast<size_t>(ch) * kSinExtChunkLd + lane;
+				e0[q] = __ldg(er);
+				e1[q] = c1 ? __ldg(er + ext_chunk) : 0.0;
+				e2[q] = c2 ? __ldg(er + 2 * ext_chunk) : 0.0;
+			}
+#pragma unroll
+			for (int q = 0; q < 4; ++q) {
+				part[0] += select_f64(v[q], e0[q]);
+				part[1] += select_f64(v[q], e1[q]);
+				part[2] += select_f64(v[q], e2[q]);
+			}
+		}
+		__syncwarp();
+#pragma unroll
+		for (int q = 0; q < 3; ++q) {
+			acc[q] = direct ? acc[q] + part[q] : acc[q] - part[q];
+		}
+	}
+	trig[lane] = acc[0];
+	if (c1) {
+		trig[lane + 32] = acc[1];
+	}
+	if (c2) {
+		trig[lane + 64] = acc[2];
+	}
+}
+
 // Solve of one row by this warp: fills the bordered matrix [[G, .], [b^T, .]] from the trig sums,
 // blocked LDL^T (8 x 8 blocks, trailing updates as DMMA), whose border row ends up as D^-1 L^-1 b,
 // then L^T x = z. Returns false (warp-uniform) when a pivot is not safely positive.
@@ -315,7 +433,9 @@ template<int NT8>
 __device__ bool WarpSolveRow(unsigned const *gtab, double const *trig, double const *bvec, double *A,
 		double *xout, int K, int lane) {
 	constexpr int Kp = 8 * NT8;
-	constexpr int LD = LdltLd(Kp);
+	auto Row = [](int i) {
+		return (i * (i + 1)) / 2; // packed lower triangle, see WarpLdltSolve<NT8, true>
+	};
 	for (int e = lane; e < Kp * (Kp + 1) / 2; e += 32) {
 		unsigned const g = gtab[e];
 		double a1 = trig[g & 0xffu];
@@ -326,13 +446,13 @@ __device__ bool WarpSolveRow(unsigned const *gtab, double const *trig, double co
 		if (g & kGramPad) {
 			v = (g & kGramPadDiag) ? 1.0 : 0.0;
 		}
-		A[(g >> 26) * LD + ((g >> 20) & 63u)] = v;
+		A[Row(static_cast<int>(g >> 26)) + ((g >> 20) & 63u)] = v;
 	}
 	for (int j = lane; j < Kp; j += 32) {
-		A[Kp * LD + j] = bvec[j];
+		A[Row(Kp) + j] = bvec[j];
 	}
 	__syncwarp();
-	return WarpLdltSolve<NT8>(A, K, xout, lane);
+	return WarpLdltSolve<NT8, true>(A, K, xout, lane);
 }
 
 template<int NT8>
@@ -390,25 +510,13 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 	for (size_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 		size_t const row0 = tile * RB;
 		__syncthreads();
-		// ---- P0: working mask + masked trigonometric sums t = mask x ext (column 0 = valid count) --
-		for (int col0 = 0; col0 < ext_ld; col0 += 32) {
-			double acc[MT][4][2];
-#pragma unroll
-			for (int mt = 0; mt < MT; ++mt) {
-#pragma unroll
-				for (int nt = 0; nt < 4; ++nt) {
-					acc[mt][nt][0] = 0.0;
-					acc[mt][nt][1] = 0.0;
-				}
-			}
-			if (col0 == 0) {
-				MaskedContract<4, false, true>(acc, p, row0, wmask, p.ext_p, kSinExtChunkLd, pp, warp, lane);
-			} else {
-				MaskedContract<4, false, false>(acc, p, row0, wmask, p.ext_p + (col0 / 32) * ext_chunk,
-						kSinExtChunkLd, pp, warp, lane);
-			}
-			ReducePartials<4>(acc, s, s.trig, ext_ld, col0, warp, lane, tid);
+		// ---- P0: working mask + masked column sums of the extended table (column 0 = valid count):
+		// "all channels minus the flagged ones", one warp per spectrum ----------------------------------
+		for (int r = warp; r < RB; r += NWARP) {
+			ComplementTrigSums(p, row0 + r, row0 + r < p.num_spectra, wmask + static_cast<size_t>(r) * n,
+					reinterpret_cast<int *>(s.gw) + warp * kSinSumStep, s.trig + r * ext_ld, lane);
 		}
+		__syncthreads(); // wmask (global) and the sums are visible to the whole CTA
 		if (tid < RB) {
 			int const cnt = static_cast<int>(s.trig[tid * ext_ld]);
 			int st = kActive;
@@ -437,15 +545,15 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 
 		// ---- clip iterations -------------------------------------------------------------------------
 		for (int iter = 1; iter <= p.num_fitting_max; ++iter) {
-			// (a) solve, one warp per row
+			// (a) solve, one warp per row (every warp: the packed workspaces fit sixteen at a time)
 			bool any_active = false;
-			for (int r = warp; r < RB && warp < NGROUP; r += NGROUP) {
+			for (int r = warp; r < RB; r += NWARP) {
 				if (s.state[r] != kActive) {
 					continue;
 				}
 				any_active = true;
 				bool const ok = WarpSolveRow<NT8>(s.gtab, s.trig + r * ext_ld, s.bvec + r * Kp,
-						s.gw + warp * s.gw_stride, s.coef + r * LDC, K, lane);
+						s.gw + warp * LdltPackedDoubles(Kp), s.coef + r * LDC, K, lane);
 				if (!ok) {
 					if (lane == 0) {
 						s.state[r] = kFallback;

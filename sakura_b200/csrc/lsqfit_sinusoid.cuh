@@ -31,6 +31,9 @@ struct SinusoidFitParams {
 	// [ext_ld / 32][n][kSinExtChunkLd]: 1, then (sin, cos)(m theta_i) for m = 1..mmax, 32 columns
 	// per chunk (+1 padding column), the columns beyond `next` are zero
 	double const *ext_p;
+	// [ceil(n / kSinSumStep) + 1][ext_ld]: column sums of the extended table over blocks of kSinSumStep
+	// channels, last row = over all channels
+	double const *ext_sums;
 	// basis k is: kind[k] = 0 constant, 1 sin, 2 cos; wave[k] its wave number
 	int8_t kind[kSinMaxKp];
 	int16_t wave[kSinMaxKp];
@@ -55,6 +58,7 @@ struct SinusoidFitParams {
 	int32_t *fallback_count;
 };
 
+constexpr int kSinSumStep = 512; // channels per block of the extended table's precomputed column sums
 constexpr int kSinExtChunkLd = 33; // row stride of one 32-column chunk of the extended table
 
 size_t SinusoidSharedBytes(int Kp, int next);
