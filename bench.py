@@ -407,8 +407,9 @@ def side_configs(lib, torch, device, host=None, rows: int = 1 << 18, n: int = 81
         ctx, 21, nw.ctypes.data, rows, n, data.data_ptr(), n, mask.data_ptr(), n, 3.0, 3, 41,
         co.data_ptr(), None, res.data_ptr(), fm.data_ptr(), rms.data_ptr(), st.data_ptr(),
         ls.data_ptr(), stream.cuda_stream))
-    # FP64 tensor-core work of the kernel: trig sums n x 96, data moments n x 48, model n x 48 per fit
-    flop = 2.0 * n * (96 + 48 + 3 * 48)
+    # FP64 tensor-core work of the kernel: data moments n x 48, model n x 48 per fit (the masked trig sums
+    # of the Gram matrix no longer are a contraction: "all channels minus flagged", lsqfit_sinusoid.cu)
+    flop = 2.0 * n * (48 + 3 * 48)
     sm_mhz = measured_peaks().get("sm_max_mhz", 1965.0)
     peak_tf = 148 * 64 * 2 * sm_mhz * 1e6 / 1e12
     bps4 = n * 10 + 8 * 41 + 8

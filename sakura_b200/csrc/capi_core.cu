@@ -417,11 +417,12 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 		}
 		if (columns_ok) {
 			size_t tiles = (f.num_spectra + kSinRowsPerTile - 1) / kSinRowsPerTile;
-			size_t sgrid = static_cast<size_t>(info.num_sms);
+			size_t sgrid = static_cast<size_t>(info.num_sms) * kSinCtasPerSm;
 			if (sgrid > tiles) {
 				sgrid = tiles;
 			}
-			CUDA_TRY(c->d_table.Reserve(SinusoidTableDoubles(sp.n, sp.Kp) * sizeof(double)));
+			CUDA_TRY(c->d_table.Reserve(SinusoidTableDoubles(sp.n, sp.Kp) * sizeof(double)
+					+ SinusoidGramEntries(sp.Kp) * sizeof(unsigned)));
 			CUDA_TRY(c->d_useidx.Reserve(kMaxBases * sizeof(int16_t)));
 			CUDA_TRY(c->d_fallback.Reserve((f.num_spectra + 1) * sizeof(int32_t)));
 			CUDA_TRY(c->ws_mask.Reserve(sgrid * kSinRowsPerTile * n));
@@ -432,8 +433,8 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 			CUDA_TRY(cudaMemcpyAsync(c->d_useidx.ptr, f.use_idx, kMaxBases * sizeof(int16_t),
 					cudaMemcpyHostToDevice, stream));
 			cudaError_t e = LaunchGatherTable(c->d_basis.As<double>(), static_cast<int>(c->num_bases),
-					sp.n, sp.K, sp.Kp, c->d_useidx.As<int16_t>(), c->d_table.As<double>(), stream);
-			g_launch_count += 1;
+					sp.n, sp.K, sp.Kp, c->d_useidx.As<int16_t>(), c->d_table.As<double>(), sp, stream);
+			g_launch_count += 2;
 			if (e != cudaSuccess) {
 				SetError("LaunchGatherTable", e);
 				return sakura_Status_kUnknownError;
@@ -442,6 +443,8 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 			CUDA_TRY(cudaMemsetAsync(fb, 0, sizeof(int32_t), stream));
 			sp.ld_p = sp.Kp + 1;
 			sp.ld_a = SinusoidLdA(sp.Kp);
+			sp.gram_table = reinterpret_cast<unsigned const *>(c->d_table.As<double>()
+					+ SinusoidTableDoubles(sp.n, sp.Kp));
 			sp.table_p = c->d_table.As<double>();
 			sp.table_a = sp.table_p + n * sp.ld_p;
 			sp.ext_p = c->d_ext.As<double>();

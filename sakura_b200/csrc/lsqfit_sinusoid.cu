@@ -28,6 +28,8 @@
 #include "async_copy.cuh"
 
 #include <float.h>
+#include <stdio.h>
+#include <stdlib.h>
 
 namespace sakura_b200 {
 
@@ -35,7 +37,7 @@ namespace {
 
 constexpr int RB = kSinRowsPerTile;
 constexpr int NWARP = kSinThreads / 32;
-constexpr int NGROUP = 8; // warp groups that split the channels; also the solve workspaces
+constexpr int NGROUP = 4; // warp groups (pairs) that split the channels
 constexpr int MT = 4 * NGROUP / NWARP; // 8-row groups of the tile handled by one warp
 static_assert(MT == 1 || MT == 2 || MT == 4, "warps of a group split the four 8-row groups");
 constexpr unsigned kFull = 0xffffffffu;
@@ -86,8 +88,7 @@ __host__ __device__ constexpr int TileDoubles(int Kp) {
 	return 16 * (LdA(Kp) > kSinExtChunkLd ? LdA(Kp) : kSinExtChunkLd);
 }
 __host__ __device__ inline int GwStride(int Kp) {
-	// bordered matrices of the solve, packed lower triangles: one per warp = two per channel group
-	int const a = (NWARP / NGROUP) * LdltPackedDoubles(Kp);
+	int const a = LdltPackedDoubles(Kp); // bordered matrix of a solve, packed lower triangle
 	int const b = RB * (Kp > 32 ? Kp : 32); // per-group partial sums of the contractions
 	int const c = 2 * TileDoubles(Kp); // two stages of table tiles per warp pair
 	int const ab = a > b ? a : b;
@@ -108,7 +109,6 @@ struct Smem {
 	float *hi; // [RB]
 	int *state; // [RB]
 	int *cnt; // [RB] valid channels (statistics count of the latest fit)
-	unsigned *gtab; // [Kp*(Kp+1)/2]
 	uint64_t *bars; // [NGROUP][4] mbarriers of the table-tile rings
 	int gw_stride;
 };
@@ -135,7 +135,6 @@ __device__ __forceinline__ Smem Carve(unsigned char *base, int Kp, int ext_ld) {
 	s.hi = s.lo + RB;
 	s.state = reinterpret_cast<int *>(s.hi + RB);
 	s.cnt = s.state + RB;
-	s.gtab = reinterpret_cast<unsigned *>(s.cnt + RB);
 	return s;
 }
 
@@ -437,7 +436,7 @@ __device__ bool WarpSolveRow(unsigned const *gtab, double const *trig, double co
 		return (i * (i + 1)) / 2; // packed lower triangle, see WarpLdltSolve<NT8, true>
 	};
 	for (int e = lane; e < Kp * (Kp + 1) / 2; e += 32) {
-		unsigned const g = gtab[e];
+		unsigned const g = __ldg(gtab + e);
 		double a1 = trig[g & 0xffu];
 		double a2 = trig[(g >> 8) & 0xffu];
 		a1 = (g & kGramNeg1) ? -a1 : a1;
@@ -456,7 +455,7 @@ __device__ bool WarpSolveRow(unsigned const *gtab, double const *trig, double co
 }
 
 template<int NT8>
-__global__ void __launch_bounds__(kSinThreads, 1)
+__global__ void __launch_bounds__(kSinThreads, kSinCtasPerSm)
 SinusoidFitKernel(SinusoidFitParams const p) {
 	constexpr int Kp = 8 * NT8;
 	constexpr int LDC = CoefLd(Kp);
@@ -482,16 +481,6 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 		}
 		return;
 	}
-	for (int e = tid; e < GramEntries(Kp); e += kSinThreads) {
-		int i = static_cast<int>((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-		while ((i + 1) * (i + 2) / 2 <= e) {
-			++i;
-		}
-		while (i * (i + 1) / 2 > e) {
-			--i;
-		}
-		s.gtab[e] = GramPack(p, i, e - i * (i + 1) / 2, p.next);
-	}
 	// table-tile ring of this warp's pair (group); its stages live in the group's workspace
 	int const group = warp / (4 / MT);
 	if (tid < NGROUP) {
@@ -506,6 +495,8 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 	pp.it = 0u;
 	pp.producer = (warp % (4 / MT)) == 0;
 	size_t const ext_chunk = static_cast<size_t>(n) * kSinExtChunkLd;
+	int const nsolve = (NGROUP * s.gw_stride / LdltPackedDoubles(Kp) < NWARP) ?
+			NGROUP * s.gw_stride / LdltPackedDoubles(Kp) : NWARP;
 
 	for (size_t tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
 		size_t const row0 = tile * RB;
@@ -545,14 +536,14 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 
 		// ---- clip iterations -------------------------------------------------------------------------
 		for (int iter = 1; iter <= p.num_fitting_max; ++iter) {
-			// (a) solve, one warp per row (every warp: the packed workspaces fit sixteen at a time)
+			// (a) solve, one warp per row, as many warps as packed workspaces fit into the groups' buffers
 			bool any_active = false;
-			for (int r = warp; r < RB; r += NWARP) {
+			for (int r = warp; r < RB && warp < nsolve; r += nsolve) {
 				if (s.state[r] != kActive) {
 					continue;
 				}
 				any_active = true;
-				bool const ok = WarpSolveRow<NT8>(s.gtab, s.trig + r * ext_ld, s.bvec + r * Kp,
+				bool const ok = WarpSolveRow<NT8>(p.gram_table, s.trig + r * ext_ld, s.bvec + r * Kp,
 						s.gw + warp * LdltPackedDoubles(Kp), s.coef + r * LDC, K, lane);
 				if (!ok) {
 					if (lane == 0) {
@@ -575,14 +566,29 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 				int const mt0 = MT * (warp % (4 / MT));
 				bool act[MT];
 				float const *yrow[MT];
+				// Where the residual / model of this pass go: the tile's staging rows, except in the last
+				// iteration -- no clip follows it, a row that is active now WILL be published -- where they
+				// are written straight to the caller's arrays (no copy afterwards, and nothing at all when
+				// the caller does not want them).
+				bool const last_iter = (iter == p.num_fitting_max);
+				float *res_row[MT];
+				float *best_row[MT];
 #pragma unroll
 				for (int mt = 0; mt < MT; ++mt) {
 					cnt[mt] = 0;
 					sum[mt] = 0.0;
 					sq[mt] = 0.0;
-					act[mt] = (s.state[8 * (mt0 + mt) + r8] == kActive);
-					size_t const row = act[mt] ? row0 + 8 * (mt0 + mt) + r8 : row0;
+					int const r = 8 * (mt0 + mt) + r8;
+					act[mt] = (s.state[r] == kActive);
+					size_t const row = act[mt] ? row0 + r : row0;
 					yrow[mt] = p.data + row * p.data_stride;
+					if (last_iter) {
+						res_row[mt] = p.residual ? p.residual + row * p.data_stride : nullptr;
+						best_row[mt] = p.best_fit ? p.best_fit + row * p.data_stride : nullptr;
+					} else {
+						res_row[mt] = wres + static_cast<size_t>(r) * n;
+						best_row[mt] = wbest ? wbest + static_cast<size_t>(r) * n : nullptr;
+					}
 				}
 				// B fragment: lane (n = r8, k = c4) of the table tile staged in shared memory (16 channels
 				// x ld_a). Column n of half h is channel 4 (n / 2) + 2 (n & 1) + h, so that this lane's C
@@ -644,7 +650,6 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 #pragma unroll
 					for (int mt = 0; mt < MT; ++mt) {
 						if (act[mt]) {
-							int const r = 8 * (mt0 + mt) + r8;
 							float4 md, rd;
 							md.x = static_cast<float>(c[mt][0][0]);
 							md.y = static_cast<float>(c[mt][1][0]);
@@ -654,9 +659,11 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 							rd.y = __fsub_rn(yv[mt].y, md.y);
 							rd.z = __fsub_rn(yv[mt].z, md.z);
 							rd.w = __fsub_rn(yv[mt].w, md.w);
-							*reinterpret_cast<float4 *>(wres + static_cast<size_t>(r) * n + ch) = rd;
-							if (wbest != nullptr) {
-								*reinterpret_cast<float4 *>(wbest + static_cast<size_t>(r) * n + ch) = md;
+							if (res_row[mt] != nullptr) {
+								*reinterpret_cast<float4 *>(res_row[mt] + ch) = rd;
+							}
+							if (best_row[mt] != nullptr) {
+								*reinterpret_cast<float4 *>(best_row[mt] + ch) = md;
 							}
 							float const rv[4] = { rd.x, rd.y, rd.z, rd.w };
 #pragma unroll
@@ -872,11 +879,12 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 				}
 				continue;
 			}
-			if (p.residual != nullptr) {
+			// (a row that was still active in the last iteration wrote both in place)
+			if (p.residual != nullptr && st == kConverged) {
 				WarpCopy(reinterpret_cast<float4 *>(p.residual + row * p.data_stride),
 						reinterpret_cast<float4 const *>(wres + static_cast<size_t>(r) * n), n / 4, lane);
 			}
-			if (p.best_fit != nullptr) {
+			if (p.best_fit != nullptr && st == kConverged) {
 				WarpCopy(reinterpret_cast<float4 *>(p.best_fit + row * p.data_stride),
 						reinterpret_cast<float4 const *>(wbest + static_cast<size_t>(r) * n), n / 4, lane);
 			}
@@ -919,6 +927,22 @@ __global__ void GatherTableKernel(double const *ctx_table, int nb_ctx, int n, in
 	}
 }
 
+// Gram index table of a call (see GramPack): entry e = i (i + 1) / 2 + j for bases i >= j
+__global__ void GramTableKernel(SinusoidFitParams const p, unsigned *out) {
+	int const e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= GramEntries(p.Kp)) {
+		return;
+	}
+	int i = static_cast<int>((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+	while ((i + 1) * (i + 2) / 2 <= e) {
+		++i;
+	}
+	while (i * (i + 1) / 2 > e) {
+		--i;
+	}
+	out[e] = GramPack(p, i, e - i * (i + 1) / 2, p.next);
+}
+
 } // namespace
 
 int SinusoidExtLd(int next) {
@@ -937,13 +961,22 @@ size_t SinusoidSharedBytes(int Kp, int next) {
 	size_t doubles = static_cast<size_t>(RB) * CoefLd(Kp) + static_cast<size_t>(RB) * Kp
 			+ static_cast<size_t>(RB) * SinusoidExtLd(next) + static_cast<size_t>(NGROUP) * GwStride(Kp)
 			+ static_cast<size_t>(NGROUP) * RB * 3 + RB + static_cast<size_t>(NGROUP) * 4;
-	return doubles * sizeof(double) + RB * (2 * sizeof(float) + 2 * sizeof(int))
-			+ GramEntries(Kp) * sizeof(unsigned) + 32;
+	return doubles * sizeof(double) + RB * (2 * sizeof(float) + 2 * sizeof(int)) + 32;
+}
+
+size_t SinusoidGramEntries(int Kp) {
+	return static_cast<size_t>(GramEntries(Kp));
 }
 
 cudaError_t LaunchGatherTable(double const *ctx_table, int nb_ctx, int n, int K, int Kp,
-		int16_t const *use_idx_dev, double *tables, cudaStream_t stream) {
+		int16_t const *use_idx_dev, double *tables, SinusoidFitParams const &p, cudaStream_t stream) {
 	GatherTableKernel<<<256, 256, 0, stream>>>(ctx_table, nb_ctx, n, K, Kp, use_idx_dev, tables);
+	cudaError_t const e = cudaGetLastError();
+	if (e != cudaSuccess) {
+		return e;
+	}
+	GramTableKernel<<<(GramEntries(Kp) + 255) / 256, 256, 0, stream>>>(p,
+			reinterpret_cast<unsigned *>(tables + SinusoidTableDoubles(n, Kp)));
 	return cudaGetLastError();
 }
 
@@ -954,6 +987,17 @@ static cudaError_t LaunchNT(SinusoidFitParams const &p, int grid, cudaStream_t s
 			cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
 	if (err != cudaSuccess) {
 		return err;
+	}
+	// two CTAs per SM need (almost) all of the SM's shared memory: ask for the largest carve-out
+	err = cudaFuncSetAttribute(SinusoidFitKernel<NT8>, cudaFuncAttributePreferredSharedMemoryCarveout,
+			static_cast<int>(cudaSharedmemCarveoutMaxShared));
+	if (err != cudaSuccess) {
+		return err;
+	}
+	if (getenv("SAKURA_B200_DEBUG_OCCUPANCY") != nullptr) {
+		int blocks = 0;
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, SinusoidFitKernel<NT8>, kSinThreads, smem);
+		fprintf(stderr, "sakura_b200: SinusoidFitKernel<%d> smem %zu B, resident CTAs per SM %d\n", NT8, smem, blocks);
 	}
 	SinusoidFitKernel<NT8><<<grid, kSinThreads, smem, stream>>>(p);
 	return cudaGetLastError();

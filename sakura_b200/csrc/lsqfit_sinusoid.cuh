@@ -10,7 +10,8 @@ namespace sakura_b200 {
 
 constexpr int kSinRowsPerTile = 32; // spectra fitted together by one CTA (4 DMMA row tiles)
 constexpr int kSinMaxKp = 48; // fitted bases, padded to a multiple of 8
-constexpr int kSinThreads = 512;
+constexpr int kSinThreads = 256; // two CTAs per SM: the scalar phases of one overlap the tensor-core phases of the other
+constexpr int kSinCtasPerSm = 2;
 
 struct SinusoidFitParams {
 	size_t num_spectra;
@@ -54,6 +55,9 @@ struct SinusoidFitParams {
 	float *ws_residual; // [gridDim.x][32][n]
 	float *ws_best_fit; // [gridDim.x][32][n] (when best_fit != NULL)
 	uint8_t *ws_mask; // [gridDim.x][32][n] working copy of the mask
+	// which two trig sums (and signs) make up each Gram matrix entry: SinusoidGramEntries(Kp) words,
+	// filled by LaunchGatherTable into the buffer behind the two tables
+	unsigned const *gram_table;
 	int32_t *fallback_rows; // rows whose normal equations are (nearly) singular
 	int32_t *fallback_count;
 };
@@ -66,10 +70,13 @@ int SinusoidExtLd(int next);
 int SinusoidLdA(int Kp);
 /** doubles of the two per-call tables together (table_p first, table_a at n * (Kp + 1)). */
 size_t SinusoidTableDoubles(int n, int Kp);
+/** 32-bit words of the Gram index table that follows the two tables in the same buffer. */
+size_t SinusoidGramEntries(int Kp);
 
-/** Gathers the selected columns of the context table into table_p and table_a. */
+/** Gathers the selected columns of the context table into table_p and table_a and builds the Gram index
+ *  table of `p` (kind / wave / K / cos_only / next must be set) behind them. */
 cudaError_t LaunchGatherTable(double const *ctx_table, int nb_ctx, int n, int K, int Kp,
-		int16_t const *use_idx_dev, double *tables, cudaStream_t stream);
+		int16_t const *use_idx_dev, double *tables, SinusoidFitParams const &p, cudaStream_t stream);
 
 cudaError_t LaunchSinusoidFit(SinusoidFitParams const &p, int grid, cudaStream_t stream);
 
