@@ -18,6 +18,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REF_SO = os.path.join(HERE, "_ref", "libsakura_ref.so")
+REF_NOFMA_SO = os.path.join(HERE, "_ref", "libsakura_ref_nofma.so")  # same sources, no fused multiply-adds
 PORT_SO = os.path.join(HERE, "libsakura_oracle.so")
 
 STAT_DTYPE = np.dtype([("count", np.uint64), ("sum", np.float64), ("square_sum", np.float64),
@@ -62,7 +63,7 @@ class Oracle:
         if kind is None:
             kind = "reference" if os.path.exists(REF_SO) else "port"
         self.kind = kind
-        path = REF_SO if kind == "reference" else PORT_SO
+        path = {"reference": REF_SO, "reference_nofma": REF_NOFMA_SO}.get(kind, PORT_SO)
         if not os.path.exists(path):
             raise OSError(f"oracle library {path} is missing; run `make -C oracle`")
         self.path = path

@@ -9,7 +9,7 @@ import pytest
 from sakura_b200 import synth
 from sakura_b200.capi import (LSQFIT_NOT_ENOUGH_DATA, LSQFIT_OK, LSQFIT_TYPE_CHEBYSHEV, STATUS_NG,
                               STATUS_OK, aligned_copy, aligned_empty)
-from parity import compare_fit
+from parity import compare_fit, forced_kernel
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
@@ -54,11 +54,19 @@ def test_orders_fast_path(lib, oracle, order):
     synth.add_edge_case_rows(data, mask, order + 1)
     g, o, kernel = run_both(lib, oracle, order, data, mask, 3.0, 4, want_best_fit=True)
     assert kernel == "poly_warp"
-    # cond(G) grows ~30x per order in the monomial basis (1.5e7 at order 5, ~1e10 at order 7):
-    # the O(eps) differences in G (power sums / downdates vs the reference's sums) move the
-    # model by cond*eps on rows with flagged gaps, so the band is widened for orders 6 and 7
-    compare_fit(g, o, data, 3.0, poly_rescale_n=2048, resid_atol={6: 2e-4, 7: 5e-3}.get(order, 0.0),
-                coeff_rtol={6: 1e-4, 7: 1e-3}.get(order, 1e-5))
+    # cond(G) grows ~30x per order in the monomial basis (1.5e7 at order 5, 4e8 at 6, ~1e10 at 7): O(eps)
+    # differences in the normal equations move the model by cond*eps, above all across flagged gaps.
+    # Measured on these rows (profiles/r02/ref_vs_ref_orders.json, gpu_vs_ref_orders.txt), residual /
+    # coefficients:
+    #   order 6: two builds of the REFERENCE ITSELF (FMA / no FMA) 1.9e-6 / 1.8e-8, GPU vs reference
+    #            3.8e-6 / 1.3e-7 (inside the 1e-5 coefficient gate);
+    #   order 7: reference vs reference 1.2e-4 / 1.7e-6; this library's general kernel -- the reference's
+    #            own table and arithmetic, sums grouped differently -- 7.4e-4; the moment form 1.3e-3 /
+    #            1.8e-5 (2.4e-5 on valid channels).
+    # At order 7 nothing short of the reference's exact summation order reproduces it to 1e-5; the bands
+    # below are 2.5 x the measured deviation. DESIGN.md section 4.
+    compare_fit(g, o, data, 3.0, poly_rescale_n=2048, resid_atol={6: 1e-5, 7: 3.3e-3}.get(order, 0.0),
+                coeff_rtol={7: 4.5e-5}.get(order, 1e-5))
 
 
 @pytest.mark.parametrize("n", [16, 64, 100, 333, 1000, 2048, 4096, 6000, 8192, 10000])
