@@ -3,6 +3,7 @@
 #include "capi_internal.cuh"
 
 #include <thread>
+#include <time.h>
 
 using namespace sakura_b200;
 using namespace sakura_b200::capi;
@@ -72,8 +73,24 @@ size_t PackedLimitBytes() {
 // kernels may overlap freely; every other kernel uses scratch of the context and is ordered after
 // the previous chunk's kernel by an event (the uploads still run ahead).
 // ---------------------------------------------------------------------------------------------
+// Optional timeline of a pipelined call (SAKURA_B200_PIPELINE_TRACE=1): device timestamps of every
+// chunk's upload, kernel and download and the host times of their submission, printed to stderr.
+struct ChunkTrace {
+	cudaEvent_t up0, up1, k1, d0, d1;
+	double host_submit_ms, host_finish_ms;
+};
+
+double HostMs() {
+	timespec ts;
+	clock_gettime(CLOCK_MONOTONIC, &ts);
+	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, size_t chunk_rows,
 		bool fast) {
+	static bool const trace_on = getenv("SAKURA_B200_PIPELINE_TRACE") != nullptr;
+	std::vector<ChunkTrace> trace;
+	double const host_t0 = HostMs();
 	size_t const n = f.num_data;
 	size_t const R = f.num_spectra;
 	size_t const dstride = RoundUp(n, 32);
@@ -81,13 +98,30 @@ sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, s
 	size_t const nb = f.npiece + 1;
 	bool const spline = (f.type == kFitCubicSpline);
 	int const published = AllPublished(f.type);
-	size_t const num_chunks = (R + chunk_rows - 1) / chunk_rows;
+	std::vector<size_t> start; // chunk boundaries (a ramp of shorter chunks at both ends was measured: no gain)
+	for (size_t r = 0; r < R; r += chunk_rows) {
+		start.push_back(r);
+	}
+	start.push_back(R);
+	size_t const num_chunks = start.size() - 1;
 	sakura_Status st = sakura_Status_kOK;
+	if (trace_on) {
+		trace.resize(num_chunks);
+		for (auto &t : trace) {
+			cudaEventCreate(&t.up0);
+			cudaEventCreate(&t.up1);
+			cudaEventCreate(&t.k1);
+			cudaEventCreate(&t.d0);
+			cudaEventCreate(&t.d1);
+			t.host_submit_ms = t.host_finish_ms = 0.0;
+		}
+	}
 	for (int s = 0; s < kPipelineSlots; ++s) {
 		PipelineSlot &sl = c->slots[s];
 		if (sl.stream == nullptr) {
 			CUDA_TRY(cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking));
 			CUDA_TRY(cudaStreamCreateWithFlags(&sl.down, cudaStreamNonBlocking));
+			CUDA_TRY(cudaEventCreateWithFlags(&sl.kernel_done, cudaEventDisableTiming));
 			CUDA_TRY(cudaEventCreateWithFlags(&sl.flags_ready, cudaEventDisableTiming));
 			CUDA_TRY(cudaEventCreateWithFlags(&sl.down_done, cudaEventDisableTiming));
 		}
@@ -108,13 +142,27 @@ sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, s
 			CUDA_TRY(sl.boundary.Reserve(chunk_rows * nb * sizeof(unsigned long long)));
 		}
 		CUDA_TRY(sl.handover.Reserve((chunk_rows + 1) * sizeof(int32_t)));
-		sl.h_flags.resize(chunk_rows);
+		if (sl.h_flags_cap < chunk_rows) {
+			if (sl.h_flags != nullptr) {
+				cudaFreeHost(sl.h_flags);
+				sl.h_flags = nullptr;
+				sl.h_flags_cap = 0;
+			}
+			CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_flags), chunk_rows * sizeof(int32_t),
+					cudaHostAllocDefault));
+			sl.h_flags_cap = chunk_rows;
+		}
 		sl.rows = 0;
 	}
 	auto finish = [&](PipelineSlot &sl) -> sakura_Status {
 		// the kernel of this slot's chunk is done and its per-row flags are on the host
 		CUDA_TRY(cudaEventSynchronize(sl.flags_ready));
 		size_t const r0 = sl.row0, rows = sl.rows;
+		ChunkTrace *tr = trace_on ? &trace[sl.chunk] : nullptr;
+		if (tr != nullptr) {
+			tr->host_finish_ms = HostMs() - host_t0;
+			cudaEventRecord(tr->d0, sl.down);
+		}
 		float *d_rms = sl.small.As<float>();
 		bool all_published = true;
 		for (size_t r = 0; r < rows; ++r) {
@@ -180,6 +228,9 @@ sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, s
 				}
 			}
 		}
+		if (tr != nullptr) {
+			cudaEventRecord(tr->d1, sl.down);
+		}
 		CUDA_TRY(cudaEventRecord(sl.down_done, sl.down));
 		sl.rows = 0;
 		return sakura_Status_kOK;
@@ -193,23 +244,31 @@ sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, s
 				return st;
 			}
 		}
-		size_t const r0 = ci * chunk_rows;
-		size_t const rows = (r0 + chunk_rows <= R) ? chunk_rows : (R - r0);
+		size_t const r0 = start[ci];
+		size_t const rows = start[ci + 1] - r0;
 		sl.row0 = r0;
 		sl.rows = rows;
+		sl.chunk = ci;
 		float *d_rms = sl.small.As<float>();
 		int32_t *d_status = reinterpret_cast<int32_t *>(d_rms + chunk_rows);
 		int32_t *d_lsq = d_status + chunk_rows;
 		int32_t *d_flags = d_lsq + chunk_rows;
+		if (trace_on) {
+			trace[ci].host_submit_ms = HostMs() - host_t0;
+			cudaEventRecord(trace[ci].up0, sl.stream);
+		}
 		CUDA_TRY(CopyRows(sl.data.ptr, dstride * sizeof(float), h.data + r0 * hds,
 				hds * sizeof(float), n * sizeof(float), rows, cudaMemcpyHostToDevice, sl.stream));
 		CUDA_TRY(CopyRows(sl.mask.ptr, dstride, h.mask + r0 * hms, hms, n, rows,
 				cudaMemcpyHostToDevice, sl.stream));
+		if (trace_on) {
+			cudaEventRecord(trace[ci].up1, sl.stream);
+		}
 		// the kernel overwrites this slot's result buffers: wait for their previous download
 		CUDA_TRY(cudaStreamWaitEvent(sl.stream, sl.down_done, 0));
 		if (!fast && previous != nullptr) {
 			// scratch of the context is shared by the chunks: kernels one after the other
-			CUDA_TRY(cudaStreamWaitEvent(sl.stream, previous->flags_ready, 0));
+			CUDA_TRY(cudaStreamWaitEvent(sl.stream, previous->kernel_done, 0));
 		}
 		CUDA_TRY(cudaMemsetAsync(d_flags, 0, rows * sizeof(int32_t), sl.stream));
 		FitCall fc = f;
@@ -232,14 +291,18 @@ sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, s
 		if (st != sakura_Status_kOK) {
 			return st;
 		}
+		if (trace_on) {
+			cudaEventRecord(trace[ci].k1, sl.stream);
+		}
+		CUDA_TRY(cudaEventRecord(sl.kernel_done, sl.stream));
+		CUDA_TRY(cudaStreamWaitEvent(sl.down, sl.kernel_done, 0));
+		CUDA_TRY(cudaMemcpyAsync(sl.h_flags, d_flags, rows * sizeof(int32_t), cudaMemcpyDeviceToHost,
+				sl.down));
 		CUDA_TRY(cudaMemcpyAsync(h.status + r0, d_status, rows * sizeof(int32_t),
-				cudaMemcpyDeviceToHost, sl.stream));
+				cudaMemcpyDeviceToHost, sl.down));
 		CUDA_TRY(cudaMemcpyAsync(h.lsq + r0, d_lsq, rows * sizeof(int32_t), cudaMemcpyDeviceToHost,
-				sl.stream));
-		CUDA_TRY(cudaMemcpyAsync(sl.h_flags.data(), d_flags, rows * sizeof(int32_t),
-				cudaMemcpyDeviceToHost, sl.stream));
-		CUDA_TRY(cudaEventRecord(sl.flags_ready, sl.stream));
-		CUDA_TRY(cudaStreamWaitEvent(sl.down, sl.flags_ready, 0));
+				sl.down));
+		CUDA_TRY(cudaEventRecord(sl.flags_ready, sl.down));
 		previous = &sl;
 	}
 	for (size_t k = 0; k < static_cast<size_t>(kPipelineSlots); ++k) {
@@ -254,6 +317,28 @@ sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, s
 	for (int s = 0; s < kPipelineSlots; ++s) {
 		CUDA_TRY(cudaStreamSynchronize(c->slots[s].stream));
 		CUDA_TRY(cudaStreamSynchronize(c->slots[s].down));
+	}
+	if (trace_on) {
+		fprintf(stderr, "sakura_b200 pipeline trace: %zu chunks of %zu rows, host total %.3f ms\n"
+				"chunk  submit  up0     up1     k1      finish  d0      d1   (ms; device times relative to up0 of chunk 0)\n",
+				num_chunks, chunk_rows, HostMs() - host_t0);
+		for (size_t ci = 0; ci < num_chunks; ++ci) {
+			float t[5] = { 0, 0, 0, 0, 0 };
+			cudaEventElapsedTime(&t[0], trace[0].up0, trace[ci].up0);
+			cudaEventElapsedTime(&t[1], trace[0].up0, trace[ci].up1);
+			cudaEventElapsedTime(&t[2], trace[0].up0, trace[ci].k1);
+			cudaEventElapsedTime(&t[3], trace[0].up0, trace[ci].d0);
+			cudaEventElapsedTime(&t[4], trace[0].up0, trace[ci].d1);
+			fprintf(stderr, "%5zu %7.3f %7.3f %7.3f %7.3f %7.3f %7.3f %7.3f\n", ci, trace[ci].host_submit_ms, t[0],
+					t[1], t[2], trace[ci].host_finish_ms, t[3], t[4]);
+		}
+		for (auto &t : trace) {
+			cudaEventDestroy(t.up0);
+			cudaEventDestroy(t.up1);
+			cudaEventDestroy(t.k1);
+			cudaEventDestroy(t.d0);
+			cudaEventDestroy(t.d1);
+		}
 	}
 	return sakura_Status_kOK;
 }

@@ -106,14 +106,20 @@ constexpr int kPipelineSlots = 4;
 
 /** One stage of the host-buffer pipeline: a stream and the device buffers of one chunk. */
 struct PipelineSlot {
-	cudaStream_t stream = nullptr; // upload + kernel + per-row status download
-	cudaStream_t down = nullptr; // bulk result download, so that it never blocks the next upload
-	cudaEvent_t flags_ready = nullptr; // kernel done and per-row flags on the host
+	// One direction per stream: a stream that has carried device->host copies gets its later
+	// host->device copies queued on the same copy engine (measured: uploads then wait for the bulk
+	// downloads of other slots), so uploads + kernels live on `stream`, every download on `down`.
+	cudaStream_t stream = nullptr; // upload + kernel
+	cudaStream_t down = nullptr; // per-row status / flags download, then the bulk result download
+	cudaEvent_t kernel_done = nullptr; // the chunk's kernel(s) have finished
+	cudaEvent_t flags_ready = nullptr; // ... and its per-row flags are on the host
 	cudaEvent_t down_done = nullptr; // result buffers of this slot may be overwritten
 	DeviceBuffer data, mask, coeff, best_fit, residual, final_mask, small, handover, boundary;
-	std::vector<int32_t> h_flags;
+	int32_t *h_flags = nullptr; // page-locked (a pageable target would make the copy block the host)
+	size_t h_flags_cap = 0;
 	size_t row0 = 0;
 	size_t rows = 0; // non-zero while a chunk is in flight in this slot
+	size_t chunk = 0; // its index in the call
 	void Release() {
 		data.Release();
 		mask.Release();
@@ -135,6 +141,15 @@ struct PipelineSlot {
 		if (flags_ready != nullptr) {
 			cudaEventDestroy(flags_ready);
 			flags_ready = nullptr;
+		}
+		if (kernel_done != nullptr) {
+			cudaEventDestroy(kernel_done);
+			kernel_done = nullptr;
+		}
+		if (h_flags != nullptr) {
+			cudaFreeHost(h_flags);
+			h_flags = nullptr;
+			h_flags_cap = 0;
 		}
 		if (down_done != nullptr) {
 			cudaEventDestroy(down_done);

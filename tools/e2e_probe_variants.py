@@ -44,3 +44,21 @@ def two():
     with torch.cuda.stream(s1): big.copy_(hu, non_blocking=True)
     with torch.cuda.stream(s2): hd.copy_(big2, non_blocking=True)
 dt = timeit(two); print(f"two single copies: {dt*1e3:.1f} ms, {R*n*5/dt/1e9:.1f} GB/s per direction")
+# does a running fit kernel slow the copy engines down? the same copy pattern with the fit kernel looping on
+# device-resident rows in another stream
+import threading
+rows2 = 24576
+d2, m2 = data[:rows2].contiguous(), mask[:rows2].contiguous()
+from sakura_b200.device_api import DeviceFits
+fits = DeviceFits(lib)
+ks = torch.cuda.Stream()
+out2 = fits.polynomial(ctx, 5, d2, m2, 3.0, 5, stream=ks)
+stop = False
+def spin():
+    while not stop:
+        for _ in range(8):
+            fits.polynomial(ctx, 5, d2, m2, 3.0, 5, out=out2, stream=ks)
+        ks.synchronize()
+t = threading.Thread(target=spin); t.start()
+dt = timeit(pattern); print(f"copy pattern with the fit kernel running all the time: {dt*1e3:.1f} ms, {R*n*5/dt/1e9:.1f} GB/s per direction")
+stop = True; t.join()
