@@ -206,7 +206,13 @@ sakura_Status sakura_SubtractSinusoidFloat(struct sakura_LSQFitContextFloat cons
  * sakura-aligned and the strides multiples that keep every row aligned.
  * Device variant: device pointers, 16-byte aligned rows, asynchronous on
  * `cuda_stream` (cudaStream_t; 0 = default stream); in-place final_mask==mask is
- * allowed, residual/best_fit must not alias data.
+ * allowed. residual (or best_fit, not both) may be the data array itself for the
+ * polynomial call where its row-resident kernels apply (num_data % 4 == 0, <= 8192,
+ * order <= 7): every row is read completely before it is written (the reference
+ * documents in-place use, sakura.h:1755-1766); any other overlap with data is
+ * kInvalidArgument. The context carries device scratch (hand-over lists, staging for
+ * the general kernel): successive device calls on ONE context must be issued on the
+ * same stream, or be separated by a synchronisation of the earlier one.
  */
 sakura_Status sakura_LSQFitPolynomialFloatBatch(
 		struct sakura_LSQFitContextFloat const *context, uint16_t order, size_t num_spectra,

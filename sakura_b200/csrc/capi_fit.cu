@@ -951,9 +951,31 @@ sakura_Status PolynomialBatchDevice(struct sakura_LSQFitContextFloat const *cont
 	if (st != sakura_Status_kOK) {
 		return st;
 	}
-	CHECK_ARGS(static_cast<void const *>(d_best_fit) != static_cast<void const *>(d_data)
-			&& static_cast<void const *>(d_residual) != static_cast<void const *>(d_data));
 	Context *c = const_cast<Context *>(context);
+	{
+		// residual / best_fit in place of data (the reference documents it, sakura.h:1755-1766): the
+		// row-resident polynomial kernels read a row completely before they write any of it, so exact
+		// aliasing of ONE of the two outputs is accepted where those kernels take the batch; the general
+		// kernel re-reads data, and a partial overlap is never meaningful.
+		size_t const span = (num_spectra == 0) ? 0 :
+				((num_spectra - 1) * data_stride + num_data) * sizeof(float);
+		auto overlaps = [&](void const *q) {
+			if (q == nullptr || span == 0) {
+				return false;
+			}
+			uintptr_t const a = reinterpret_cast<uintptr_t>(d_data), b = reinterpret_cast<uintptr_t>(q);
+			return a < b + span && b < a + span;
+		};
+		bool const res_alias = overlaps(d_residual), best_alias = overlaps(d_best_fit);
+		if (res_alias || best_alias) {
+			bool const exact = (!res_alias || static_cast<void const *>(d_residual) == static_cast<void const *>(d_data))
+					&& (!best_alias || static_cast<void const *>(d_best_fit) == static_cast<void const *>(d_data));
+			bool const row_resident = (c->type == kFitPolynomial || (c->type == kFitChebyshev && num_coeff <= 6))
+					&& cal == nullptr && PolyFastSupported(num_data, num_coeff, data_stride, mask_stride, d_data,
+							d_mask, d_best_fit, d_residual, d_final_mask);
+			CHECK_ARGS(exact && !(res_alias && best_alias) && row_resident);
+		}
+	}
 	FitCall f;
 	memset(&f, 0, sizeof(f));
 	f.type = c->type;

@@ -220,8 +220,12 @@ __device__ __forceinline__ double warp_max_upper(double a) {
 	return static_cast<double>(__uint_as_float(__reduce_max_sync(0xffffffffu, bits)));
 }
 
-/** 1/sqrt(v) to ~1e-13 relative for v in [1e-30, 1e30] (float rsqrt estimate + two Newton steps);
- *  sqrt(v) = v * rsqrt_fast(v) */
+/** 1/sqrt(v) for v in [1e-30, 1e30]; sqrt(v) = v * rsqrt_fast(v). FP64 hardware estimate
+ *  (rsqrt.approx.ftz.f64: only the upper 32 bits of v are used, relative error e0 < 2^-20) and two
+ *  Newton steps, each mapping an error e to 1.5 e^2: < 2^-39 after the first, at the FP64 rounding level
+ *  (~2^-52) after the second. The threshold intervals' safety factors (1 -/+ 3 * 2^-40) need the result
+ *  to better than 2^-41: that holds for any estimate better than 2^-11, i.e. with a margin of 2^9 on the
+ *  hardware's accuracy (tools/rcp_check.cu on B200, [1e-30, 1e30]: estimate 2^-20.1, result 2.2e-16). */
 __device__ __forceinline__ double rsqrt_fast(double v) {
 	// FP64 hardware estimate (relative error ~2^-20; no float round trip: a conversion costs as much
 	// as the estimate itself)

@@ -124,3 +124,49 @@ def test_statistics_device_arrays(lib, dev, oracle):
         assert np.array_equal(got[f], o[f]), f
     for f in ("sum", "square_sum"):
         assert np.all(np.abs(got[f] - o[f]) <= 1e-6 * np.abs(o[f]) + 1e-12), f
+
+
+@pytest.mark.parametrize("n,nfit,kernel", [(4096, 5, "poly_warp"), (8192, 4, "poly_screen"), (1024, 3, "poly_fast"),
+                                           (4096, 1, "poly_fast")])
+def test_residual_in_place_of_data(lib, dev, n, nfit, kernel):
+    """residual == data (the reference documents in-place use, sakura.h:1755-1766): the row-resident
+    kernels read a row completely before writing it; results equal the out-of-place call bit for bit.
+    Any other overlap, or a shape the general kernel fits, is rejected."""
+    import torch
+    from sakura_b200.capi import STATUS_INVALID_ARGUMENT
+    data, mask = synth.make_spectra(300, n, seed=n + nfit)
+    synth.add_edge_case_rows(data, mask, 6)
+    d, m = to_cuda(data, mask)
+    st, ctx = lib.create_polynomial_context(5, n)
+    ref = dev.polynomial(ctx, 5, d, m, 3.0, nfit)
+    assert ref["call_status"] == STATUS_OK and lib.last_kernel_name() == kernel
+    torch.cuda.synchronize()
+    work = d.clone()
+    out = dev.polynomial(ctx, 5, work, m, 3.0, nfit, out={"residual": work})
+    assert out["call_status"] == STATUS_OK and lib.last_kernel_name() == kernel
+    torch.cuda.synchronize()
+    good = ref["status"] == 0
+    for k in ("status", "lsqfit_status", "final_mask", "rms", "coeff"):
+        assert torch.equal(out[k][good] if k not in ("status", "lsqfit_status") else out[k],
+                           ref[k][good] if k not in ("status", "lsqfit_status") else ref[k]), k
+    assert torch.equal(work[good].view(torch.int32), ref["residual"][good].view(torch.int32))
+    assert torch.equal(work[~good].view(torch.int32), d[~good].view(torch.int32))   # failing rows: data untouched
+    # best_fit in place as well, but not both
+    work = d.clone()
+    out = dev.polynomial(ctx, 5, work, m, 3.0, nfit, want_best_fit=True, out={"best_fit": work})
+    assert out["call_status"] == STATUS_OK
+    torch.cuda.synchronize()
+    assert torch.equal((d[good] - work[good]).view(torch.int32), ref["residual"][good].view(torch.int32))
+    work = d.clone()
+    assert dev.polynomial(ctx, 5, work, m, 3.0, nfit, want_best_fit=True,
+                          out={"best_fit": work, "residual": work})["call_status"] == STATUS_INVALID_ARGUMENT
+    # a partial overlap (residual one row further down the same buffer)
+    big = torch.empty((301, n), dtype=torch.float32, device="cuda")
+    big[:300] = d
+    assert dev.polynomial(ctx, 5, big[:300], m, 3.0, nfit, out={"residual": big[1:301]})["call_status"] == STATUS_INVALID_ARGUMENT
+    lib.destroy_context(ctx)
+    # order 9 goes through the general kernel, which re-reads data: in place is refused
+    st, ctx9 = lib.create_polynomial_context(9, n)
+    work = d.clone()
+    assert dev.polynomial(ctx9, 9, work, m, 3.0, 2, out={"residual": work})["call_status"] == STATUS_INVALID_ARGUMENT
+    lib.destroy_context(ctx9)
