@@ -677,19 +677,24 @@ def run_ours(args) -> None:
             dt = float(t.item())
         # copy-only ceiling of the box for the same step: the same bytes up and down on the same pinned
         # buffers with no kernel, every rank at once (what the host feed allows at this GPU count)
-        d_up = torch.empty(er * n * 5, dtype=torch.uint8, device=device)
-        d_dn = torch.empty(er * n * 5, dtype=torch.uint8, device=device)
-        flat_in = [h_data.view(-1).view(torch.uint8), h_mask.view(-1).view(torch.uint8)]
-        flat_out = [h_resid.view(-1).view(torch.uint8), h_fmask.view(-1).view(torch.uint8)]
-        s_up, s_dn = torch.cuda.Stream(device), torch.cuda.Stream(device)
+        # (the pipeline's own pattern: 96 MiB chunks through four slots, one stream per direction and slot)
+        crow = 24576
+        slots = [dict(data=torch.empty(crow, n, dtype=torch.float32, device=device),
+                      mask=torch.empty(crow, n, dtype=torch.bool, device=device),
+                      resid=torch.empty(crow, n, dtype=torch.float32, device=device),
+                      fmask=torch.empty(crow, n, dtype=torch.bool, device=device),
+                      up=torch.cuda.Stream(device), down=torch.cuda.Stream(device)) for _ in range(4)]
 
         def copy_only():
-            with torch.cuda.stream(s_up):
-                d_up[:er * n * 4].copy_(flat_in[0], non_blocking=True)
-                d_up[er * n * 4:].copy_(flat_in[1], non_blocking=True)
-            with torch.cuda.stream(s_dn):
-                flat_out[0].copy_(d_dn[:er * n * 4], non_blocking=True)
-                flat_out[1].copy_(d_dn[er * n * 4:], non_blocking=True)
+            for ci, r0 in enumerate(range(0, er, crow)):
+                sl = slots[ci % 4]
+                r1 = min(er, r0 + crow)
+                with torch.cuda.stream(sl["up"]):
+                    sl["data"][:r1 - r0].copy_(h_data[r0:r1], non_blocking=True)
+                    sl["mask"][:r1 - r0].copy_(h_mask[r0:r1], non_blocking=True)
+                with torch.cuda.stream(sl["down"]):
+                    h_resid[r0:r1].copy_(sl["resid"][:r1 - r0], non_blocking=True)
+                    h_fmask[r0:r1].copy_(sl["fmask"][:r1 - r0], non_blocking=True)
             torch.cuda.synchronize(device)
 
         copy_only()
@@ -702,7 +707,7 @@ def run_ours(args) -> None:
             t = torch.tensor([cdt], dtype=torch.float64, device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             cdt = float(t.item())
-        del d_up, d_dn
+        del slots
         e2e_step()  # the probe overwrote the result buffers: put the fit's results back
         torch.cuda.synchronize(device)
         e2e = {"value": world * er / dt, "unit": UNIT,

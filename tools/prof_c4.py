@@ -1,10 +1,10 @@
-"""ncu target: a few launches of the sinusoid (C4) kernel on 4736 rows (148 tiles)."""
+"""ncu target: a few launches of the sinusoid (C4) kernel on 9472 rows (296 tiles = 2 per SM)."""
 import sys
 sys.path.insert(0, ".")
 import numpy as np, torch
 from sakura_b200.capi import SakuraLib
 import bench
-lib = SakuraLib(); R, n = 4736, 8192
+lib = SakuraLib(); R, n = 9472, 8192  # 296 tiles: two resident CTAs per SM
 dev = torch.device("cuda", 0)
 data, mask = bench.generate_on_device(torch, R, n, seed=3, device=dev)
 res = torch.empty(R, n, dtype=torch.float32, device=dev); fm = torch.empty(R, n, dtype=torch.bool, device=dev)
