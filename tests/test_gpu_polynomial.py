@@ -303,10 +303,11 @@ def test_device_pointer_api_matches_host_api(lib, oracle):
     assert np.array_equal(d_coeff.cpu().numpy(), h["coeff"], equal_nan=True)
     assert np.array_equal(d_rms.cpu().numpy(), h["rms"], equal_nan=True)
     assert np.array_equal(d_st.cpu().numpy(), h["status"])
-    # aliasing data with an output is rejected on the device entry point
+    # residual in place of data is accepted on the row-resident kernels (tests/test_gpu_device_api.py::
+    # test_residual_in_place_of_data compares it with the out-of-place call); a partial overlap is not
     rc = lib.lib.sakura_LSQFitPolynomialFloatBatchDevice(
-        ctx, 5, R, n, d_data.data_ptr(), n, d_mask.data_ptr(), n, 3.0, 5, K, None, None, d_data.data_ptr(),
-        d_mask.data_ptr(), d_rms.data_ptr(), d_st.data_ptr(), d_ls.data_ptr(), None)
+        ctx, 5, R - 1, n, d_data.data_ptr(), n, d_mask.data_ptr(), n, 3.0, 5, K, None, None,
+        d_data.data_ptr() + 4 * n, d_mask.data_ptr(), d_rms.data_ptr(), d_st.data_ptr(), d_ls.data_ptr(), None)
     assert rc == 2
     lib.destroy_context(ctx)
 
