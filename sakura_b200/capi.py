@@ -64,6 +64,10 @@ def _ptr(a: Optional[np.ndarray]):
 
 
 def default_library_path() -> str:
+    # SAKURA_B200_LIB: another build of the same library (A/B timing of two builds in one session)
+    override = os.environ.get("SAKURA_B200_LIB")
+    if override:
+        return override
     return os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsakura_b200.so")
 
 

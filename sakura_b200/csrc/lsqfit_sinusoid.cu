@@ -88,7 +88,9 @@ __host__ __device__ constexpr int TileDoubles(int Kp) {
 	return 16 * (LdA(Kp) > kSinExtChunkLd ? LdA(Kp) : kSinExtChunkLd);
 }
 __host__ __device__ inline int GwStride(int Kp) {
-	int const a = LdltPackedDoubles(Kp); // bordered matrix of a solve, packed lower triangle
+	// bordered matrices of the solves (packed lower triangles) share the groups' buffers: room for six
+	// solving warps (eight would push the CTA over half an SM's shared memory at 48 bases)
+	int const a = (6 * LdltPackedDoubles(Kp) + NGROUP - 1) / NGROUP;
 	int const b = RB * (Kp > 32 ? Kp : 32); // per-group partial sums of the contractions
 	int const c = 2 * TileDoubles(Kp); // two stages of table tiles per warp pair
 	int const ab = a > b ? a : b;
@@ -338,6 +340,39 @@ __device__ __forceinline__ void ComplementTrigSums(SinusoidFitParams const &p, s
 		acc[1] = (live && c1) ? tot[32] : 0.0;
 		acc[2] = (live && c2) ? tot[64] : 0.0;
 	}
+	// the channels to visit are listed across the row (tagged: subtract a flagged one, add a valid one of a
+	// dense block) and their table rows gathered eight at a time per lane
+	int nlist = 0;
+	double const *ext_lane = p.ext_p + lane;
+	auto gather = [&](int total) {
+		int t = 0;
+		for (; t + 8 <= total; t += 8) {
+			double e0[8], e1[8], e2[8], sg[8];
+#pragma unroll
+			for (int q = 0; q < 8; ++q) {
+				unsigned const e = static_cast<unsigned>(list[t + q]);
+				double const *er = ext_lane + (e & 0x7fffffffu) * static_cast<unsigned>(kSinExtChunkLd);
+				sg[q] = (e & 0x80000000u) ? 1.0 : -1.0;
+				e0[q] = __ldg(er);
+				e1[q] = c1 ? __ldg(er + ext_chunk) : 0.0;
+				e2[q] = c2 ? __ldg(er + 2 * ext_chunk) : 0.0;
+			}
+#pragma unroll
+			for (int q = 0; q < 8; ++q) {
+				acc[0] = fma(sg[q], e0[q], acc[0]);
+				acc[1] = fma(sg[q], e1[q], acc[1]);
+				acc[2] = fma(sg[q], e2[q], acc[2]);
+			}
+		}
+		for (; t < total; ++t) {
+			unsigned const e = static_cast<unsigned>(list[t]);
+			double const *er = ext_lane + (e & 0x7fffffffu) * static_cast<unsigned>(kSinExtChunkLd);
+			double const sg = (e & 0x80000000u) ? 1.0 : -1.0;
+			acc[0] = fma(sg, __ldg(er), acc[0]);
+			acc[1] = fma(sg, c1 ? __ldg(er + ext_chunk) : 0.0, acc[1]);
+			acc[2] = fma(sg, c2 ? __ldg(er + 2 * ext_chunk) : 0.0, acc[2]);
+		}
+	};
 	uint8_t const *gm = p.mask + (live ? row : 0) * p.mask_stride;
 	uint4 m_next = make_uint4(0u, 0u, 0u, 0u);
 	if (live && 16 * lane < n) {
@@ -376,6 +411,7 @@ __device__ __forceinline__ void ComplementTrigSums(SinusoidFitParams const &p, s
 			acc[2] -= c2 ? blk[64] : 0.0;
 		}
 		unsigned bits = direct ? valid16 : flag16;
+		unsigned const tag = direct ? 0x80000000u : 0u; // the channel is ADDED (valid one of a dense block)
 		int const mine = __popc(bits);
 		int incl = mine;
 #pragma unroll
@@ -384,38 +420,22 @@ __device__ __forceinline__ void ComplementTrigSums(SinusoidFitParams const &p, s
 			incl += (lane >= o) ? v : 0;
 		}
 		int const total = __shfl_sync(kFull, incl, 31);
-		int at = incl - mine;
+		int at = nlist + incl - mine;
 		while (bits != 0u) {
-			list[at++] = base + __ffs(bits) - 1;
+			list[at++] = static_cast<int>(static_cast<unsigned>(base + __ffs(bits) - 1) | tag);
 			bits &= bits - 1u;
 		}
-		__syncwarp();
-		double part[3] = { 0.0, 0.0, 0.0 };
-		for (int t = 0; t < total; t += 4) {
-			bool v[4];
-			double e0[4], e1[4], e2[4];
-#pragma unroll
-			for (int q = 0; q < 4; ++q) {
-				v[q] = t + q < total;
-				int const ch = list[v[q] ? t + q : t];
-				double const *er = p.ext_p + static_cast<size_t>(ch) * kSinExtChunkLd + lane;
-				e0[q] = __ldg(er);
-				e1[q] = c1 ? __ldg(er + ext_chunk) : 0.0;
-				e2[q] = c2 ? __ldg(er + 2 * ext_chunk) : 0.0;
-			}
-#pragma unroll
-			for (int q = 0; q < 4; ++q) {
-				part[0] += select_f64(v[q], e0[q]);
-				part[1] += select_f64(v[q], e1[q]);
-				part[2] += select_f64(v[q], e2[q]);
-			}
-		}
-		__syncwarp();
-#pragma unroll
-		for (int q = 0; q < 3; ++q) {
-			acc[q] = direct ? acc[q] + part[q] : acc[q] - part[q];
+		nlist += total;
+		if (nlist > kSinSumStep / 2) { // the next block adds at most half a block
+			__syncwarp();
+			gather(nlist);
+			nlist = 0;
+			__syncwarp();
 		}
 	}
+	__syncwarp();
+	gather(nlist);
+	__syncwarp();
 	trig[lane] = acc[0];
 	if (c1) {
 		trig[lane + 32] = acc[1];
@@ -726,10 +746,60 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 				uint8_t *wm = wmask + static_cast<size_t>(r) * n;
 				float const *rr = wres + static_cast<size_t>(r) * n;
 				float const *yy = p.data + row * p.data_stride;
-				int *list = reinterpret_cast<int *>(s.gw) + warp * 256;
+				// clipped channels are listed across the whole row and subtracted from the sums afterwards,
+				// four table rows in flight per lane (listing per 256-channel step left most groups of four
+				// nearly empty and paid an L2 round trip per step)
+				constexpr int kClipListCap = 512;
+				int *list = reinterpret_cast<int *>(s.gw) + warp * kClipListCap;
+				int nlist = 0;
 				double dt[3] = { 0.0, 0.0, 0.0 };
 				double db[2] = { 0.0, 0.0 };
 				int num_clipped = 0;
+				auto downdate = [&](int total) {
+					for (int t = 0; t < total; t += 4) {
+						int ch[4];
+						bool v[4];
+						float y[4];
+						double e0[4], e1[4], e2[4], t0[4], t1[4];
+#pragma unroll
+						for (int q = 0; q < 4; ++q) {
+							v[q] = t + q < total;
+							ch[q] = list[v[q] ? t + q : t];
+						}
+#pragma unroll
+						for (int q = 0; q < 4; ++q) {
+							double const *er = p.ext_p + static_cast<size_t>(ch[q]) * kSinExtChunkLd + lane;
+							double const *tr = p.table_p + static_cast<size_t>(ch[q]) * (Kp + 1);
+							y[q] = yy[ch[q]];
+							e0[q] = er[0];
+							e1[q] = (32 < ext_ld) ? er[ext_chunk] : 0.0;
+							e2[q] = (64 < ext_ld) ? er[2 * ext_chunk] : 0.0;
+							t0[q] = (lane < Kp) ? tr[lane] : 0.0;
+							t1[q] = (Kp > 32 && lane + 32 < Kp) ? tr[lane + 32] : 0.0;
+						}
+						if (t + 4 <= total) {
+#pragma unroll
+							for (int q = 0; q < 4; ++q) {
+								double const yd = static_cast<double>(y[q]);
+								dt[0] += e0[q];
+								dt[1] += e1[q];
+								dt[2] += e2[q];
+								db[0] = fma(yd, t0[q], db[0]);
+								db[1] = fma(yd, t1[q], db[1]);
+							}
+						} else {
+#pragma unroll
+							for (int q = 0; q < 4; ++q) {
+								double const yd = select_f64(v[q], static_cast<double>(y[q]));
+								dt[0] += select_f64(v[q], e0[q]);
+								dt[1] += select_f64(v[q], e1[q]);
+								dt[2] += select_f64(v[q], e2[q]);
+								db[0] = fma(yd, t0[q], db[0]);
+								db[1] = fma(yd, t1[q], db[1]);
+							}
+						}
+					}
+				};
 				// the loads of the next step are issued before this step is examined
 				uint2 mv_next = make_uint2(0u, 0u);
 				float4 ra_next = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
@@ -783,47 +853,24 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 						incl += (lane >= o) ? v : 0;
 					}
 					int const total = __shfl_sync(kFull, incl, 31);
-					int at = incl - mine;
+					int at = nlist + incl - mine;
 					unsigned b = bits;
 					while (b != 0u) {
 						list[at++] = base + __ffs(b) - 1;
 						b &= b - 1u;
 					}
-					__syncwarp();
+					nlist += total;
 					num_clipped += total;
-					for (int t = 0; t < total; t += 4) {
-						int ch[4];
-						bool v[4];
-						float y[4];
-						double e0[4], e1[4], e2[4], t0[4], t1[4];
-#pragma unroll
-						for (int q = 0; q < 4; ++q) {
-							v[q] = t + q < total;
-							ch[q] = list[v[q] ? t + q : t];
-						}
-#pragma unroll
-						for (int q = 0; q < 4; ++q) {
-							double const *er = p.ext_p + static_cast<size_t>(ch[q]) * kSinExtChunkLd + lane;
-							double const *tr = p.table_p + static_cast<size_t>(ch[q]) * (Kp + 1);
-							y[q] = yy[ch[q]];
-							e0[q] = er[0];
-							e1[q] = (32 < ext_ld) ? er[ext_chunk] : 0.0;
-							e2[q] = (64 < ext_ld) ? er[2 * ext_chunk] : 0.0;
-							t0[q] = (lane < Kp) ? tr[lane] : 0.0;
-							t1[q] = (Kp > 32 && lane + 32 < Kp) ? tr[lane + 32] : 0.0;
-						}
-#pragma unroll
-						for (int q = 0; q < 4; ++q) {
-							double const yd = select_f64(v[q], static_cast<double>(y[q]));
-							dt[0] += select_f64(v[q], e0[q]);
-							dt[1] += select_f64(v[q], e1[q]);
-							dt[2] += select_f64(v[q], e2[q]);
-							db[0] = fma(yd, t0[q], db[0]);
-							db[1] = fma(yd, t1[q], db[1]);
-						}
+					if (nlist > kClipListCap - 256) { // the next step may add up to 256 entries
+						__syncwarp();
+						downdate(nlist);
+						nlist = 0;
+						__syncwarp();
 					}
-					__syncwarp();
 				}
+				__syncwarp();
+				downdate(nlist);
+				__syncwarp();
 				if (num_clipped != 0) {
 					double *trig = s.trig + r * ext_ld;
 					double *bv = s.bvec + r * Kp;
