@@ -40,6 +40,24 @@ __device__ __forceinline__ int warp_sum(int v) {
 	return v;
 }
 
+__device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a, double b) {
+	// (not volatile: a pure function of its operands, so that independent products can be interleaved)
+	asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+			: "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+/** Sum of `v` over the 32 lanes, delivered to every lane: two FP64 tensor-core products with a matrix
+ *  of ones (B[k][n] comes from lane k + 4 n, so the first product adds groups of four lanes, the second
+ *  the eight group sums) instead of five shuffle rounds. Fixed order: deterministic. */
+__device__ __forceinline__ double warp_total(double v) {
+	double c0 = 0.0, c1 = 0.0;
+	dmma8x8x4(c0, c1, 1.0, v);
+	double const h = c0 + c1;
+	double d0 = 0.0, d1 = 0.0;
+	dmma8x8x4(d0, d1, 1.0, h);
+	return d0;
+}
+
 /**
  * Deterministic block-wide sum of (count, s1, s2). `scratch` must hold
  * 3 * (blockDim.x/32) doubles. Every thread receives the totals.

@@ -70,24 +70,6 @@ __host__ __device__ constexpr size_t TableBytes() {
 	return 32 * 8 * sizeof(double); // DMMA B fragments: 8 doubles per lane
 }
 
-__device__ __forceinline__ void dmma8x8x4(double &c0, double &c1, double a, double b) {
-	// (not volatile: a pure function of its operands, so that independent products can be interleaved)
-	asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-			: "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
-
-/** Sum of `v` over the 32 lanes, delivered to every lane: two FP64 tensor-core products with a matrix
- *  of ones (B[k][n] comes from lane k + 4 n, so the first product adds groups of four lanes, the second
- *  the eight group sums) instead of five shuffle rounds. Fixed order: deterministic. */
-__device__ __forceinline__ double warp_total(double v) {
-	double c0 = 0.0, c1 = 0.0;
-	dmma8x8x4(c0, c1, 1.0, v);
-	double const h = c0 + c1;
-	double d0 = 0.0, d1 = 0.0;
-	dmma8x8x4(d0, d1, 1.0, h);
-	return d0;
-}
-
 __device__ __forceinline__ double warp_max_upper(double a) {
 	unsigned const bits = __float_as_uint(__double2float_ru(a));
 	return static_cast<double>(__uint_as_float(__reduce_max_sync(0xffffffffu, bits)));
@@ -292,7 +274,10 @@ __device__ __forceinline__ uint32_t MaskBits16(uint4 const m) {
 	return nib(m.x) | (nib(m.y) << 4) | (nib(m.z) << 8) | (nib(m.w) << 12);
 }
 
-template<int K, int NB>
+// CAL: position-switch calibration (and NaN/Inf flagging) applied in shared memory as soon
+// as the row has arrived: the fit then sees scaling * (data - reference) / reference, the calibrated
+// spectrum is never written to global memory.
+template<int K, int NB, bool CAL>
 __global__ void __launch_bounds__(32 * WarpsPerCta(NB), 1)
 PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__restrict__ seg_sums) {
 	constexpr int NS = 2 * K - 1;
@@ -376,11 +361,52 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 			for (int j = 0; j < NSEG; ++j) {
 				mb[j] = __ldg(gmask + lane + 32 * j);
 			}
+			uint32_t fin[NSEG]; // CAL: finite flags of the calibrated values of segment j
+			if (CAL) {
+				// the row has arrived: calibrate the lane's mask segments in place (16 channels each)
+				mbar_wait(mbar, phase);
+				phase ^= 1u;
+				float4 const *ref4 = reinterpret_cast<float4 const *>(p.cal.reference + row * p.cal.reference_stride);
+				float4 const *scl4 = (p.cal.scaling != nullptr) ?
+						reinterpret_cast<float4 const *>(p.cal.scaling + row * p.cal.scaling_stride) : nullptr;
+#pragma unroll
+				for (int j = 0; j < NSEG; ++j) {
+					int const g0 = 4 * (lane + 32 * j);
+					float4 r4[4], s4[4];
+#pragma unroll
+					for (int e = 0; e < 4; ++e) {
+						r4[e] = __ldg(ref4 + g0 + e);
+						s4[e] = (scl4 != nullptr) ? __ldg(scl4 + g0 + e) : make_float4(p.cal.const_scaling,
+								p.cal.const_scaling, p.cal.const_scaling, p.cal.const_scaling);
+					}
+					uint32_t f = 0u;
+#pragma unroll
+					for (int e = 0; e < 4; ++e) {
+						float4 y = sd4[g0 + e];
+						y.x = CalibrateOne(s4[e].x, y.x, r4[e].x);
+						y.y = CalibrateOne(s4[e].y, y.y, r4[e].y);
+						y.z = CalibrateOne(s4[e].z, y.z, r4[e].z);
+						y.w = CalibrateOne(s4[e].w, y.w, r4[e].w);
+						sd4[g0 + e] = y;
+						auto finite = [](float v) {
+							return (__float_as_uint(v) & 0x7f800000u) != 0x7f800000u;
+						};
+						f |= ((finite(y.x) ? 1u : 0u) | (finite(y.y) ? 2u : 0u) | (finite(y.z) ? 4u : 0u)
+								| (finite(y.w) ? 8u : 0u)) << (4 * e);
+					}
+					fin[j] = p.cal.flag_nonfinite ? f : 0xffffu; // sakura_SetFalseIfNanOrInfFloat merged into the mask
+				}
+				__syncwarp();
+			}
 			int c = 0;
 #pragma unroll
 			for (int w = 0; w < NPW; ++w) {
-				uint32_t const a = MaskBits16(mb[2 * w]);
-				uint32_t const b = MaskBits16(mb[2 * w + 1]);
+				uint32_t a = MaskBits16(mb[2 * w]);
+				uint32_t b = MaskBits16(mb[2 * w + 1]);
+				if (CAL) {
+					a &= fin[2 * w];
+					b &= fin[2 * w + 1];
+				}
 				reinterpret_cast<uint16_t *>(svalid)[lane + 32 * (2 * w)] = static_cast<uint16_t>(a);
 				reinterpret_cast<uint16_t *>(svalid)[lane + 32 * (2 * w + 1)] = static_cast<uint16_t>(b);
 				vseg[w] = a | (b << 16);
@@ -477,8 +503,10 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 			}
 		}
 		// ---- the row has arrived ------------------------------------------------------------------
-		mbar_wait(mbar, phase);
-		phase ^= 1u;
+		if (!CAL) {
+			mbar_wait(mbar, phase);
+			phase ^= 1u;
+		}
 		if (giveup) {
 			if (lane == 0) {
 				int const pos = atomicAdd(p.fallback_count, 1);
@@ -751,8 +779,25 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 			while (dirty != 0u) {
 				int const g = __ffs(dirty) - 1;
 				dirty &= dirty - 1u;
-				asm volatile("cp.async.ca.shared.global [%0], [%1], 16;"
-						:: "r"(smem_u32(sd4 + own4 + g)), "l"(grow4 + own4 + g) : "memory");
+				if (CAL) { // calibrated again from the three input rows (the same operations: the same bits)
+					float4 y = __ldg(grow4 + own4 + g);
+					float4 const r = __ldg(reinterpret_cast<float4 const *>(p.cal.reference
+							+ row * p.cal.reference_stride) + own4 + g);
+					float4 sc = make_float4(p.cal.const_scaling, p.cal.const_scaling, p.cal.const_scaling,
+							p.cal.const_scaling);
+					if (p.cal.scaling != nullptr) {
+						sc = __ldg(reinterpret_cast<float4 const *>(p.cal.scaling + row * p.cal.scaling_stride)
+								+ own4 + g);
+					}
+					y.x = CalibrateOne(sc.x, y.x, r.x);
+					y.y = CalibrateOne(sc.y, y.y, r.y);
+					y.z = CalibrateOne(sc.z, y.z, r.z);
+					y.w = CalibrateOne(sc.w, y.w, r.w);
+					sd4[own4 + g] = y;
+				} else {
+					asm volatile("cp.async.ca.shared.global [%0], [%1], 16;"
+							:: "r"(smem_u32(sd4 + own4 + g)), "l"(grow4 + own4 + g) : "memory");
+				}
 			}
 			asm volatile("cp.async.commit_group;" ::: "memory");
 		}
@@ -763,6 +808,18 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 						:: "l"(p.data + nrow * p.data_stride), "r"(static_cast<unsigned>(n) * 4u) : "memory");
 				asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
 						:: "l"(p.mask + nrow * p.mask_stride), "r"(static_cast<unsigned>(n)) : "memory");
+				if (CAL) {
+					if (p.cal.reference_stride != 0) {
+						asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+								:: "l"(p.cal.reference + nrow * p.cal.reference_stride),
+								"r"(static_cast<unsigned>(n) * 4u) : "memory");
+					}
+					if (p.cal.scaling != nullptr && p.cal.scaling_stride != 0) {
+						asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;"
+								:: "l"(p.cal.scaling + nrow * p.cal.scaling_stride),
+								"r"(static_cast<unsigned>(n) * 4u) : "memory");
+					}
+				}
 			}
 		}
 		// ---- final mask: 32 NB consecutive bytes per lane ---------------------------------------------
@@ -948,7 +1005,7 @@ cudaError_t GetSegmentTable(int n, double const **out) {
 	return cudaSuccess;
 }
 
-template<int K, int NB>
+template<int K, int NB, bool CAL>
 cudaError_t LaunchWarpKN(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
 	constexpr int W = WarpsPerCta(NB);
 	constexpr size_t smem = TableBytes() + W * SliceBytes(NB);
@@ -957,7 +1014,7 @@ cudaError_t LaunchWarpKN(PolyFitParams const &p, int num_sms, cudaStream_t strea
 	if (err != cudaSuccess) {
 		return err;
 	}
-	err = cudaFuncSetAttribute(PolyWarpFitKernel<K, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+	err = cudaFuncSetAttribute(PolyWarpFitKernel<K, NB, CAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
 			static_cast<int>(smem));
 	if (err != cudaSuccess) {
 		return err;
@@ -967,16 +1024,19 @@ cudaError_t LaunchWarpKN(PolyFitParams const &p, int num_sms, cudaStream_t strea
 	if (grid > need) {
 		grid = need;
 	}
-	PolyWarpFitKernel<K, NB><<<static_cast<unsigned>(grid), 32 * W, smem, stream>>>(p, GetPolyConst(p.n), seg);
+	PolyWarpFitKernel<K, NB, CAL><<<static_cast<unsigned>(grid), 32 * W, smem, stream>>>(p, GetPolyConst(p.n), seg);
 	return cudaGetLastError();
 }
 
 template<int K>
 cudaError_t LaunchWarpK(PolyFitParams const &p, int num_sms, cudaStream_t stream) {
-	if (p.n == 4096) {
-		return LaunchWarpKN<K, 4>(p, num_sms, stream);
+	if (p.cal.reference != nullptr) {
+		return p.n == 4096 ? LaunchWarpKN<K, 4, true>(p, num_sms, stream) : LaunchWarpKN<K, 2, true>(p, num_sms, stream);
 	}
-	return LaunchWarpKN<K, 2>(p, num_sms, stream);
+	if (p.n == 4096) {
+		return LaunchWarpKN<K, 4, false>(p, num_sms, stream);
+	}
+	return LaunchWarpKN<K, 2, false>(p, num_sms, stream);
 }
 
 } // namespace
@@ -988,8 +1048,12 @@ bool PolyWarpSupported(PolyFitParams const &p) {
 	if (p.K < 1 || p.K > kMaxPolyK || p.num_spectra > static_cast<size_t>(INT32_MAX)) {
 		return false;
 	}
-	if (p.cal.reference != nullptr) {
-		return false; // the fused calibration lives in the other two kernels
+	if (p.cal.reference != nullptr) { // calibrated in shared memory with 128-bit loads of the two other rows
+		auto a16c = [](void const *q) {return (reinterpret_cast<uintptr_t>(q) % 16) == 0;};
+		if (!a16c(p.cal.reference) || p.cal.reference_stride % 4 != 0 || !a16c(p.cal.scaling)
+				|| p.cal.scaling_stride % 4 != 0) {
+			return false;
+		}
 	}
 	// bulk copies of the data rows, 128-bit accesses to the mask rows
 	auto a16 = [](void const *q) {return (reinterpret_cast<uintptr_t>(q) % 16) == 0;};

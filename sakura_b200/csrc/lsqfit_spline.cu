@@ -27,6 +27,7 @@
 // (:1081-1096), thresholds, early exit, not-enough-data and which outputs a failing row leaves
 // untouched follow the general kernel (lsqfit_general.cu), which remains the restatement of the
 // reference's arithmetic order.
+#include <stdio.h>
 #include "lsqfit_spline.cuh"
 #include "device_common.cuh"
 
@@ -38,6 +39,17 @@ constexpr int NTHR = kSplineThreads;
 constexpr int NW = NTHR / 32;
 constexpr unsigned kFull = 0xffffffffu;
 constexpr double kPivotTol = 1e-9; // pivot / diagonal entry below which a row goes to the LU kernel
+
+// -DSPLINE_CLOCKS: CTA 0 prints the cycles its warp 0 spent per phase (development only)
+#ifdef SPLINE_CLOCKS
+#define CLK(k) do { long long const t_ = clock64(); clk[k] += t_ - tprev; tprev = t_; } while (0)
+#define CLK_ARGS , long long (&clk)[12], long long &tprev
+#define CLK_PASS , clk, tprev
+#else
+#define CLK(k) do { } while (0)
+#define CLK_ARGS
+#define CLK_PASS
+#endif
 
 // exact for 0 <= v < 2^31, without the (slow) conversion pipe
 __device__ __forceinline__ double int_to_double(int v) {
@@ -54,16 +66,20 @@ __device__ __forceinline__ double rcp_pos(double x) {
 	return r;
 }
 
+constexpr int kGpStride = 11; // 10 band contributions per basis row (odd: conflict-free lane reads)
+constexpr int kFpStride = 5;
+constexpr int kBandStride = 6;
+
 struct Smem {
 	double *M; // [npiece][4][4] local cubic of the four B-splines alive in every piece
 	double *H; // [npiece][8] local power sums (7 used)
 	double *T; // [npiece][4] local data moments
-	double *E; // [npiece][16] M_q Hank(h_q) M_q^T (lower triangle used); dead after the assembly:
-	double *loc; //   [npiece][4] local cubic of the fitted model (aliases E)
-	double *F; // [npiece][4] M_q t_q; dead after the assembly:
-	double *cvec; //  [32] solution (aliases F; npiece >= 8 or padded)
-	double *band; // [32][5] band rows G[k][k-d], d = 0..3, right-hand side; then the factors;
-	double *part; //  [3 * NW] block reduction scratch (aliases band)
+	double *Gp; // [K][11] piece contributions to band row k: slot kGpBase[d] + c is E_q[c + d][c], q = k - d - c;
+	double *loc; //   dead after the assembly: [npiece][4] local cubic of the fitted model (aliases Gp)
+	double *Fp; // [K][5] piece contributions to the right-hand side: slot r is F_q[r], q = k - r;
+	double *cvec; //  dead after the assembly: [32] solution (aliases Fp, K >= 7 or padded)
+	double *band; // [K][6] band rows G[k][k-d], d = 0..3, right-hand side; then the factors;
+	double *part; //  [3 * NW] block reduction scratch (aliases band, K >= 4)
 	float *y; // [n]
 	float *r; // [n]
 	int *bound; // [npiece + 1]
@@ -71,9 +87,21 @@ struct Smem {
 	unsigned *bits; // [ceil(n / 32)] working mask, one bit per channel
 };
 
+// (all sizes even: the arrays behind them stay 16-byte aligned)
+__host__ __device__ inline int GpDoubles(int npiece) {
+	return ((npiece + 3) * kGpStride + 1) & ~1;
+}
+__host__ __device__ inline int FpDoubles(int npiece) {
+	int const f = ((npiece + 3) * kFpStride + 1) & ~1;
+	return f > 32 ? f : 32;
+}
+__host__ __device__ inline int BandDoubles(int npiece) {
+	return (npiece + 3) * kBandStride > 3 * NW ? (npiece + 3) * kBandStride : 3 * NW;
+}
+
 __host__ __device__ inline size_t SmemDoubles(int npiece) {
-	int const f = 4 * npiece > 32 ? 4 * npiece : 32;
-	return static_cast<size_t>(npiece) * (16 + 8 + 4 + 16) + f + 32 * 5;
+	return static_cast<size_t>(npiece) * (16 + 8 + 4) + GpDoubles(npiece) + FpDoubles(npiece)
+			+ BandDoubles(npiece);
 }
 
 __host__ __device__ inline size_t SmemInts(int n, int npiece) {
@@ -89,15 +117,15 @@ __device__ __forceinline__ Smem Carve(unsigned char *base, int n, int npiece) {
 	d += npiece * 8;
 	s.T = d;
 	d += npiece * 4;
-	s.E = d;
+	s.Gp = d;
 	s.loc = d;
-	d += npiece * 16;
-	s.F = d;
+	d += GpDoubles(npiece);
+	s.Fp = d;
 	s.cvec = d;
-	d += 4 * npiece > 32 ? 4 * npiece : 32;
+	d += FpDoubles(npiece);
 	s.band = d;
 	s.part = d;
-	d += 32 * 5;
+	d += BandDoubles(npiece);
 	s.y = reinterpret_cast<float *>(d);
 	s.r = s.y + n;
 	s.bound = reinterpret_cast<int *>(s.r + n);
@@ -147,6 +175,60 @@ __device__ __forceinline__ void AddMoments(double (&h)[7], double (&t)[4], doubl
 	t[3] = fma(y, u3, t[3]);
 }
 
+// The same sums for four channels at once, flagged channels silenced by u = 0, y = 0 (they then add
+// nothing to any sum but h[0], which is counted from the mask bits instead): every accumulator takes
+// ONE dependent addition per call, the four channels' terms are combined in a tree first.
+__device__ __forceinline__ void AddMoments4(double (&h)[7], double (&t)[4], double d0, double inv,
+		float4 yf, unsigned m) {
+	double u[4], y[4], sq[4], cu[4];
+	float const ys[4] = { yf.x, yf.y, yf.z, yf.w };
+#pragma unroll
+	for (int j = 0; j < 4; ++j) {
+		bool const valid = (m >> j) & 1u;
+		double const uj = (d0 + static_cast<double>(j)) * inv;
+		u[j] = valid ? uj : 0.0;
+		y[j] = static_cast<double>(valid ? ys[j] : 0.0f);
+		sq[j] = u[j] * u[j];
+		cu[j] = sq[j] * u[j];
+	}
+	h[1] += (u[0] + u[1]) + (u[2] + u[3]);
+	h[2] += (sq[0] + sq[1]) + (sq[2] + sq[3]);
+	h[3] += (cu[0] + cu[1]) + (cu[2] + cu[3]);
+	h[4] += fma(sq[0], sq[0], sq[1] * sq[1]) + fma(sq[2], sq[2], sq[3] * sq[3]);
+	h[5] += fma(sq[0], cu[0], sq[1] * cu[1]) + fma(sq[2], cu[2], sq[3] * cu[3]);
+	h[6] += fma(cu[0], cu[0], cu[1] * cu[1]) + fma(cu[2], cu[2], cu[3] * cu[3]);
+	t[0] += (y[0] + y[1]) + (y[2] + y[3]);
+	t[1] += fma(y[0], u[0], y[1] * u[1]) + fma(y[2], u[2], y[3] * u[3]);
+	t[2] += fma(y[0], sq[0], y[1] * sq[1]) + fma(y[2], sq[2], y[3] * sq[3]);
+	t[3] += fma(y[0], cu[0], y[1] * cu[1]) + fma(y[2], cu[2], y[3] * cu[3]);
+}
+
+// Block-wide sums without a leading barrier (callers guarantee that the scratch is free): warp totals
+// on the tensor cores, the eight warp results added by one more warp total in every warp.
+__device__ __forceinline__ int BlockSumInt(int v, int *scratch, int lane, int warp) {
+	v = __reduce_add_sync(kFull, v);
+	if (lane == 0) {
+		scratch[warp] = v;
+	}
+	__syncthreads();
+	return __reduce_add_sync(kFull, lane < NW ? scratch[lane] : 0);
+}
+
+__device__ __forceinline__ void BlockSum3(int &cnt, double &s1, double &s2, double *scratch, int lane, int warp) {
+	cnt = __reduce_add_sync(kFull, cnt);
+	s1 = warp_total(s1);
+	s2 = warp_total(s2);
+	if (lane == 0) {
+		scratch[warp] = s1;
+		scratch[NW + warp] = s2;
+		reinterpret_cast<int *>(scratch + 2 * NW)[warp] = cnt;
+	}
+	__syncthreads();
+	cnt = __reduce_add_sync(kFull, lane < NW ? reinterpret_cast<int const *>(scratch + 2 * NW)[lane] : 0);
+	s1 = warp_total(lane < NW ? scratch[lane] : 0.0);
+	s2 = warp_total(lane < NW ? scratch[NW + lane] : 0.0);
+}
+
 // baseline.cc:808-844: boundary[idx] (1 <= idx < npiece) is the unmasked channel whose rank among
 // the unmasked channels equals ceil(N*idx/npiece). Every thread owns a run of mask words.
 __device__ void Boundaries(int n, int npiece, int num_valid, Smem const &s, int tid) {
@@ -171,7 +253,7 @@ __device__ void Boundaries(int n, int npiece, int num_valid, Smem const &s, int 
 		s.iscr[warp] = incl;
 	}
 	// rank targets once per row (64-bit divisions), then every thread only compares
-	int *tgt = reinterpret_cast<int *>(s.E);
+	int *tgt = reinterpret_cast<int *>(s.Gp);
 	if (tid >= 1 && tid < npiece) {
 		long long const N = num_valid;
 		tgt[tid] = static_cast<int>((N * tid + npiece - 1) / npiece);
@@ -262,34 +344,35 @@ __device__ void PieceBasis(int q, int npiece, Smem const &s, double inv) {
 	}
 }
 
-// Warp 0: band rows from the piece blocks, banded LDL^T bordered by the right-hand side, back
-// substitution, local cubic of the model per piece. Returns false (warp-uniform) when a pivot is not
-// safely positive. The serial loops run redundantly in all lanes on broadcast shared-memory reads;
-// lane k keeps what belongs to basis k.
-__device__ bool BandSolve(int npiece, int K, Smem const &s, int lane) {
+// Warp 0: band rows from the piece contributions, banded LDL^T bordered by the right-hand side, back
+// substitution. Returns false (warp-uniform) when a pivot is not safely positive. The serial loops run
+// redundantly in all lanes on broadcast shared-memory reads; lane k keeps what belongs to basis k.
+__device__ bool BandSolve(int npiece, int K, Smem const &s, int lane CLK_ARGS) {
 	double *band = s.band;
 	if (lane < K) {
 		int const k = lane;
-		int const q0 = max(0, k - 3);
-#pragma unroll
-		for (int d = 0; d < 4; ++d) {
-			double v = 0.0;
-			if (k - d >= 0) {
-				int const q1 = min(npiece - 1, k - d);
-				for (int q = q0; q <= q1; ++q) {
-					v += s.E[q * 16 + 4 * (k - q) + (k - d - q)];
-				}
-			}
-			band[5 * k + d] = v;
-		}
-		double v = 0.0;
-		int const q1 = min(npiece - 1, k);
-		for (int q = q0; q <= q1; ++q) {
-			v += s.F[4 * q + (k - q)];
-		}
-		band[5 * k + 4] = v;
+		double const *gp = s.Gp + k * kGpStride;
+		double const *fp = s.Fp + k * kFpStride;
+		// contribution (d, c) comes from piece q = k - d - c, slot r of the right-hand side from piece k - r
+		auto alive = [&](int r) {
+			return r <= k && k - r < npiece;
+		};
+		double const g0 = ((alive(0) ? gp[0] : 0.0) + (alive(1) ? gp[1] : 0.0))
+				+ ((alive(2) ? gp[2] : 0.0) + (alive(3) ? gp[3] : 0.0));
+		double const g1 = ((alive(1) ? gp[4] : 0.0) + (alive(2) ? gp[5] : 0.0)) + (alive(3) ? gp[6] : 0.0);
+		double const g2 = (alive(2) ? gp[7] : 0.0) + (alive(3) ? gp[8] : 0.0);
+		double const g3 = alive(3) ? gp[9] : 0.0;
+		double const bk = ((alive(0) ? fp[0] : 0.0) + (alive(1) ? fp[1] : 0.0))
+				+ ((alive(2) ? fp[2] : 0.0) + (alive(3) ? fp[3] : 0.0));
+		double *row = band + kBandStride * k;
+		row[0] = g0;
+		row[1] = g1;
+		row[2] = g2;
+		row[3] = g3;
+		row[4] = bk;
 	}
 	__syncwarp();
+	CLK(2);
 	// row i: w_d = G[i][i-d] - (earlier columns), l_d = w_d / D[i-d], D[i] = G[i][i] - sum w_d l_d,
 	// z[i] = b[i] - sum l_d z[i-d]
 	double p12 = 0.0, p13 = 0.0, p23 = 0.0; // L[i-1][i-2], L[i-1][i-3], L[i-2][i-3]
@@ -299,8 +382,9 @@ __device__ bool BandSolve(int npiece, int K, Smem const &s, int lane) {
 	bool ok = true;
 #pragma unroll 4
 	for (int i = 0; i < K; ++i) {
-		double const g0 = band[5 * i], g1 = band[5 * i + 1], g2 = band[5 * i + 2], g3 = band[5 * i + 3];
-		double const bi = band[5 * i + 4];
+		double const *row = band + kBandStride * i;
+		double const g0 = row[0], g1 = row[1], g2 = row[2], g3 = row[3];
+		double const bi = row[4];
 		double const w3 = g3;
 		double const w2 = fma(-w3, p23, g2);
 		double const w1 = fma(-w2, p12, fma(-w3, p13, g1));
@@ -327,6 +411,7 @@ __device__ bool BandSolve(int npiece, int K, Smem const &s, int lane) {
 		z2 = z1;
 		z1 = zi;
 	}
+	CLK(3);
 	if (!ok) {
 		return false;
 	}
@@ -336,16 +421,18 @@ __device__ bool BandSolve(int npiece, int K, Smem const &s, int lane) {
 	double const c3 = __shfl_down_sync(kFull, ml3, 3);
 	__syncwarp();
 	if (lane < K) {
-		band[5 * lane] = mzr;
-		band[5 * lane + 1] = (lane + 1 < K) ? c1 : 0.0;
-		band[5 * lane + 2] = (lane + 2 < K) ? c2 : 0.0;
-		band[5 * lane + 3] = (lane + 3 < K) ? c3 : 0.0;
+		double *row = band + kBandStride * lane;
+		row[0] = mzr;
+		row[1] = (lane + 1 < K) ? c1 : 0.0;
+		row[2] = (lane + 2 < K) ? c2 : 0.0;
+		row[3] = (lane + 3 < K) ? c3 : 0.0;
 	}
 	__syncwarp();
 	double x1 = 0.0, x2 = 0.0, x3 = 0.0, mine = 0.0;
 #pragma unroll 4
 	for (int i = K - 1; i >= 0; --i) {
-		double const xi = fma(-band[5 * i + 1], x1, fma(-band[5 * i + 2], x2, fma(-band[5 * i + 3], x3, band[5 * i])));
+		double const *row = band + kBandStride * i;
+		double const xi = fma(-row[1], x1, fma(-row[2], x2, fma(-row[3], x3, row[0])));
 		if (lane == i) {
 			mine = xi;
 		}
@@ -354,13 +441,7 @@ __device__ bool BandSolve(int npiece, int K, Smem const &s, int lane) {
 		x1 = xi;
 	}
 	s.cvec[lane] = mine;
-	__syncwarp();
-	for (int e = lane; e < 4 * npiece; e += 32) { // E is dead: loc may be written
-		int const q = e >> 2;
-		int const a = e & 3;
-		double const *m = s.M + q * 16 + a;
-		s.loc[e] = fma(s.cvec[q + 3], m[12], fma(s.cvec[q + 2], m[8], fma(s.cvec[q + 1], m[4], s.cvec[q] * m[0])));
-	}
+	CLK(4);
 	return true;
 }
 
@@ -376,30 +457,60 @@ SplineFitKernel(SplineFitParams const p) {
 	int const warp = tid >> 5;
 	double const max_x = static_cast<double>(n - 1);
 	double const inv = 1.0 / max_x;
+#ifdef SPLINE_CLOCKS
+	long long clk[12] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+	long long tprev = clock64();
+#endif
 
 	for (size_t row = blockIdx.x; row < p.num_spectra; row += gridDim.x) {
 		float const *data = p.data + row * p.data_stride;
 		uint8_t const *mask = p.mask + row * p.mask_stride;
 		__syncthreads(); // previous row's shared state fully consumed
+		CLK(11);
 		int cnt = 0;
-		for (int i0 = warp * 128; i0 < n; i0 += NTHR * 4) { // warp-uniform bounds: shuffles inside
-			int const i = i0 + 4 * lane;
-			unsigned v = 0u;
-			if (i < n) {
-				v = *reinterpret_cast<unsigned const *>(mask + i);
-				*reinterpret_cast<float4 *>(s.y + i) = *reinterpret_cast<float4 const *>(data + i);
+		for (int i0 = warp * 128; i0 < n; i0 += NTHR * 8) { // warp-uniform bounds: shuffles inside
+			// two 128-channel groups per step, their loads in flight together
+			unsigned v[2] = { 0u, 0u };
+			float4 yv[2];
+#pragma unroll
+			for (int g = 0; g < 2; ++g) {
+				int const i = i0 + g * NTHR * 4 + 4 * lane;
+				if (i < n) {
+					v[g] = *reinterpret_cast<unsigned const *>(mask + i);
+					yv[g] = *reinterpret_cast<float4 const *>(data + i);
+				}
 			}
-			v = __vcmpne4(v, 0u) & 0x01010101u;
-			v = ((v * 0x10204080u) >> 28) << (4 * (lane & 7)); // the four flags as a nibble
-			v |= __shfl_xor_sync(kFull, v, 1);
-			v |= __shfl_xor_sync(kFull, v, 2);
-			v |= __shfl_xor_sync(kFull, v, 4);
-			if ((lane & 7) == 0 && i < n) {
-				s.bits[i >> 5] = v;
-				cnt += __popc(v);
+#pragma unroll
+			for (int g = 0; g < 2; ++g) {
+				int const i = i0 + g * NTHR * 4 + 4 * lane;
+				if (i0 + g * NTHR * 4 >= n) {
+					break;
+				}
+				if (i < n) {
+					*reinterpret_cast<float4 *>(s.y + i) = yv[g];
+				}
+				unsigned w = __vcmpne4(v[g], 0u) & 0x01010101u;
+				w = ((w * 0x10204080u) >> 28) << (4 * (lane & 7)); // the four flags as a nibble
+				w |= __shfl_xor_sync(kFull, w, 1);
+				w |= __shfl_xor_sync(kFull, w, 2);
+				w |= __shfl_xor_sync(kFull, w, 4);
+				if ((lane & 7) == 0 && i < n) {
+					s.bits[i >> 5] = w;
+					cnt += __popc(w);
+				}
 			}
 		}
-		int const num_valid = block_sum_int(cnt, s.iscr);
+		if (row + gridDim.x < p.num_spectra) { // the next spectrum of this CTA: into L2 while this one is fitted
+			char const *nd = reinterpret_cast<char const *>(data + gridDim.x * p.data_stride);
+			char const *nm = reinterpret_cast<char const *>(mask + gridDim.x * p.mask_stride);
+			for (int b = tid * 128; b < n * 4; b += NTHR * 128) {
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(nd + b));
+			}
+			for (int b = tid * 128; b < n; b += NTHR * 128) {
+				asm volatile("prefetch.global.L2 [%0];" :: "l"(nm + b));
+			}
+		}
+		int const num_valid = BlockSumInt(cnt, s.iscr, lane, warp);
 		if (num_valid < npiece) { // baseline.cc:822-824 -> Status_kNG, lsqfit_status stays kNG
 			if (tid == 0) {
 				p.status[row] = kStatusNG;
@@ -440,41 +551,35 @@ SplineFitKernel(SplineFitParams const p) {
 			int const b1 = s.bound[q + 1];
 			double h[7] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
 			double t[4] = { 0.0, 0.0, 0.0, 0.0 };
-			auto one = [&](int i, float yf, bool valid) {
-				if (valid) {
-					AddMoments(h, t, int_to_double(i - b0) * inv, static_cast<double>(yf));
-				}
-			};
+			int nv = 0;
 			ForPiece(b0, b1, lane, [&](int i) {
-				float4 const y = *reinterpret_cast<float4 const *>(s.y + i);
 				unsigned const m = Nibble(s.bits, i);
-				one(i, y.x, (m & 1u) != 0u);
-				one(i + 1, y.y, (m & 2u) != 0u);
-				one(i + 2, y.z, (m & 4u) != 0u);
-				one(i + 3, y.w, (m & 8u) != 0u);
+				nv += __popc(m);
+				AddMoments4(h, t, int_to_double(i - b0), inv, *reinterpret_cast<float4 const *>(s.y + i), m);
 			}, [&](int i) {
-				one(i, s.y[i], Bit(s.bits, i));
+				if (Bit(s.bits, i)) {
+					AddMoments(h, t, int_to_double(i - b0) * inv, static_cast<double>(s.y[i]));
+				}
 			});
+			h[0] += static_cast<double>(nv);
+			// warp totals: every lane gets them, lane m < 7 keeps h[m], lane 8 + a keeps t[a]
+			double mine = 0.0;
 #pragma unroll
 			for (int m = 0; m < 7; ++m) {
-				h[m] = warp_sum(h[m]);
+				double const tot = warp_total(h[m]);
+				mine = (lane == m) ? tot : mine;
 			}
 #pragma unroll
 			for (int a = 0; a < 4; ++a) {
-				t[a] = warp_sum(t[a]);
+				double const tot = warp_total(t[a]);
+				mine = (lane == 8 + a) ? tot : mine;
 			}
-			if (lane == 0) {
-#pragma unroll
-				for (int m = 0; m < 7; ++m) {
-					s.H[q * 8 + m] = h[m];
-				}
-#pragma unroll
-				for (int a = 0; a < 4; ++a) {
-					s.T[q * 4 + a] = t[a];
-				}
+			if (lane < 12) { // H[q][0..7] and T[q][0..3] are contiguous per kind
+				(lane < 8 ? s.H + q * 8 + lane : s.T + q * 4 + (lane - 8))[0] = mine;
 			}
 		}
 		__syncthreads();
+		CLK(0); // load, boundaries, bases, moments
 
 		int num_unmasked = n; // baseline.cc:1152 (sic)
 		double rms_d = 0.0;
@@ -498,24 +603,40 @@ SplineFitKernel(SplineFitParams const p) {
 				for (int a = 0; a < 4; ++a) {
 					w[a] = fma(m3, h[a + 3], fma(m2, h[a + 2], fma(m1, h[a + 1], m0 * h[a])));
 				}
+				// E_q[r][c] (r >= c) belongs to band row q + r, offset d = r - c: slot kGpBase[d] + c
 #pragma unroll
-				for (int r = 0; r < 4; ++r) {
-					s.E[q * 16 + 4 * r + c] = fma(m[4 * r + 3], w[3], fma(m[4 * r + 2], w[2], fma(m[4 * r + 1], w[1], m[4 * r] * w[0])));
+				for (int d = 0; d < 4; ++d) {
+					int const r = c + d;
+					if (r < 4) {
+						int const base = d == 0 ? 0 : (d == 1 ? 4 : (d == 2 ? 7 : 9));
+						s.Gp[(q + r) * kGpStride + base + c] = fma(m[4 * r + 3], w[3],
+								fma(m[4 * r + 2], w[2], fma(m[4 * r + 1], w[1], m[4 * r] * w[0])));
+					}
 				}
-				s.F[tid] = fma(m3, t[3], fma(m2, t[2], fma(m1, t[1], m0 * t[0])));
+				s.Fp[(q + c) * kFpStride + c] = fma(m3, t[3], fma(m2, t[2], fma(m1, t[1], m0 * t[0])));
 			}
 			__syncthreads();
+			CLK(1);
 			if (warp == 0) {
-				bool const ok = BandSolve(npiece, K, s, lane);
+				bool const ok = BandSolve(npiece, K, s, lane CLK_PASS);
 				if (lane == 0) {
 					s.iscr[NW] = ok ? 1 : 0;
 				}
 			}
 			__syncthreads();
+			CLK(6);
 			if (s.iscr[NW] == 0) {
 				fallback = true;
 				break;
 			}
+			// ---- local cubic of the model in the pieces of this warp ------------------------------------
+			for (int e = lane; e < 4 * ((npiece - warp + NW - 1) / NW); e += 32) { // Gp is dead: loc may be written
+				int const q = warp + NW * (e >> 2);
+				int const a = e & 3;
+				double const *m = s.M + q * 16 + a;
+				s.loc[4 * q + a] = fma(s.cvec[q + 3], m[12], fma(s.cvec[q + 2], m[8], fma(s.cvec[q + 1], m[4], s.cvec[q] * m[0])));
+			}
+			__syncwarp();
 			// ---- model, residual, statistics: one warp per piece -------------------------------------
 			int c = 0;
 			double sum = 0.0, sq = 0.0;
@@ -523,31 +644,41 @@ SplineFitKernel(SplineFitParams const p) {
 				int const b0 = s.bound[q];
 				int const b1 = s.bound[q + 1];
 				double const l0 = s.loc[4 * q], l1 = s.loc[4 * q + 1], l2 = s.loc[4 * q + 2], l3 = s.loc[4 * q + 3];
-				auto one = [&](int i, float yf, bool valid) {
-					double const u = int_to_double(i - b0) * inv;
-					double const m = fma(fma(fma(l3, u, l2), u, l1), u, l0);
-					float const rr = __fsub_rn(yf, static_cast<float>(m));
-					// flagged channels contribute +0.0 (a select: NaN/Inf under the mask must not leak)
-					double const rd = static_cast<double>(__int_as_float(valid ? __float_as_int(rr) : 0));
-					c += valid ? 1 : 0;
-					sum += rd;
-					sq = fma(rd, rd, sq);
-					return rr;
+				auto resid = [&](double d, float yf) {
+					double const u = d * inv;
+					return __fsub_rn(yf, static_cast<float>(fma(fma(fma(l3, u, l2), u, l1), u, l0)));
 				};
 				ForPiece(b0, b1, lane, [&](int i) {
 					float4 const y = *reinterpret_cast<float4 const *>(s.y + i);
 					unsigned const m = Nibble(s.bits, i);
+					double const d0 = int_to_double(i - b0);
 					float4 rr;
-					rr.x = one(i, y.x, (m & 1u) != 0u);
-					rr.y = one(i + 1, y.y, (m & 2u) != 0u);
-					rr.z = one(i + 2, y.z, (m & 4u) != 0u);
-					rr.w = one(i + 3, y.w, (m & 8u) != 0u);
+					rr.x = resid(d0, y.x);
+					rr.y = resid(d0 + 1.0, y.y);
+					rr.z = resid(d0 + 2.0, y.z);
+					rr.w = resid(d0 + 3.0, y.w);
 					*reinterpret_cast<float4 *>(s.r + i) = rr;
+					// flagged channels contribute +0.0 (a select: NaN/Inf under the mask must not leak)
+					double const r0 = static_cast<double>((m & 1u) ? rr.x : 0.0f);
+					double const r1 = static_cast<double>((m & 2u) ? rr.y : 0.0f);
+					double const r2 = static_cast<double>((m & 4u) ? rr.z : 0.0f);
+					double const r3 = static_cast<double>((m & 8u) ? rr.w : 0.0f);
+					c += __popc(m);
+					sum += (r0 + r1) + (r2 + r3);
+					sq += fma(r0, r0, r1 * r1) + fma(r2, r2, r3 * r3);
 				}, [&](int i) {
-					s.r[i] = one(i, s.y[i], Bit(s.bits, i));
+					float const rr = resid(int_to_double(i - b0), s.y[i]);
+					s.r[i] = rr;
+					bool const valid = Bit(s.bits, i);
+					double const rd = static_cast<double>(valid ? rr : 0.0f);
+					c += valid ? 1 : 0;
+					sum += rd;
+					sq = fma(rd, rd, sq);
 				});
 			}
-			block_sum3(c, sum, sq, s.part); // band is dead: part may be written
+			CLK(7);
+			BlockSum3(c, sum, sq, s.part, lane, warp); // band is dead: part may be written
+			CLK(8);
 			ClipThresholds const th = make_thresholds(c, sum, sq, p.clip_threshold_sigma);
 			rms_d = th.rms;
 			if (iter == p.num_fitting_max) {
@@ -585,27 +716,25 @@ SplineFitKernel(SplineFitParams const p) {
 					}
 				});
 				if (__any_sync(kFull, mine)) {
+					double keep = 0.0;
 #pragma unroll
 					for (int m = 0; m < 7; ++m) {
-						h[m] = warp_sum(h[m]);
+						double const tot = warp_total(h[m]);
+						keep = (lane == m) ? tot : keep;
 					}
 #pragma unroll
 					for (int a = 0; a < 4; ++a) {
-						t[a] = warp_sum(t[a]);
+						double const tot = warp_total(t[a]);
+						keep = (lane == 8 + a) ? tot : keep;
 					}
-					if (lane == 0) {
-#pragma unroll
-						for (int m = 0; m < 7; ++m) {
-							s.H[q * 8 + m] -= h[m];
-						}
-#pragma unroll
-						for (int a = 0; a < 4; ++a) {
-							s.T[q * 4 + a] -= t[a];
-						}
+					if (lane < 12) {
+						(lane < 8 ? s.H + q * 8 + lane : s.T + q * 4 + (lane - 8))[0] -= keep;
 					}
 				}
 			}
-			int const num_clipped = block_sum_int(nclip, s.iscr);
+			CLK(9);
+			int const num_clipped = BlockSumInt(nclip, s.iscr, lane, warp);
+			CLK(10);
 			if (num_clipped == 0) { // baseline.cc:1211-1213
 				break;
 			}
@@ -678,6 +807,14 @@ SplineFitKernel(SplineFitParams const p) {
 			}
 		}
 	}
+#ifdef SPLINE_CLOCKS
+	CLK(11);
+	if (blockIdx.x == 0 && tid == 0) {
+		printf("spline clocks (CTA 0, warp 0): moments %lld | blocks %lld assemble %lld factor %lld backsub %lld - %lld "
+				"(unused) barrier %lld | model %lld sum3 %lld | clip %lld sumint %lld | outputs+load %lld\n", clk[0], clk[1], clk[2],
+				clk[3], clk[4], clk[5], clk[6], clk[7], clk[8], clk[9], clk[10], clk[11]);
+	}
+#endif
 }
 
 cudaError_t LaunchImpl(SplineFitParams const &p, int grid, cudaStream_t stream) {
