@@ -776,25 +776,38 @@ PolyWarpFitKernel(PolyFitParams const p, PolyConst const pc, double const *__res
 		if (p.residual != nullptr && !failed) {
 			uint32_t dirty = (NB == 4) ? sdirty[lane] : ((sdirty[lane >> 1] >> (16 * (lane & 1))) & 0xffffu);
 			float4 const *grow4 = reinterpret_cast<float4 const *>(grow);
-			while (dirty != 0u) {
-				int const g = __ffs(dirty) - 1;
-				dirty &= dirty - 1u;
-				if (CAL) { // calibrated again from the three input rows (the same operations: the same bits)
-					float4 y = __ldg(grow4 + own4 + g);
-					float4 const r = __ldg(reinterpret_cast<float4 const *>(p.cal.reference
-							+ row * p.cal.reference_stride) + own4 + g);
-					float4 sc = make_float4(p.cal.const_scaling, p.cal.const_scaling, p.cal.const_scaling,
-							p.cal.const_scaling);
-					if (p.cal.scaling != nullptr) {
-						sc = __ldg(reinterpret_cast<float4 const *>(p.cal.scaling + row * p.cal.scaling_stride)
-								+ own4 + g);
-					}
-					y.x = CalibrateOne(sc.x, y.x, r.x);
-					y.y = CalibrateOne(sc.y, y.y, r.y);
-					y.z = CalibrateOne(sc.z, y.z, r.z);
-					y.w = CalibrateOne(sc.w, y.w, r.w);
-					sd4[own4 + g] = y;
-				} else {
+			if (CAL) {
+				// calibrated again from the three input rows (the same operations: the same bits), two groups
+				// per step so that their six loads are in flight together
+				float4 const *ref4 = reinterpret_cast<float4 const *>(p.cal.reference + row * p.cal.reference_stride);
+				float4 const *scl4 = (p.cal.scaling != nullptr) ?
+						reinterpret_cast<float4 const *>(p.cal.scaling + row * p.cal.scaling_stride) : nullptr;
+				float4 const cs4 = make_float4(p.cal.const_scaling, p.cal.const_scaling, p.cal.const_scaling,
+						p.cal.const_scaling);
+				while (dirty != 0u) {
+					int const ga = __ffs(dirty) - 1;
+					dirty &= dirty - 1u;
+					int const gb = (dirty != 0u) ? __ffs(dirty) - 1 : ga;
+					dirty &= dirty - 1u; // (0 & anything = 0)
+					float4 ya = __ldg(grow4 + own4 + ga), yb = __ldg(grow4 + own4 + gb);
+					float4 const ra = __ldg(ref4 + own4 + ga), rb = __ldg(ref4 + own4 + gb);
+					float4 const sa = (scl4 != nullptr) ? __ldg(scl4 + own4 + ga) : cs4;
+					float4 const sb = (scl4 != nullptr) ? __ldg(scl4 + own4 + gb) : cs4;
+					ya.x = CalibrateOne(sa.x, ya.x, ra.x);
+					ya.y = CalibrateOne(sa.y, ya.y, ra.y);
+					ya.z = CalibrateOne(sa.z, ya.z, ra.z);
+					ya.w = CalibrateOne(sa.w, ya.w, ra.w);
+					yb.x = CalibrateOne(sb.x, yb.x, rb.x);
+					yb.y = CalibrateOne(sb.y, yb.y, rb.y);
+					yb.z = CalibrateOne(sb.z, yb.z, rb.z);
+					yb.w = CalibrateOne(sb.w, yb.w, rb.w);
+					sd4[own4 + ga] = ya;
+					sd4[own4 + gb] = yb;
+				}
+			} else {
+				while (dirty != 0u) {
+					int const g = __ffs(dirty) - 1;
+					dirty &= dirty - 1u;
 					asm volatile("cp.async.ca.shared.global [%0], [%1], 16;"
 							:: "r"(smem_u32(sd4 + own4 + g)), "l"(grow4 + own4 + g) : "memory");
 				}

@@ -43,7 +43,7 @@ constexpr double kPivotTol = 1e-9; // pivot / diagonal entry below which a row g
 // -DSPLINE_CLOCKS: CTA 0 prints the cycles its warp 0 spent per phase (development only)
 #ifdef SPLINE_CLOCKS
 #define CLK(k) do { long long const t_ = clock64(); clk[k] += t_ - tprev; tprev = t_; } while (0)
-#define CLK_ARGS , long long (&clk)[12], long long &tprev
+#define CLK_ARGS , long long (&clk)[16], long long &tprev
 #define CLK_PASS , clk, tprev
 #else
 #define CLK(k) do { } while (0)
@@ -56,14 +56,13 @@ __device__ __forceinline__ double int_to_double(int v) {
 	return __hiloint2double(0x43300000, v) - 4503599627370496.0;
 }
 
+// reciprocal of a positive, normal double: hardware estimate (e ~ 2^-23) + one third-order step,
+// r (1 + e + e^2) = (1 - e^3) / x: ~1 ulp with three dependent operations after the estimate
 __device__ __forceinline__ double rcp_pos(double x) {
 	double r;
 	asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
-	double e = fma(-x, r, 1.0);
-	r = fma(r, e, r);
-	e = fma(-x, r, 1.0);
-	r = fma(r, e, r);
-	return r;
+	double const e = fma(-x, r, 1.0);
+	return fma(r, fma(e, e, e), r);
 }
 
 constexpr int kGpStride = 11; // 10 band contributions per basis row (odd: conflict-free lane reads)
@@ -144,7 +143,7 @@ __device__ __forceinline__ bool Bit(unsigned const *bits, int i) {
 // One warp walks the channels [b0, b1) of a piece: the 4-aligned interior four channels per lane
 // (128-bit shared-memory accesses, vec(i) with i % 4 == 0), the <= 3 + 3 channels at the two ends
 // one per lane (one(i)). The order in which channels are visited does not matter to the callers.
-template<class Vec, class One>
+template<int UNROLL = 1, class Vec, class One>
 __device__ __forceinline__ void ForPiece(int b0, int b1, int lane, Vec vec, One one) {
 	int const a0 = min((b0 + 3) & ~3, b1);
 	int const a1 = max(b1 & ~3, a0);
@@ -153,6 +152,7 @@ __device__ __forceinline__ void ForPiece(int b0, int b1, int lane, Vec vec, One 
 	} else if (lane >= 16 && lane - 16 < b1 - a1) {
 		one(a1 + lane - 16);
 	}
+#pragma unroll UNROLL
 	for (int i = a0 + 4 * lane; i < a1; i += 128) {
 		vec(i);
 	}
@@ -458,7 +458,7 @@ SplineFitKernel(SplineFitParams const p) {
 	double const max_x = static_cast<double>(n - 1);
 	double const inv = 1.0 / max_x;
 #ifdef SPLINE_CLOCKS
-	long long clk[12] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
+	long long clk[16] = { 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0 };
 	long long tprev = clock64();
 #endif
 
@@ -511,6 +511,7 @@ SplineFitKernel(SplineFitParams const p) {
 			}
 		}
 		int const num_valid = BlockSumInt(cnt, s.iscr, lane, warp);
+		CLK(12);
 		if (num_valid < npiece) { // baseline.cc:822-824 -> Status_kNG, lsqfit_status stays kNG
 			if (tid == 0) {
 				p.status[row] = kStatusNG;
@@ -519,6 +520,7 @@ SplineFitKernel(SplineFitParams const p) {
 			continue;
 		}
 		Boundaries(n, npiece, num_valid, s, tid);
+		CLK(13);
 		if (p.boundary != nullptr) {
 			for (int i = tid; i <= npiece; i += NTHR) {
 				p.boundary[row * (npiece + 1) + i] = static_cast<unsigned long long>(s.bound[i]);
@@ -545,6 +547,7 @@ SplineFitKernel(SplineFitParams const p) {
 		if (warp == NW - 1 && lane < npiece) {
 			PieceBasis(lane, npiece, s, inv);
 		}
+		CLK(14);
 		// ---- local moments, one warp per piece ---------------------------------------------------------
 		for (int q = warp; q < npiece; q += NW) {
 			int const b0 = s.bound[q];
@@ -692,11 +695,16 @@ SplineFitKernel(SplineFitParams const p) {
 				double h[7] = { 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0 };
 				double t[4] = { 0.0, 0.0, 0.0, 0.0 };
 				bool mine = false;
+				int pend = -1; // a clipped channel whose moments are not yet taken (most lanes meet at most one
+				// per piece: all of them are then processed together after the scan, not one by one)
 				auto hit = [&](int i) { // channel i is clipped: unflag it, remember its moments
 					atomicAnd(s.bits + (i >> 5), ~(1u << (i & 31)));
 					++nclip;
 					mine = true;
-					AddMoments(h, t, int_to_double(i - b0) * inv, static_cast<double>(s.y[i]));
+					if (pend >= 0) {
+						AddMoments(h, t, int_to_double(pend - b0) * inv, static_cast<double>(s.y[pend]));
+					}
+					pend = i;
 				};
 				ForPiece(b0, last, lane, [&](int i) {
 					float4 const r = *reinterpret_cast<float4 const *>(s.r + i);
@@ -715,6 +723,9 @@ SplineFitKernel(SplineFitParams const p) {
 						hit(i);
 					}
 				});
+				if (pend >= 0) {
+					AddMoments(h, t, int_to_double(pend - b0) * inv, static_cast<double>(s.y[pend]));
+				}
 				if (__any_sync(kFull, mine)) {
 					double keep = 0.0;
 #pragma unroll
@@ -810,8 +821,8 @@ SplineFitKernel(SplineFitParams const p) {
 #ifdef SPLINE_CLOCKS
 	CLK(11);
 	if (blockIdx.x == 0 && tid == 0) {
-		printf("spline clocks (CTA 0, warp 0): moments %lld | blocks %lld assemble %lld factor %lld backsub %lld - %lld "
-				"(unused) barrier %lld | model %lld sum3 %lld | clip %lld sumint %lld | outputs+load %lld\n", clk[0], clk[1], clk[2],
+		printf("spline clocks (CTA 0, warp 0): load %lld bounds %lld basis %lld moments %lld | blocks %lld assemble %lld factor %lld backsub %lld - %lld "
+				"(unused) barrier %lld | model %lld sum3 %lld | clip %lld sumint %lld | outputs+load %lld\n", clk[12], clk[13], clk[14], clk[0], clk[1], clk[2],
 				clk[3], clk[4], clk[5], clk[6], clk[7], clk[8], clk[9], clk[10], clk[11]);
 	}
 #endif

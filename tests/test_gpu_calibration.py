@@ -84,8 +84,8 @@ def test_batch_device_matches_oracle(lib, dev, oracle):
     assert np.array_equal(bits(dd.cpu().numpy()), bits(ref))
 
 
-@pytest.mark.parametrize("n,order,kernel", [(4096, 5, "poly_screen"), (1008, 3, "poly_fast"), (8192, 7, "poly_screen"),
-                                            (1024, 9, "general")])
+@pytest.mark.parametrize("n,order,kernel", [(4096, 5, "poly_warp"), (2048, 5, "poly_warp"), (2048, 2, "poly_warp"),
+                                            (1008, 3, "poly_fast"), (8192, 7, "poly_screen"), (1024, 9, "general")])
 def test_fused_calibration_equals_sequence(lib, dev, oracle, n, order, kernel):
     import torch
     rows = 48
@@ -104,7 +104,7 @@ def test_fused_calibration_equals_sequence(lib, dev, oracle, n, order, kernel):
     cal = dev.calibrate(s, d, r)
     m2 = m & torch.isfinite(cal)
     # (bit-for-bit: the sequence must run the kernel family the fused call ran)
-    with forced_kernel({"poly_screen": "screen"}.get(kernel, "channel")):
+    with forced_kernel({"poly_screen": "screen", "poly_warp": "warp"}.get(kernel, "channel")):
         seq = dev.polynomial(ctx, order, cal, m2, 3.0, 4, want_best_fit=True)
     torch.cuda.synchronize()
     for k in ("status", "lsqfit_status", "final_mask", "rms", "coeff", "residual", "best_fit"):
