@@ -254,8 +254,8 @@ __device__ void Boundaries(int n, int npiece, int num_valid, Smem const &s, int 
 	}
 	// rank targets once per row (64-bit divisions), then every thread only compares
 	int *tgt = reinterpret_cast<int *>(s.Gp);
+	unsigned const N = static_cast<unsigned>(num_valid); // N * npiece < 2^31: 32-bit divisions
 	if (tid >= 1 && tid < npiece) {
-		long long const N = num_valid;
 		tgt[tid] = static_cast<int>((N * tid + npiece - 1) / npiece);
 	}
 	if (tid == 0) {
@@ -267,19 +267,26 @@ __device__ void Boundaries(int n, int npiece, int num_valid, Smem const &s, int 
 	for (int w = 0; w < warp; ++w) {
 		start += s.iscr[w];
 	}
-	for (int idx = 1; idx < npiece; ++idx) {
-		int const target = tgt[idx];
-		if (target >= start && target < start + cnt) {
-			int rem = target - start;
-			for (int w = lo; w < hi; ++w) {
-				unsigned const v = s.bits[w];
-				int const c = __popc(v);
-				if (rem < c) {
-					// position of the set bit of rank rem
-					s.bound[idx] = 32 * w + (__fns(v, 0, rem + 1));
-					break;
+	if (cnt > 0) {
+		// the targets ceil(N idx / npiece) ascend: the first one >= start has idx > (start - 1) npiece / N
+		int idx = (start == 0) ? 1 : static_cast<int>((static_cast<unsigned>(start - 1) * npiece) / N) + 1;
+		for (; idx < npiece; ++idx) {
+			int const target = tgt[idx];
+			if (target >= start + cnt) {
+				break;
+			}
+			if (target >= start) {
+				int rem = target - start;
+				for (int w = lo; w < hi; ++w) {
+					unsigned const v = s.bits[w];
+					int const c = __popc(v);
+					if (rem < c) {
+						// position of the set bit of rank rem
+						s.bound[idx] = 32 * w + (__fns(v, 0, rem + 1));
+						break;
+					}
+					rem -= c;
 				}
-				rem -= c;
 			}
 		}
 	}
@@ -445,6 +452,14 @@ __device__ bool BandSolve(int npiece, int K, Smem const &s, int lane CLK_ARGS) {
 	return true;
 }
 
+__device__ __forceinline__ void LoadRowAsync(float *sy, float const *data, int n, int tid) {
+	for (int i = tid * 4; i < n; i += NTHR * 4) {
+		asm volatile("cp.async.ca.shared.global [%0], [%1], 16;"
+				:: "r"(static_cast<unsigned>(__cvta_generic_to_shared(sy + i))), "l"(data + i) : "memory");
+	}
+	asm volatile("cp.async.commit_group;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(NTHR, 3)
 SplineFitKernel(SplineFitParams const p) {
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -462,32 +477,33 @@ SplineFitKernel(SplineFitParams const p) {
 	long long tprev = clock64();
 #endif
 
+	bool preloaded = false;
 	for (size_t row = blockIdx.x; row < p.num_spectra; row += gridDim.x) {
 		float const *data = p.data + row * p.data_stride;
 		uint8_t const *mask = p.mask + row * p.mask_stride;
 		__syncthreads(); // previous row's shared state fully consumed
 		CLK(11);
+		// the spectrum: asynchronous 16-byte copies straight into shared memory, all in flight at once
+		// (already under way when the previous row of this CTA started them behind its last pass)
+		if (!preloaded) {
+			LoadRowAsync(s.y, data, n, tid);
+		}
+		preloaded = false;
+		// the mask: bytes -> one bit per channel, four 128-channel groups per warp and step in flight
 		int cnt = 0;
-		for (int i0 = warp * 128; i0 < n; i0 += NTHR * 8) { // warp-uniform bounds: shuffles inside
-			// two 128-channel groups per step, their loads in flight together
-			unsigned v[2] = { 0u, 0u };
-			float4 yv[2];
+		constexpr int kGroups = 4;
+		for (int i0 = warp * 128; i0 < n; i0 += NTHR * 4 * kGroups) { // warp-uniform bounds: shuffles inside
+			unsigned v[kGroups];
 #pragma unroll
-			for (int g = 0; g < 2; ++g) {
+			for (int g = 0; g < kGroups; ++g) {
 				int const i = i0 + g * NTHR * 4 + 4 * lane;
-				if (i < n) {
-					v[g] = *reinterpret_cast<unsigned const *>(mask + i);
-					yv[g] = *reinterpret_cast<float4 const *>(data + i);
-				}
+				v[g] = (i < n) ? *reinterpret_cast<unsigned const *>(mask + i) : 0u;
 			}
 #pragma unroll
-			for (int g = 0; g < 2; ++g) {
+			for (int g = 0; g < kGroups; ++g) {
 				int const i = i0 + g * NTHR * 4 + 4 * lane;
 				if (i0 + g * NTHR * 4 >= n) {
 					break;
-				}
-				if (i < n) {
-					*reinterpret_cast<float4 *>(s.y + i) = yv[g];
 				}
 				unsigned w = __vcmpne4(v[g], 0u) & 0x01010101u;
 				w = ((w * 0x10204080u) >> 28) << (4 * (lane & 7)); // the four flags as a nibble
@@ -500,6 +516,7 @@ SplineFitKernel(SplineFitParams const p) {
 				}
 			}
 		}
+		asm volatile("cp.async.wait_group 0;" ::: "memory");
 		if (row + gridDim.x < p.num_spectra) { // the next spectrum of this CTA: into L2 while this one is fitted
 			char const *nd = reinterpret_cast<char const *>(data + gridDim.x * p.data_stride);
 			char const *nm = reinterpret_cast<char const *>(mask + gridDim.x * p.mask_stride);
@@ -751,6 +768,12 @@ SplineFitKernel(SplineFitParams const p) {
 			}
 			num_unmasked = c - num_clipped;
 			__syncthreads();
+		}
+		// every warp is past its last pass over the spectrum (a block barrier lies behind each way out of the
+		// loop): the next row's copy can run while this row's results are written
+		if (row + gridDim.x < p.num_spectra) {
+			LoadRowAsync(s.y, data + gridDim.x * p.data_stride, n, tid);
+			preloaded = true;
 		}
 		if (fallback) {
 			if (tid == 0) {
