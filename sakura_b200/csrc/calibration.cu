@@ -29,7 +29,8 @@ CalibrateKernel(CalibrateParams const p) {
 	}
 }
 
-// four channels per thread with 128-bit accesses; no mask output
+// four channels per thread with 128-bit accesses; MASK: mask_out = mask && finite(result) (32-bit accesses)
+template<bool MASK>
 __global__ void __launch_bounds__(256)
 CalibrateKernel4(CalibrateParams const p) {
 	size_t const n4 = p.num_data / 4;
@@ -39,6 +40,8 @@ CalibrateKernel4(CalibrateParams const p) {
 		float4 const *s = p.spec.scaling ?
 				reinterpret_cast<float4 const *>(p.spec.scaling + row * p.spec.scaling_stride) : nullptr;
 		float4 *out = reinterpret_cast<float4 *>(p.result + row * p.result_stride);
+		uint32_t const *m = MASK ? reinterpret_cast<uint32_t const *>(p.mask + row * p.mask_stride) : nullptr;
+		uint32_t *mo = MASK ? reinterpret_cast<uint32_t *>(p.mask_out + row * p.mask_stride) : nullptr;
 		for (size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
 				i += static_cast<size_t>(gridDim.x) * blockDim.x) {
 			float4 const tv = t[i];
@@ -48,8 +51,20 @@ CalibrateKernel4(CalibrateParams const p) {
 			if (s != nullptr) {
 				sv = s[i];
 			}
-			out[i] = make_float4(CalibrateOne(sv.x, tv.x, rv.x), CalibrateOne(sv.y, tv.y, rv.y),
+			float4 const v = make_float4(CalibrateOne(sv.x, tv.x, rv.x), CalibrateOne(sv.y, tv.y, rv.y),
 					CalibrateOne(sv.z, tv.z, rv.z), CalibrateOne(sv.w, tv.w, rv.w));
+			out[i] = v;
+			if (MASK) {
+				uint32_t w = __vcmpne4(m[i], 0u) & 0x01010101u; // any non-zero byte is "true"
+				if (p.spec.flag_nonfinite) {
+					auto finite = [](float x) {
+						return (__float_as_uint(x) & 0x7f800000u) != 0x7f800000u;
+					};
+					w &= (finite(v.x) ? 0x1u : 0u) | (finite(v.y) ? 0x100u : 0u) | (finite(v.z) ? 0x10000u : 0u)
+							| (finite(v.w) ? 0x1000000u : 0u);
+				}
+				mo[i] = w;
+			}
 		}
 	}
 }
@@ -64,7 +79,10 @@ cudaError_t LaunchCalibrate(CalibrateParams const &p, int num_sms, cudaStream_t 
 	if (p.num_spectra == 0 || p.num_data == 0) {
 		return cudaSuccess;
 	}
-	if (p.mask_out == nullptr && p.num_data % 4 == 0 && Aligned16(p.data, p.data_stride)
+	bool const mask4 = p.mask_out == nullptr
+			|| ((reinterpret_cast<uintptr_t>(p.mask) % 4) == 0 && (reinterpret_cast<uintptr_t>(p.mask_out) % 4) == 0
+					&& p.mask_stride % 4 == 0);
+	if (mask4 && p.num_data % 4 == 0 && Aligned16(p.data, p.data_stride)
 			&& Aligned16(p.spec.reference, p.spec.reference_stride)
 			&& Aligned16(p.spec.scaling, p.spec.scaling_stride) && Aligned16(p.result, p.result_stride)) {
 		unsigned bx4 = static_cast<unsigned>((p.num_data / 4 + 255) / 256);
@@ -78,7 +96,11 @@ cudaError_t LaunchCalibrate(CalibrateParams const &p, int num_sms, cudaStream_t 
 		if (by4 > 65535) {
 			by4 = 65535;
 		}
-		CalibrateKernel4<<<dim3(bx4, static_cast<unsigned>(by4)), 256, 0, stream>>>(p);
+		if (p.mask_out != nullptr) {
+			CalibrateKernel4<true><<<dim3(bx4, static_cast<unsigned>(by4)), 256, 0, stream>>>(p);
+		} else {
+			CalibrateKernel4<false><<<dim3(bx4, static_cast<unsigned>(by4)), 256, 0, stream>>>(p);
+		}
 		return cudaGetLastError();
 	}
 	unsigned bx = static_cast<unsigned>((p.num_data + 255) / 256);

@@ -295,7 +295,11 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 	if (f.cal.reference != nullptr) {
 		// The polynomial kernel calibrates while it loads a row. Every other path gets the
 		// calibrated spectra (and the NaN/Inf-merged mask) from a pre-pass into context scratch.
+		// Exception (measured, profiles/README.md): where the warp-per-spectrum kernel fits (2048 / 4096
+		// channels from two fits on) the pre-pass at HBM speed plus the plain fit beats calibrating inside
+		// that latency-bound kernel (10.9 against 12.4 ms at 524 288 x 2048), so the pre-pass is used there.
 		bool const fused = (f.type == kFitPolynomial || (f.type == kFitChebyshev && f.K <= 6))
+				&& !PolyPrefersCalibrationPrePass(f.num_data, f.nfit)
 				&& PolyFusedCalibrationSupported(f.num_data)
 				&& PolyFastSupported(f.num_data, f.K, f.data_stride, f.mask_stride, f.data, f.mask,
 						f.best_fit, f.residual, f.final_mask)

@@ -943,6 +943,21 @@ bool PolyFusedCalibrationSupported(size_t n) {
 	return n == 4u * 64u * kSlotGroups || n == 4u * 128u * kSlotGroups || n == 4u * 256u * kSlotGroups;
 }
 
+bool PolyPrefersCalibrationPrePass(size_t n, int num_fitting_max) {
+	char const *fused = getenv("SAKURA_B200_CAL_FUSED");
+	if (fused != nullptr && fused[0] == '1') {
+		return false;
+	}
+	char const *k = getenv("SAKURA_B200_POLY_KERNEL");
+	if (k != nullptr && (k[0] == 'c' || k[0] == 's')) {
+		return false; // a forced kernel keeps its fused variant
+	}
+	if (getenv("SAKURA_B200_POLY_SCREEN") != nullptr) {
+		return false;
+	}
+	return (n == 2048 || n == 4096) && num_fitting_max >= 2;
+}
+
 namespace {
 
 cudaError_t LaunchPolyFitKernel(PolyFitParams const &p, int num_sms, cudaStream_t stream);

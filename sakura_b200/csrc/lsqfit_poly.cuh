@@ -50,6 +50,10 @@ bool PolyFastSupported(size_t n, size_t K, size_t data_stride, size_t mask_strid
  *  (4096 and 8192: every thread owns all of its 32 channel slots). */
 bool PolyFusedCalibrationSupported(size_t n);
 
+/** True when a separate calibration pass followed by the plain fit is the faster way for this shape
+ *  (the warp-per-spectrum kernel would run the fit; SAKURA_B200_CAL_FUSED=1 keeps the fused variants). */
+bool PolyPrefersCalibrationPrePass(size_t n, int num_fitting_max);
+
 cudaError_t LaunchPolyFit(PolyFitParams const &p, int num_sms, cudaStream_t stream, int *launches,
 		char const **kernel_name);
 

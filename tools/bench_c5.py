@@ -6,7 +6,7 @@ from sakura_b200.capi import SakuraLib
 from sakura_b200.device_api import DeviceFits
 import bench
 lib = SakuraLib(); dev = DeviceFits(lib)
-R, n = (int(sys.argv[1]) if len(sys.argv) > 1 else 262144), 4096
+R, n = (int(sys.argv[1]) if len(sys.argv) > 1 else 262144), (int(sys.argv[2]) if len(sys.argv) > 2 else 4096)
 device = torch.device("cuda", 0)
 data, mask = bench.generate_on_device(torch, R, n, seed=5, device=device)
 off = 300.0 + 20.0 * torch.randn(R, n, device=device)
