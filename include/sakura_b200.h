@@ -505,6 +505,17 @@ char const *sakura_b200_GetVersionString(void) SAKURA_B200_NOEXCEPT;
  *  less than this many KiB use one pinned arena with a single upload and download (default 2048,
  *  environment SAKURA_B200_PACKED_KIB; 0 disables that path). Results do not depend on either. */
 void sakura_b200_SetHostPipelineTuning(int64_t chunk_mib, int64_t packed_kib) SAKURA_B200_NOEXCEPT;
+/** The host-side codec of the pipelined paths (no GPU involved): boolean masks (one byte per channel, any
+ *  non-zero byte is true, as `bool const mask[]` of sakura.h:1773-1781) to one bit per channel and back.
+ *  The batch entry points move masks over PCIe in this form (a fifth of the bytes of a spectrum in either
+ *  direction; SAKURA_B200_PACK_MASKS=0 turns that off); exported so that the codec can be tested and used
+ *  on its own. `num_data` must be a multiple of 32; `bits` holds num_rows * num_data / 32 words, bit b of
+ *  word w of a row = channel 32 w + b. Unpacking writes bytes 0 / 1 and only the rows r with
+ *  (row_flags[r] & flag_bit) != 0 when `row_flags` is not NULL. */
+sakura_Status sakura_b200_PackBoolMaskRows(size_t num_rows, size_t num_data, bool const mask[],
+		size_t mask_stride, uint32_t bits[]) SAKURA_B200_NOEXCEPT;
+sakura_Status sakura_b200_UnpackBoolMaskRows(size_t num_rows, size_t num_data, uint32_t const bits[],
+		bool mask[], size_t mask_stride, int32_t const row_flags[], int32_t flag_bit) SAKURA_B200_NOEXCEPT;
 
 #ifdef __cplusplus
 }

@@ -19,8 +19,8 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsakura_b200.so")
 
 CUDA_SOURCES = ["capi_core.cu", "capi_fit.cu", "capi_filters.cu", "capi_stats.cu", "lsqfit_general.cu", "lsqfit_poly.cu", "lsqfit_poly_screen.cu", "lsqfit_poly_warp.cu", "statistics.cu",
-                "lsq_blocks.cu", "lsqfit_sinusoid.cu", "lsqfit_spline.cu", "calibration.cu", "bool_filters.cu", "interpolation.cu"]
-HOST_SOURCES = ["basis_tables.cc"]
+                "lsq_blocks.cu", "lsqfit_sinusoid.cu", "lsqfit_spline.cu", "calibration.cu", "bool_filters.cu", "interpolation.cu", "mask_bits.cu"]
+HOST_SOURCES = ["basis_tables.cc", "host_bits.cc"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

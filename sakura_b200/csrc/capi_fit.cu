@@ -1,6 +1,8 @@
 // C ABI of libsakura_b200.so, part 2: the least-squares fit entry points (host-pointer batches with the
 // copy/compute pipeline, device-array batches, the reference's single-row signatures, Subtract*).
 #include "capi_internal.cuh"
+#include "host_bits.h"
+#include "mask_bits.cuh"
 
 #include <thread>
 #include <time.h>
@@ -86,6 +88,12 @@ double HostMs() {
 	return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
+// Masks over PCIe as bits (host_bits.h): on unless SAKURA_B200_PACK_MASKS=0 (read per call: A/B timing).
+bool PackMasksEnabled() {
+	char const *e = getenv("SAKURA_B200_PACK_MASKS");
+	return e == nullptr || e[0] != '0';
+}
+
 sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, size_t chunk_rows,
 		bool fast) {
 	static bool const trace_on = getenv("SAKURA_B200_PIPELINE_TRACE") != nullptr;
@@ -98,6 +106,8 @@ sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, s
 	size_t const nb = f.npiece + 1;
 	bool const spline = (f.type == kFitCubicSpline);
 	int const published = AllPublished(f.type);
+	bool const pack = (n % 32 == 0) && PackMasksEnabled();
+	size_t const words = n / 32;
 	std::vector<size_t> start; // chunk boundaries (a ramp of shorter chunks at both ends was measured: no gain)
 	for (size_t r = 0; r < R; r += chunk_rows) {
 		start.push_back(r);
@@ -152,8 +162,42 @@ sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, s
 					cudaHostAllocDefault));
 			sl.h_flags_cap = chunk_rows;
 		}
+		if (pack) {
+			CUDA_TRY(sl.mask_bits.Reserve(chunk_rows * words * sizeof(uint32_t)));
+			CUDA_TRY(sl.fmask_bits.Reserve(chunk_rows * words * sizeof(uint32_t)));
+			if (sl.h_bits_cap < chunk_rows * words) {
+				if (sl.h_mask_bits != nullptr) {
+					cudaFreeHost(sl.h_mask_bits);
+					sl.h_mask_bits = nullptr;
+				}
+				if (sl.h_fmask_bits != nullptr) {
+					cudaFreeHost(sl.h_fmask_bits);
+					sl.h_fmask_bits = nullptr;
+				}
+				sl.h_bits_cap = 0;
+				CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_mask_bits),
+						chunk_rows * words * sizeof(uint32_t), cudaHostAllocDefault));
+				CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&sl.h_fmask_bits),
+						chunk_rows * words * sizeof(uint32_t), cudaHostAllocDefault));
+				sl.h_bits_cap = chunk_rows * words;
+			}
+		}
+		sl.unpack_rows = 0;
 		sl.rows = 0;
 	}
+	// final-mask bits of an earlier chunk of this slot, downloaded meanwhile: expand them into the caller's
+	// array (worker threads) before the staging buffer is used again
+	auto complete_unpack = [&](PipelineSlot &sl) -> sakura_Status {
+		if (sl.unpack_rows == 0) {
+			return sakura_Status_kOK;
+		}
+		CUDA_TRY(cudaEventSynchronize(sl.down_done));
+		UnpackMaskRows(sl.h_fmask_bits, n, sl.unpack_rows,
+				reinterpret_cast<uint8_t *>(h.final_mask) + sl.unpack_row0 * hms, hms,
+				sl.unpack_all ? nullptr : sl.unpack_flags.data(), 2);
+		sl.unpack_rows = 0;
+		return sakura_Status_kOK;
+	};
 	auto finish = [&](PipelineSlot &sl) -> sakura_Status {
 		// the kernel of this slot's chunk is done and its per-row flags are on the host
 		CUDA_TRY(cudaEventSynchronize(sl.flags_ready));
@@ -171,6 +215,20 @@ sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, s
 				break;
 			}
 		}
+		if (pack) {
+			sakura_Status const us = complete_unpack(sl);
+			if (us != sakura_Status_kOK) {
+				return us;
+			}
+			CUDA_TRY(cudaMemcpyAsync(sl.h_fmask_bits, sl.fmask_bits.ptr, rows * words * sizeof(uint32_t),
+					cudaMemcpyDeviceToHost, sl.down));
+			sl.unpack_rows = rows;
+			sl.unpack_row0 = r0;
+			sl.unpack_all = all_published;
+			if (!all_published) {
+				sl.unpack_flags.assign(sl.h_flags, sl.h_flags + rows);
+			}
+		}
 		if (all_published) {
 			if (h.coeff != nullptr) {
 				CUDA_TRY(cudaMemcpyAsync(h.coeff + r0 * f.coeff_stride, sl.coeff.ptr,
@@ -186,8 +244,10 @@ sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, s
 						dstride * sizeof(float), n * sizeof(float), rows, cudaMemcpyDeviceToHost,
 						sl.down));
 			}
-			CUDA_TRY(CopyRows(h.final_mask + r0 * hms, hms, sl.final_mask.ptr, dstride, n, rows,
-					cudaMemcpyDeviceToHost, sl.down));
+			if (!pack) {
+				CUDA_TRY(CopyRows(h.final_mask + r0 * hms, hms, sl.final_mask.ptr, dstride, n, rows,
+						cudaMemcpyDeviceToHost, sl.down));
+			}
 			CUDA_TRY(cudaMemcpyAsync(h.rms + r0, d_rms, rows * sizeof(float), cudaMemcpyDeviceToHost,
 					sl.down));
 			if (spline) {
@@ -216,7 +276,7 @@ sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, s
 					CUDA_TRY(cudaMemcpyAsync(h.rms + r0 + r, d_rms + r, sizeof(float),
 							cudaMemcpyDeviceToHost, sl.down));
 				}
-				if (fl & 2) {
+				if ((fl & 2) && !pack) {
 					CUDA_TRY(cudaMemcpyAsync(h.final_mask + (r0 + r) * hms,
 							sl.final_mask.As<uint8_t>() + r * dstride, n, cudaMemcpyDeviceToHost,
 							sl.down));
@@ -259,8 +319,18 @@ sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, s
 		}
 		CUDA_TRY(CopyRows(sl.data.ptr, dstride * sizeof(float), h.data + r0 * hds,
 				hds * sizeof(float), n * sizeof(float), rows, cudaMemcpyHostToDevice, sl.stream));
-		CUDA_TRY(CopyRows(sl.mask.ptr, dstride, h.mask + r0 * hms, hms, n, rows,
-				cudaMemcpyHostToDevice, sl.stream));
+		if (pack) {
+			// (the slot's previous upload of the staging words is long done: its kernel has finished)
+			PackMaskRows(reinterpret_cast<uint8_t const *>(h.mask) + r0 * hms, hms, n, rows, sl.h_mask_bits);
+			CUDA_TRY(cudaMemcpyAsync(sl.mask_bits.ptr, sl.h_mask_bits, rows * words * sizeof(uint32_t),
+					cudaMemcpyHostToDevice, sl.stream));
+			CUDA_TRY(LaunchMaskBitsToBytes(sl.mask_bits.As<uint32_t>(), words, rows, sl.mask.As<uint8_t>(),
+					dstride, sl.stream));
+			g_launch_count += 1;
+		} else {
+			CUDA_TRY(CopyRows(sl.mask.ptr, dstride, h.mask + r0 * hms, hms, n, rows,
+					cudaMemcpyHostToDevice, sl.stream));
+		}
 		if (trace_on) {
 			cudaEventRecord(trace[ci].up1, sl.stream);
 		}
@@ -291,6 +361,11 @@ sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, s
 		if (st != sakura_Status_kOK) {
 			return st;
 		}
+		if (pack) {
+			CUDA_TRY(LaunchMaskBytesToBits(sl.final_mask.As<uint8_t>(), dstride, words, rows,
+					sl.fmask_bits.As<uint32_t>(), sl.stream));
+			g_launch_count += 1;
+		}
 		if (trace_on) {
 			cudaEventRecord(trace[ci].k1, sl.stream);
 		}
@@ -317,6 +392,14 @@ sakura_Status PipelineBody(Context *c, FitCall const &f, HostFitArgs const &h, s
 	for (int s = 0; s < kPipelineSlots; ++s) {
 		CUDA_TRY(cudaStreamSynchronize(c->slots[s].stream));
 		CUDA_TRY(cudaStreamSynchronize(c->slots[s].down));
+	}
+	if (pack) {
+		for (int s = 0; s < kPipelineSlots; ++s) {
+			st = complete_unpack(c->slots[s]);
+			if (st != sakura_Status_kOK) {
+				return st;
+			}
+		}
 	}
 	if (trace_on) {
 		fprintf(stderr, "sakura_b200 pipeline trace: %zu chunks of %zu rows, host total %.3f ms\n"
@@ -365,6 +448,7 @@ sakura_Status RunHostBatchPipelined(Context *c, FitCall const &f, HostFitArgs co
 				(void) cudaStreamSynchronize(sl.down);
 			}
 			sl.rows = 0;
+			sl.unpack_rows = 0;
 		}
 		(void) cudaGetLastError();
 	}
@@ -1520,4 +1604,29 @@ void sakura_b200_SetHostPipelineTuning(int64_t chunk_mib, int64_t packed_kib) no
 	if (packed_kib >= 0 && packed_kib <= (1 << 20)) {
 		g_packed_kib.store(static_cast<size_t>(packed_kib));
 	}
+}
+
+sakura_Status sakura_b200_PackBoolMaskRows(size_t num_rows, size_t num_data, bool const mask[],
+		size_t mask_stride, uint32_t bits[]) noexcept {
+	CHECK_ARGS(num_data % 32 == 0 && mask_stride >= num_data);
+	CHECK_ARGS(num_rows == 0 || (mask != nullptr && bits != nullptr));
+	try {
+		sakura_b200::PackMaskRows(reinterpret_cast<uint8_t const *>(mask), mask_stride, num_data, num_rows, bits);
+	} catch (...) {
+		return sakura_Status_kUnknownError;
+	}
+	return sakura_Status_kOK;
+}
+
+sakura_Status sakura_b200_UnpackBoolMaskRows(size_t num_rows, size_t num_data, uint32_t const bits[],
+		bool mask[], size_t mask_stride, int32_t const row_flags[], int32_t flag_bit) noexcept {
+	CHECK_ARGS(num_data % 32 == 0 && mask_stride >= num_data);
+	CHECK_ARGS(num_rows == 0 || (mask != nullptr && bits != nullptr));
+	try {
+		sakura_b200::UnpackMaskRows(bits, num_data, num_rows, reinterpret_cast<uint8_t *>(mask), mask_stride,
+				row_flags, flag_bit);
+	} catch (...) {
+		return sakura_Status_kUnknownError;
+	}
+	return sakura_Status_kOK;
 }

@@ -117,6 +117,14 @@ struct PipelineSlot {
 	DeviceBuffer data, mask, coeff, best_fit, residual, final_mask, small, handover, boundary;
 	int32_t *h_flags = nullptr; // page-locked (a pageable target would make the copy block the host)
 	size_t h_flags_cap = 0;
+	// bit-packed mask transfer (host_bits.h): device words, page-locked staging of both directions, and
+	// the chunk whose downloaded final-mask bits still wait to be expanded into the caller's array
+	DeviceBuffer mask_bits, fmask_bits;
+	uint32_t *h_mask_bits = nullptr, *h_fmask_bits = nullptr;
+	size_t h_bits_cap = 0; // words each
+	size_t unpack_rows = 0, unpack_row0 = 0;
+	bool unpack_all = true;
+	std::vector<int32_t> unpack_flags; // per-row flags of that chunk when not every row published
 	size_t row0 = 0;
 	size_t rows = 0; // non-zero while a chunk is in flight in this slot
 	size_t chunk = 0; // its index in the call
@@ -151,6 +159,18 @@ struct PipelineSlot {
 			h_flags = nullptr;
 			h_flags_cap = 0;
 		}
+		mask_bits.Release();
+		fmask_bits.Release();
+		if (h_mask_bits != nullptr) {
+			cudaFreeHost(h_mask_bits);
+			h_mask_bits = nullptr;
+		}
+		if (h_fmask_bits != nullptr) {
+			cudaFreeHost(h_fmask_bits);
+			h_fmask_bits = nullptr;
+		}
+		h_bits_cap = 0;
+		unpack_rows = 0;
 		if (down_done != nullptr) {
 			cudaEventDestroy(down_done);
 			down_done = nullptr;

@@ -106,6 +106,25 @@ def test_packed_equals_single_chunk(lib, kind, n, rows):
     assert_bitwise(a, b)
 
 
+@pytest.mark.parametrize("kind,n,rows", [("poly", 4096, 1500), ("spline", 2048, 1200)])
+def test_pipeline_with_and_without_bit_packed_masks(lib, kind, n, rows, monkeypatch):
+    """The pipeline moves the masks over PCIe as bits by default (host_bits.h); SAKURA_B200_PACK_MASKS=0 keeps
+    them as bytes. Both against the single-chunk path, with mask bytes other than 0 / 1 ("any non-zero
+    byte is true") and failing rows whose final_mask must stay the caller's."""
+    K = {"poly": 6, "spline": 9}[kind]
+    data, mask = rows_with_failures(rows, n, K, seed=7 * n + rows)
+    odd = (mask.view(np.uint8) * np.uint8(0x84)).view(np.bool_)      # true = 0x84 instead of 0x01
+    a, _ = run(lib, kind, "serial", data, mask)
+    for packed in ("1", "0"):
+        monkeypatch.setenv("SAKURA_B200_PACK_MASKS", packed)
+        # (as bytes the general kernel hands a row's mask bytes through as they are: 0 / 1 input there)
+        b, _ = run(lib, kind, "pipeline", data, odd if packed == "1" else mask)
+        assert_bitwise(a, b)
+        bad = a["lsqfit_status"] == LSQFIT_NOT_ENOUGH_DATA
+        assert bad.sum() >= 3 and not b["final_mask"][bad].any()
+        assert set(np.unique(b["final_mask"].view(np.uint8))) <= {0, 1}
+
+
 def test_host_paths_against_oracle(lib, oracle):
     data, mask = rows_with_failures(1200, 4096, 6, seed=99)
     o = oracle.lsqfit_polynomial_batch(5, data, mask, 3.0, 4, want_best_fit=True)
