@@ -370,8 +370,10 @@ def side_configs(lib, torch, device, host=None, rows: int = 1 << 18, n: int = 81
         dt = (time.perf_counter() - t0) / reps
         er = hv["rows"]
         same = bool(torch.equal(hv["fmask"], fm[:er].cpu())) and bool(torch.equal(hv["status"], st[:er].cpu()))
+        packed = n % 32 == 0 and os.environ.get("SAKURA_B200_PACK_MASKS", "1")[:1] != "0"
+        mb = n // 8 if packed else n       # masks over PCIe as bits (sakura_b200/csrc/host_bits.cc)
         return {"value": er / dt, "unit": UNIT, "spectra_per_step": er, "ms_per_step": dt * 1e3,
-                "h2d_bytes_per_step": er * n * 5, "d2h_bytes_per_step": er * (n * 5 + d2h_extra),
+                "h2d_bytes_per_step": er * (n * 4 + mb), "d2h_bytes_per_step": er * (n * 4 + mb + d2h_extra),
                 "final_mask_and_status_match_device_path": same}
 
     peak_hbm = measured_peak_gbs()[0]
@@ -710,17 +712,23 @@ def run_ours(args) -> None:
         del slots
         e2e_step()  # the probe overwrote the result buffers: put the fit's results back
         torch.cuda.synchronize(device)
+        # the library moves the boolean masks over PCIe as one bit per channel (host codec on worker threads,
+        # sakura_b200/csrc/host_bits.cc) unless SAKURA_B200_PACK_MASKS=0: count what is actually copied
+        packed = n % 32 == 0 and os.environ.get("SAKURA_B200_PACK_MASKS", "1")[:1] != "0"
+        mask_bytes = n // 8 if packed else n
         e2e = {"value": world * er / dt, "unit": UNIT,
-               "h2d_bytes_per_step": er * (n * 4 + n),
-               "d2h_bytes_per_step": er * (n * 4 + n + 8 * K + 4 + 4 + 4),
+               "h2d_bytes_per_step": er * (n * 4 + mask_bytes),
+               "d2h_bytes_per_step": er * (n * 4 + mask_bytes + 8 * K + 4 + 4 + 4 + 4),
                "spectra_per_step": er, "ms_per_step": dt * 1e3,
                "api": "sakura_LSQFitPolynomialFloatBatchMultiDevice (pinned host buffers, per GPU a 4-slot "
-                      "upload | kernel | download pipeline)",
-               "pcie_gbs_per_direction_per_gpu": er * (n * 4 + n) / dt / 1e9,
+                      "upload | kernel | download pipeline" + (", masks bit-packed by host worker threads)"
+                                                                if packed else ")"),
+               "masks_bit_packed": packed,
+               "pcie_gbs_per_direction_per_gpu": er * (n * 4 + mask_bytes) / dt / 1e9,
                "copy_only_ceiling": {"spectra_per_s": world * er / cdt, "ms_per_step": cdt * 1e3,
                                      "gbs_per_direction_per_gpu": er * n * 5 / cdt / 1e9,
-                                     "what": "the step's bytes (5 per channel each way) copied up and down "
-                                             "concurrently on every rank, no kernel"},
+                                     "what": "the caller's arrays as they are (5 bytes per channel each way) "
+                                             "copied up and down concurrently on every rank, no kernel"},
                "frac_of_copy_only_ceiling": cdt / dt,
                "pinned_buffers_numa_node": near.node,
                "status_match_device_path": bool(np.array_equal(h_status.numpy()[:snap_rows],
