@@ -1,5 +1,6 @@
-// Warp-level solve of a small symmetric positive definite system in shared memory, shared by the
-// sinusoid and cubic-spline kernels: blocked LDL^T (8 x 8 blocks) whose trailing updates are FP64
+// Warp-level solve of a small symmetric positive definite system in shared memory, used by the
+// sinusoid kernel (the cubic-spline kernel has its own banded solve since it fits in the B-spline
+// basis): blocked LDL^T (8 x 8 blocks) whose trailing updates are FP64
 // tensor-core MMAs (mma.sync m8n8k4). The reference solves the same normal equations with Eigen's
 // full-pivot LU (numeric_operation.cc:609-622); rows whose pivots are not safely positive are
 // reported to the caller, which hands them to the kernel that restates that LU.
