@@ -404,20 +404,52 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 		sp.num_spectra = f.num_spectra;
 		sp.n = static_cast<int>(n);
 		sp.K = static_cast<int>(f.K);
-		sp.Kp = static_cast<int>(RoundUp(f.K, 8));
 		sp.next = c->ext_cols;
 		bool columns_ok = true;
 		sp.cos_only = cheb_dmma ? 1 : 0;
-		for (size_t k = 0; k < f.K; ++k) {
-			int const col = f.use_idx[k];
-			if (cheb_dmma) { // basis T_col: a "cosine" of wave number col
-				sp.kind[k] = static_cast<int8_t>(col == 0 ? 0 : 2);
-				sp.wave[k] = static_cast<int16_t>(col);
-			} else {
-				sp.kind[k] = static_cast<int8_t>(col == 0 ? 0 : ((col & 1) ? 1 : 2));
-				sp.wave[k] = static_cast<int16_t>((col + 1) / 2);
+		// Slots of the fit: the bases that are EVEN about the middle of the row first (constant, cosines;
+		// Chebyshev T_m with even m), padded to a multiple of 8, then the ODD ones (sines; odd m), padded
+		// likewise -- the kernel contracts over half a row with the folded data y_i +- y_{n-1-i}
+		// (lsqfit_sinusoid.cu). Padding slots have kind -1 and no column of the context table.
+		int16_t slot_col[kSinMaxKp];
+		int num_slots = 0;
+		for (int pass = 0; pass < 2; ++pass) {
+			for (size_t k = 0; k < f.K; ++k) {
+				int const col = f.use_idx[k];
+				columns_ok = columns_ok && (col >= 0 && static_cast<size_t>(col) < c->num_bases);
+				bool const odd = (col & 1) != 0; // sinusoid: 1, sin w, cos w, ...; Chebyshev: T_col
+				if (odd != (pass == 1) || num_slots >= kSinMaxKp) {
+					continue;
+				}
+				if (cheb_dmma) { // basis T_col: a "cosine" of wave number col
+					sp.kind[num_slots] = static_cast<int8_t>(col == 0 ? 0 : 2);
+					sp.wave[num_slots] = static_cast<int16_t>(col);
+				} else {
+					sp.kind[num_slots] = static_cast<int8_t>(col == 0 ? 0 : ((col & 1) ? 1 : 2));
+					sp.wave[num_slots] = static_cast<int16_t>((col + 1) / 2);
+				}
+				sp.out_pos[num_slots] = static_cast<int8_t>(k);
+				slot_col[num_slots] = static_cast<int16_t>(col);
+				++num_slots;
 			}
-			columns_ok = columns_ok && (col >= 0 && static_cast<size_t>(col) < c->num_bases);
+			while (num_slots % 8 != 0 && num_slots < kSinMaxKp) {
+				sp.kind[num_slots] = -1;
+				sp.wave[num_slots] = 0;
+				sp.out_pos[num_slots] = -1;
+				slot_col[num_slots] = -1;
+				++num_slots;
+			}
+			if (pass == 0) {
+				sp.kc_p = num_slots;
+			}
+		}
+		sp.Kp = num_slots;
+		{ // every basis has a slot (the padded groups fit into kSinMaxKp slots)?
+			int real = 0;
+			for (int s2 = 0; s2 < num_slots; ++s2) {
+				real += sp.out_pos[s2] >= 0 ? 1 : 0;
+			}
+			columns_ok = columns_ok && real == sp.K && SinusoidLayoutSupported(sp.kc_p, sp.Kp);
 		}
 		if (columns_ok) {
 			size_t tiles = (f.num_spectra + kSinRowsPerTile - 1) / kSinRowsPerTile;
@@ -434,7 +466,8 @@ sakura_Status LaunchFit(Context *c, FitCall const &f_in, cudaStream_t stream) {
 			if (f.best_fit != nullptr) {
 				CUDA_TRY(c->ws_sin_best_fit.Reserve(sgrid * kSinRowsPerTile * n * sizeof(float)));
 			}
-			CUDA_TRY(cudaMemcpyAsync(c->d_useidx.ptr, f.use_idx, kMaxBases * sizeof(int16_t),
+			// (pageable source: the copy is staged by the runtime before the call returns)
+			CUDA_TRY(cudaMemcpyAsync(c->d_useidx.ptr, slot_col, kSinMaxKp * sizeof(int16_t),
 					cudaMemcpyHostToDevice, stream));
 			cudaError_t e = LaunchGatherTable(c->d_basis.As<double>(), static_cast<int>(c->num_bases),
 					sp.n, sp.K, sp.Kp, c->d_useidx.As<int16_t>(), c->d_table.As<double>(), sp, stream);

@@ -144,7 +144,7 @@ __device__ __forceinline__ Smem Carve(unsigned char *base, int Kp, int ext_ld) {
 // trig sums that is identically zero (S_0)
 __device__ unsigned GramPack(SinusoidFitParams const &p, int i, int j, int zero) {
 	unsigned const pos = (static_cast<unsigned>(i) << 26) | (static_cast<unsigned>(j) << 20);
-	if (i >= p.K || j >= p.K) {
+	if (p.kind[i] < 0 || p.kind[j] < 0) { // padding slot: identity row / column
 		return pos | kGramPad | (i == j ? kGramPadDiag : 0u);
 	}
 	int const ki = p.kind[i], wi = p.wave[i], kj = p.kind[j], wj = p.wave[j];
@@ -178,75 +178,70 @@ __device__ unsigned GramPack(SinusoidFitParams const &p, int i, int j, int zero)
 	return pos | neg | i1 | (i2 << 8);
 }
 
-// acc[m][nt] += sum over the warp's channel groups of A[8 (mt0 + m) + r][ch] * B[ch][8 nt + c],
-// where A = mask (WITH_Y: mask * y). A warp pair shares the channel groups and splits the four
-// 8-row groups of the tile (mt0 = 0 or 2). 16 channels per step; lane (r8, c4) feeds channels
-// c0 + 4 c4 + s.
-// The B tiles (16 channels x ldb doubles, contiguous in global memory) arrive through the pair's
-// two-stage bulk-copy ring; the A operands (this lane's mask word and float4 of y per row group)
-// are loaded one step ahead into registers.
-template<int NTC, bool WITH_Y, bool NORMALIZE>
-__device__ __forceinline__ void MaskedContract(double (&acc)[MT][NTC][2], SinusoidFitParams const &p,
-		size_t row0, uint8_t *wmask, double const *B, int ldb, PairPipe &pp, int warp, int lane) {
+// Data moments b[r][k] = sum_i (mask*y)[r][i] * table[i][k] over the whole row from HALF of the table.
+// Every slot k is even or odd about the middle of the row, table[n-1-i][k] = +-table[i][k] (constant and
+// cosines / sines of integer wave numbers on x_i = i/(n-1); Chebyshev T_m on x_i = 2i/(n-1) - 1), so with the
+// folded data
+//     e[r][i] = (m y)[r][i] + (m y)[r][n-1-i],   o[r][i] = (m y)[r][i] - (m y)[r][n-1-i],   i < n/2
+// (exact in FP64: sums of two floats) the even slots contract e and the odd slots o: half the tensor-core
+// work of the plain contraction and half the table traffic. (The table's own two halves agree to a few
+// ulps, not bit for bit: an O(eps) difference like that of any other summation order.)
+// acc[m][nt] += sum over the warp's channel groups, 16 channels per step; lane (r8, c4) feeds channels
+// c0 + 4 c4 + s and their mirror images. A warp pair shares the channel groups and splits the four 8-row
+// groups of the tile (mt0 = 0 or 2). The B tiles (16 channels x ldb doubles, contiguous in global memory)
+// arrive through the pair's two-stage bulk-copy ring; the A operands (mask words and float4s of y of both
+// sides per row group) are loaded one step ahead into registers.
+template<int NTE, int NTO>
+__device__ __forceinline__ void FoldedMoments(double (&acc)[MT][NTE + NTO][2], SinusoidFitParams const &p,
+		size_t row0, uint8_t const *wmask, double const *B, int ldb, PairPipe &pp, int warp, int lane) {
+	constexpr int NTC = NTE + NTO;
 	int const r8 = lane >> 2;
 	int const c4 = lane & 3;
 	int const n = p.n;
+	int const half = n / 2;
 	int const mt0 = MT * (warp % (4 / MT));
 	unsigned const tile_bytes = 16u * static_cast<unsigned>(ldb) * sizeof(double);
 	float const *yrow[MT];
 	uint8_t const *mrow[MT];
-	bool live[MT];
 #pragma unroll
 	for (int mt = 0; mt < MT; ++mt) {
 		size_t row = row0 + 8 * (mt0 + mt) + r8;
-		live[mt] = row < p.num_spectra;
-		row = live[mt] ? row : p.num_spectra - 1;
+		row = row < p.num_spectra ? row : p.num_spectra - 1; // (its working mask is all false)
 		yrow[mt] = p.data + row * p.data_stride;
-		mrow[mt] = NORMALIZE ? p.mask + row * p.mask_stride
-				: wmask + static_cast<size_t>(8 * (mt0 + mt) + r8) * n;
+		mrow[mt] = wmask + static_cast<size_t>(8 * (mt0 + mt) + r8) * n;
 	}
 	unsigned use = pp.it;
 	int const first = (warp / (4 / MT)) * 16;
-	unsigned mw_next[MT];
-	float4 yv_next[MT];
-	if (first < n) {
-		PipeIssue(pp, use, B + static_cast<size_t>(first) * ldb, tile_bytes, lane);
+	unsigned mw_next[MT], mr_next[MT];
+	float4 yv_next[MT], yr_next[MT];
+	auto load = [&](int c0) {
+		int const ch = c0 + 4 * c4;
 #pragma unroll
 		for (int mt = 0; mt < MT; ++mt) {
-			mw_next[mt] = *reinterpret_cast<unsigned const *>(mrow[mt] + first + 4 * c4);
-			if (WITH_Y) {
-				yv_next[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + first + 4 * c4);
-			}
+			mw_next[mt] = *reinterpret_cast<unsigned const *>(mrow[mt] + ch);
+			yv_next[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + ch);
+			mr_next[mt] = *reinterpret_cast<unsigned const *>(mrow[mt] + n - 4 - ch); // channels n-1-ch-3 .. n-1-ch
+			yr_next[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + n - 4 - ch);
 		}
+	};
+	if (first < half) {
+		PipeIssue(pp, use, B + static_cast<size_t>(first) * ldb, tile_bytes, lane);
+		load(first);
 	}
-	for (int c0 = first; c0 < n; c0 += 16 * NGROUP, ++use) {
-		int const ch = c0 + 4 * c4;
-		unsigned mw[MT];
-		float4 yv[MT];
+	for (int c0 = first; c0 < half; c0 += 16 * NGROUP, ++use) {
+		unsigned mw[MT], mr[MT];
+		float4 yv[MT], yr[MT];
 #pragma unroll
 		for (int mt = 0; mt < MT; ++mt) {
 			mw[mt] = mw_next[mt];
-			if (WITH_Y) {
-				yv[mt] = yv_next[mt];
-			}
+			yv[mt] = yv_next[mt];
+			mr[mt] = mr_next[mt];
+			yr[mt] = yr_next[mt];
 		}
 		int const cn = c0 + 16 * NGROUP;
-		if (cn < n) {
+		if (cn < half) {
 			PipeIssue(pp, use + 1u, B + static_cast<size_t>(cn) * ldb, tile_bytes, lane);
-#pragma unroll
-			for (int mt = 0; mt < MT; ++mt) {
-				mw_next[mt] = *reinterpret_cast<unsigned const *>(mrow[mt] + cn + 4 * c4);
-				if (WITH_Y) {
-					yv_next[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + cn + 4 * c4);
-				}
-			}
-		}
-		if (NORMALIZE) {
-#pragma unroll
-			for (int mt = 0; mt < MT; ++mt) {
-				mw[mt] = live[mt] ? (__vcmpne4(mw[mt], 0u) & 0x01010101u) : 0u;
-				*reinterpret_cast<unsigned *>(wmask + static_cast<size_t>(8 * (mt0 + mt) + r8) * n + ch) = mw[mt];
-			}
+			load(cn);
 		}
 		double const *brow = PipeWait(pp, use) + 4 * c4 * ldb + r8;
 #pragma unroll
@@ -256,22 +251,25 @@ __device__ __forceinline__ void MaskedContract(double (&acc)[MT][NTC][2], Sinuso
 			for (int nt = 0; nt < NTC; ++nt) {
 				b[nt] = brow[s * ldb + 8 * nt];
 			}
-			double a[MT];
+			double ae[MT], ao[MT];
 #pragma unroll
 			for (int mt = 0; mt < MT; ++mt) {
-				bool const m = ((mw[mt] >> (8 * s)) & 0xffu) != 0u;
-				if (WITH_Y) {
-					float const y = s == 0 ? yv[mt].x : (s == 1 ? yv[mt].y : (s == 2 ? yv[mt].z : yv[mt].w));
-					a[mt] = static_cast<double>(__int_as_float(m ? __float_as_int(y) : 0));
-				} else {
-					a[mt] = m ? 1.0 : 0.0;
-				}
+				// channel ch + s and its mirror image n-1-ch-s = element 3 - s of the mirror side's float4
+				bool const mf = ((mw[mt] >> (8 * s)) & 0xffu) != 0u;
+				bool const mm = ((mr[mt] >> (8 * (3 - s))) & 0xffu) != 0u;
+				float const yf = s == 0 ? yv[mt].x : (s == 1 ? yv[mt].y : (s == 2 ? yv[mt].z : yv[mt].w));
+				float const ym = s == 0 ? yr[mt].w : (s == 1 ? yr[mt].z : (s == 2 ? yr[mt].y : yr[mt].x));
+				// (selects on the bits: a NaN / Inf under the mask must not leak)
+				double const df = static_cast<double>(__int_as_float(mf ? __float_as_int(yf) : 0));
+				double const dm = static_cast<double>(__int_as_float(mm ? __float_as_int(ym) : 0));
+				ae[mt] = df + dm;
+				ao[mt] = df - dm;
 			}
 #pragma unroll
 			for (int nt = 0; nt < NTC; ++nt) {
 #pragma unroll
 				for (int mt = 0; mt < MT; ++mt) {
-					dmma(acc[mt][nt][0], acc[mt][nt][1], a[mt], b[nt]);
+					dmma(acc[mt][nt][0], acc[mt][nt][1], nt < NTE ? ae[mt] : ao[mt], b[nt]);
 				}
 			}
 		}
@@ -474,9 +472,11 @@ __device__ bool WarpSolveRow(unsigned const *gtab, double const *trig, double co
 	return WarpLdltSolve<NT8, true>(A, K, xout, lane);
 }
 
-template<int NT8>
+// NTE / NTO: 8-slot groups of the bases that are even / odd about the middle of the row (p.kc_p = 8 NTE)
+template<int NTE, int NTO>
 __global__ void __launch_bounds__(kSinThreads, kSinCtasPerSm)
 SinusoidFitKernel(SinusoidFitParams const p) {
+	constexpr int NT8 = NTE + NTO;
 	constexpr int Kp = 8 * NT8;
 	constexpr int LDC = CoefLd(Kp);
 	extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -550,7 +550,7 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 					acc[mt][nt][1] = 0.0;
 				}
 			}
-			MaskedContract<NT8, true, false>(acc, p, row0, wmask, p.table_p, Kp + 1, pp, warp, lane);
+			FoldedMoments<NTE, NTO>(acc, p, row0, wmask, p.table_p, Kp + 1, pp, warp, lane);
 			ReducePartials<NT8>(acc, s, s.bvec, Kp, 0, warp, lane, tid);
 		}
 
@@ -621,38 +621,48 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 				unsigned use = pp.it;
 				float4 yv_next[MT];
 				unsigned mw_next[MT];
-				if (first < n) {
-					PipeIssue(pp, use, p.table_a + static_cast<size_t>(first) * LDA, tile_bytes, lane);
+				// Half of the row: the even slots give E[i], the odd slots O[i]; model[i] = E + O,
+				// model[n-1-i] = E - O (see FoldedMoments). The lane's four channels ch .. ch + 3 have their
+				// mirror images in the float4 at n - 4 - ch, in reverse order.
+				int const half = n / 2;
+				float4 yr_next[MT];
+				unsigned mr_next[MT];
+				auto load = [&](int c0) {
 #pragma unroll
 					for (int mt = 0; mt < MT; ++mt) {
-						yv_next[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + first + 4 * c4);
-						mw_next[mt] = *reinterpret_cast<unsigned const *>(wmask
-								+ static_cast<size_t>(8 * (mt0 + mt) + r8) * n + first + 4 * c4);
+						uint8_t const *wm = wmask + static_cast<size_t>(8 * (mt0 + mt) + r8) * n;
+						yv_next[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + c0 + 4 * c4);
+						mw_next[mt] = *reinterpret_cast<unsigned const *>(wm + c0 + 4 * c4);
+						yr_next[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + n - 4 - (c0 + 4 * c4));
+						mr_next[mt] = *reinterpret_cast<unsigned const *>(wm + n - 4 - (c0 + 4 * c4));
 					}
+				};
+				if (first < half) {
+					PipeIssue(pp, use, p.table_a + static_cast<size_t>(first) * LDA, tile_bytes, lane);
+					load(first);
 				}
-				for (int c0 = first; c0 < n; c0 += 16 * NGROUP, ++use) {
+				for (int c0 = first; c0 < half; c0 += 16 * NGROUP, ++use) {
 					int const ch = c0 + 4 * c4;
-					float4 yv[MT];
-					unsigned mw[MT];
+					int const chm = n - 4 - ch;
+					float4 yv[MT], yr[MT];
+					unsigned mw[MT], mr[MT];
 #pragma unroll
 					for (int mt = 0; mt < MT; ++mt) {
 						yv[mt] = yv_next[mt];
 						mw[mt] = mw_next[mt];
+						yr[mt] = yr_next[mt];
+						mr[mt] = mr_next[mt];
 					}
 					int const cn = c0 + 16 * NGROUP;
-					if (cn < n) {
+					if (cn < half) {
 						PipeIssue(pp, use + 1u, p.table_a + static_cast<size_t>(cn) * LDA, tile_bytes, lane);
-#pragma unroll
-						for (int mt = 0; mt < MT; ++mt) {
-							yv_next[mt] = *reinterpret_cast<float4 const *>(yrow[mt] + cn + 4 * c4);
-							mw_next[mt] = *reinterpret_cast<unsigned const *>(wmask
-									+ static_cast<size_t>(8 * (mt0 + mt) + r8) * n + cn + 4 * c4);
-						}
+						load(cn);
 					}
-					double c[MT][2][2];
+					double ce[MT][2][2], co[MT][2][2];
 #pragma unroll
 					for (int mt = 0; mt < MT; ++mt) {
-						c[mt][0][0] = c[mt][0][1] = c[mt][1][0] = c[mt][1][1] = 0.0;
+						ce[mt][0][0] = ce[mt][0][1] = ce[mt][1][0] = ce[mt][1][1] = 0.0;
+						co[mt][0][0] = co[mt][0][1] = co[mt][1][0] = co[mt][1][1] = 0.0;
 					}
 					double const *tb = PipeWait(pp, use) + brow * LDA + c4;
 #pragma unroll
@@ -662,33 +672,52 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 #pragma unroll
 						for (int mt = 0; mt < MT; ++mt) {
 							double const a = s.coef[(8 * (mt0 + mt) + r8) * LDC + ks + c4];
-							dmma(c[mt][0][0], c[mt][0][1], a, b0);
-							dmma(c[mt][1][0], c[mt][1][1], a, b1);
+							if (ks < 8 * NTE) {
+								dmma(ce[mt][0][0], ce[mt][0][1], a, b0);
+								dmma(ce[mt][1][0], ce[mt][1][1], a, b1);
+							} else {
+								dmma(co[mt][0][0], co[mt][0][1], a, b0);
+								dmma(co[mt][1][0], co[mt][1][1], a, b1);
+							}
 						}
 					}
 					PipeRelease(pp, use, lane);
 #pragma unroll
 					for (int mt = 0; mt < MT; ++mt) {
 						if (act[mt]) {
-							float4 md, rd;
-							md.x = static_cast<float>(c[mt][0][0]);
-							md.y = static_cast<float>(c[mt][1][0]);
-							md.z = static_cast<float>(c[mt][0][1]);
-							md.w = static_cast<float>(c[mt][1][1]);
+							// forward side: channels ch .. ch + 3; mirror side: chm .. chm + 3 = images of ch + 3 .. ch
+							double const e4[4] = { ce[mt][0][0], ce[mt][1][0], ce[mt][0][1], ce[mt][1][1] };
+							double const o4[4] = { co[mt][0][0], co[mt][1][0], co[mt][0][1], co[mt][1][1] };
+							float4 md, rd, mdm, rdm;
+							md.x = static_cast<float>(e4[0] + o4[0]);
+							md.y = static_cast<float>(e4[1] + o4[1]);
+							md.z = static_cast<float>(e4[2] + o4[2]);
+							md.w = static_cast<float>(e4[3] + o4[3]);
+							mdm.x = static_cast<float>(e4[3] - o4[3]);
+							mdm.y = static_cast<float>(e4[2] - o4[2]);
+							mdm.z = static_cast<float>(e4[1] - o4[1]);
+							mdm.w = static_cast<float>(e4[0] - o4[0]);
 							rd.x = __fsub_rn(yv[mt].x, md.x);
 							rd.y = __fsub_rn(yv[mt].y, md.y);
 							rd.z = __fsub_rn(yv[mt].z, md.z);
 							rd.w = __fsub_rn(yv[mt].w, md.w);
+							rdm.x = __fsub_rn(yr[mt].x, mdm.x);
+							rdm.y = __fsub_rn(yr[mt].y, mdm.y);
+							rdm.z = __fsub_rn(yr[mt].z, mdm.z);
+							rdm.w = __fsub_rn(yr[mt].w, mdm.w);
 							if (res_row[mt] != nullptr) {
 								*reinterpret_cast<float4 *>(res_row[mt] + ch) = rd;
+								*reinterpret_cast<float4 *>(res_row[mt] + chm) = rdm;
 							}
 							if (best_row[mt] != nullptr) {
 								*reinterpret_cast<float4 *>(best_row[mt] + ch) = md;
+								*reinterpret_cast<float4 *>(best_row[mt] + chm) = mdm;
 							}
-							float const rv[4] = { rd.x, rd.y, rd.z, rd.w };
+							float const rv[8] = { rd.x, rd.y, rd.z, rd.w, rdm.x, rdm.y, rdm.z, rdm.w };
 #pragma unroll
-							for (int q = 0; q < 4; ++q) {
-								bool const m = ((mw[mt] >> (8 * q)) & 0xffu) != 0u;
+							for (int q = 0; q < 8; ++q) {
+								unsigned const word = q < 4 ? mw[mt] : mr[mt];
+								bool const m = ((word >> (8 * (q & 3))) & 0xffu) != 0u;
 								double const v = static_cast<double>(__int_as_float(m ? __float_as_int(rv[q]) : 0));
 								cnt[mt] += m ? 1 : 0;
 								sum[mt] += v;
@@ -936,8 +965,10 @@ SinusoidFitKernel(SinusoidFitParams const p) {
 						reinterpret_cast<float4 const *>(wbest + static_cast<size_t>(r) * n), n / 4, lane);
 			}
 			if (p.coeff != nullptr) {
-				for (int k = lane; k < K; k += 32) {
-					p.coeff[row * K + k] = s.coef[r * LDC + k]; // no rescale for sinusoids
+				for (int k = lane; k < Kp; k += 32) {
+					if (p.out_pos[k] >= 0) { // slot -> position in the caller's order; no rescale for sinusoids
+						p.coeff[row * K + p.out_pos[k]] = s.coef[r * LDC + k];
+					}
 				}
 			}
 			if (lane == 0) {
@@ -970,7 +1001,8 @@ __global__ void GatherTableKernel(double const *ctx_table, int nb_ctx, int n, in
 			i = (e - np) / lda;
 			k = static_cast<int>((e - np) - i * lda);
 		}
-		tables[e] = (k < K) ? ctx_table[i * nb_ctx + use_idx[k]] : 0.0;
+		// (slot k of the fit: a column of the context table, or padding)
+		tables[e] = (k < Kp && use_idx[k] >= 0) ? ctx_table[i * nb_ctx + use_idx[k]] : 0.0;
 	}
 }
 
@@ -1027,47 +1059,56 @@ cudaError_t LaunchGatherTable(double const *ctx_table, int nb_ctx, int n, int K,
 	return cudaGetLastError();
 }
 
-template<int NT8>
+template<int NTE, int NTO>
 static cudaError_t LaunchNT(SinusoidFitParams const &p, int grid, cudaStream_t stream) {
 	size_t const smem = SinusoidSharedBytes(p.Kp, p.next);
-	cudaError_t err = cudaFuncSetAttribute(SinusoidFitKernel<NT8>,
+	cudaError_t err = cudaFuncSetAttribute(SinusoidFitKernel<NTE, NTO>,
 			cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
 	if (err != cudaSuccess) {
 		return err;
 	}
 	// two CTAs per SM need (almost) all of the SM's shared memory: ask for the largest carve-out
-	err = cudaFuncSetAttribute(SinusoidFitKernel<NT8>, cudaFuncAttributePreferredSharedMemoryCarveout,
+	err = cudaFuncSetAttribute(SinusoidFitKernel<NTE, NTO>, cudaFuncAttributePreferredSharedMemoryCarveout,
 			static_cast<int>(cudaSharedmemCarveoutMaxShared));
 	if (err != cudaSuccess) {
 		return err;
 	}
 	if (getenv("SAKURA_B200_DEBUG_OCCUPANCY") != nullptr) {
 		int blocks = 0;
-		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, SinusoidFitKernel<NT8>, kSinThreads, smem);
-		fprintf(stderr, "sakura_b200: SinusoidFitKernel<%d> smem %zu B, resident CTAs per SM %d\n", NT8, smem, blocks);
+		cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, SinusoidFitKernel<NTE, NTO>, kSinThreads, smem);
+		fprintf(stderr, "sakura_b200: SinusoidFitKernel<%d, %d> smem %zu B, resident CTAs per SM %d\n", NTE, NTO, smem,
+				blocks);
 	}
-	SinusoidFitKernel<NT8><<<grid, kSinThreads, smem, stream>>>(p);
+	SinusoidFitKernel<NTE, NTO><<<grid, kSinThreads, smem, stream>>>(p);
 	return cudaGetLastError();
+}
+
+// The bases of a sinusoid (1, sin w, cos w ...) or Chebyshev fit are balanced between even and odd: these are
+// the group counts that occur (the constant alone: no odd group).
+bool SinusoidLayoutSupported(int kc_p, int Kp) {
+	int const nte = kc_p / 8, nto = (Kp - kc_p) / 8;
+	return kc_p % 8 == 0 && Kp % 8 == 0 && Kp <= kSinMaxKp && nte >= 1 && nte <= 3
+			&& (nto == nte || nto == nte - 1);
 }
 
 cudaError_t LaunchSinusoidFit(SinusoidFitParams const &p, int grid, cudaStream_t stream) {
 	if (p.ext_ld != SinusoidExtLd(p.next) || p.ext_ld > 96 || p.ld_p != p.Kp + 1
-			|| p.ld_a != LdA(p.Kp) || p.n % 16 != 0) {
+			|| p.ld_a != LdA(p.Kp) || p.n % 32 != 0 || !SinusoidLayoutSupported(p.kc_p, p.Kp)) {
 		return cudaErrorInvalidValue;
 	}
-	switch (p.Kp / 8) {
-	case 1:
-		return LaunchNT<1>(p, grid, stream);
-	case 2:
-		return LaunchNT<2>(p, grid, stream);
-	case 3:
-		return LaunchNT<3>(p, grid, stream);
-	case 4:
-		return LaunchNT<4>(p, grid, stream);
-	case 5:
-		return LaunchNT<5>(p, grid, stream);
-	case 6:
-		return LaunchNT<6>(p, grid, stream);
+	switch (10 * (p.kc_p / 8) + (p.Kp - p.kc_p) / 8) {
+	case 10:
+		return LaunchNT<1, 0>(p, grid, stream);
+	case 11:
+		return LaunchNT<1, 1>(p, grid, stream);
+	case 21:
+		return LaunchNT<2, 1>(p, grid, stream);
+	case 22:
+		return LaunchNT<2, 2>(p, grid, stream);
+	case 32:
+		return LaunchNT<3, 2>(p, grid, stream);
+	case 33:
+		return LaunchNT<3, 3>(p, grid, stream);
 	default:
 		return cudaErrorInvalidValue;
 	}

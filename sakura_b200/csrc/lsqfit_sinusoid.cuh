@@ -17,7 +17,8 @@ struct SinusoidFitParams {
 	size_t num_spectra;
 	int n; // channels (multiple of 8)
 	int K; // fitted bases
-	int Kp; // K rounded up to a multiple of 8
+	int Kp; // slots of the fit, a multiple of 8: [even bases | padding | odd bases | padding]
+	int kc_p; // slots of the even group (a multiple of 8)
 	int next; // columns of the extended trigonometric table: 2*mmax + 1
 	int cos_only; // extended table holds only C_m (column m): Chebyshev bases T_m = cos(m t)
 	// Selected basis columns (zero padded to Kp), built per call, in two row strides so that tiles
@@ -35,9 +36,11 @@ struct SinusoidFitParams {
 	// [ceil(n / kSinSumStep) + 1][ext_ld]: column sums of the extended table over blocks of kSinSumStep
 	// channels, last row = over all channels
 	double const *ext_sums;
-	// basis k is: kind[k] = 0 constant, 1 sin, 2 cos; wave[k] its wave number
+	// slot s holds: kind[s] = 0 constant, 1 sin, 2 cos, -1 padding; wave[s] its wave number; out_pos[s] the
+	// position of its coefficient in the caller's array (-1 padding)
 	int8_t kind[kSinMaxKp];
 	int16_t wave[kSinMaxKp];
+	int8_t out_pos[kSinMaxKp];
 	float const *data;
 	size_t data_stride;
 	uint8_t const *mask;
@@ -77,6 +80,9 @@ size_t SinusoidGramEntries(int Kp);
  *  table of `p` (kind / wave / K / cos_only / next must be set) behind them. */
 cudaError_t LaunchGatherTable(double const *ctx_table, int nb_ctx, int n, int K, int Kp,
 		int16_t const *use_idx_dev, double *tables, SinusoidFitParams const &p, cudaStream_t stream);
+
+/** True when the kernel is instantiated for this split of the slots into an even and an odd group. */
+bool SinusoidLayoutSupported(int kc_p, int Kp);
 
 cudaError_t LaunchSinusoidFit(SinusoidFitParams const &p, int grid, cudaStream_t stream);
 
