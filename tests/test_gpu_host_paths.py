@@ -196,3 +196,29 @@ def test_multi_device_argument_rules(lib):
     h = lib.lsqfit_polynomial_batch(ctx, 3, data[:1], mask[:1], 3.0, 2)
     assert_bitwise(g, h)
     lib.destroy_context(ctx)
+
+
+@pytest.mark.parametrize("packed", ["1", "0"])
+def test_pipeline_in_place_outputs(lib, packed, monkeypatch):
+    """residual in place of data and final_mask in place of mask (the reference allows both, sakura.h:1755-1766)
+    through the chunked pipeline: a chunk's results come back while later chunks are still being read from the
+    same arrays (and, with bit-packed masks, while worker threads pack / expand other rows of them)."""
+    monkeypatch.setenv("SAKURA_B200_PACK_MASKS", packed)
+    rows, n = 1500, 4096
+    data, mask = rows_with_failures(rows, n, 6, seed=4242)
+    a, _ = run(lib, "poly", "serial", data, mask)
+    d2, m2 = aligned_copy(data), aligned_copy(mask)
+    st, ctx = lib.create_polynomial_context(5, n)
+    assert st == STATUS_OK
+    with Tuning(lib, "pipeline"):
+        out = {"residual": d2, "final_mask": m2}
+        b = lib.lsqfit_polynomial_batch(ctx, 5, d2, m2, 3.0, 4, out=out)
+    lib.destroy_context(ctx)
+    assert b["call_status"] == STATUS_OK
+    assert np.array_equal(a["status"], b["status"])
+    ok = a["status"] == STATUS_OK
+    assert np.array_equal(a["residual"][ok].view(np.uint32), d2[ok].view(np.uint32))
+    assert np.array_equal(a["final_mask"][ok], m2[ok])
+    # failing rows: data untouched; the mask only where the reference writes final_mask for them
+    bad = a["lsqfit_status"] == LSQFIT_NOT_ENOUGH_DATA
+    assert np.array_equal(d2[bad].view(np.uint32), data[bad].view(np.uint32))
