@@ -3,6 +3,7 @@
 #include "host_bits.h"
 
 #include <immintrin.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -77,6 +78,15 @@ public:
 	Pool() {
 		unsigned hw = std::thread::hardware_concurrency();
 		unsigned want = hw >= 16 ? 6 : (hw >= 8 ? 3 : (hw >= 4 ? 1 : 0));
+		// SAKURA_B200_HOST_THREADS = 0 .. 64: worker threads of the mask codec (0: the calling threads do it
+		// themselves), for hosts whose callers bring their own thread pools
+		if (char const *e = getenv("SAKURA_B200_HOST_THREADS")) {
+			char *end = nullptr;
+			long const v = strtol(e, &end, 10);
+			if (end != e && v >= 0 && v <= 64) {
+				want = static_cast<unsigned>(v);
+			}
+		}
 		for (unsigned i = 0; i < want; ++i) {
 			workers_.emplace_back([this] { Work(); });
 		}
